@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract of this repository.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one buffer of every track: b200conv_process on inputs
+already resident in HBM (`value`), and the same through the C-ABI with HOST buffers, host<->device
+copies inside the timed region (`e2e`).  Workloads (BASELINE.json configs):
+    c2 (default): direct FIR, 128 tracks x 512-sample buffers x 16384-tap IR per GPU  [configs[1]]
+    c3          : UPOLS,     1024 tracks x 256-sample blocks  x 65536-tap IR per GPU  [configs[2]]
+    c4          : UPOLS,      512 tracks x 512-sample buffers x 96000-tap IR per GPU  [configs[3] / 8]
+Tracks shard across ranks (weak scaling: the per-GPU track count is fixed, IRs and mix gains use
+the global track index); the only collective is the NCCL all-reduce of the stereo mix bus [2][B].
+The default line also carries the c3 and c4 results under "also" so one run shows both engines.
+
+Timing: W warm-up steps, then K timed steps, each bracketed by CUDA events on the launch stream,
+with an L2 flush (write of a 256 MiB buffer) between steps outside the brackets; the whole timed
+region is bracketed by barrier + torch.cuda.synchronize(); per-rank totals are max-reduced.
+`--impl reference` times the reference's own CPU implementation (oracle/_ref when built, else the
+oracle port) on the host cores for the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 48000
+WORKLOADS = {
+    # name: (algo, tracks per GPU, B, L, layout, BASELINE config label)
+    "c2": ("direct", 128, 512, 16384, "track_major", "bench_conv1d direct FIR: 128 tracks x 512-sample buffers x 16k-tap IR per GPU"),
+    "c3": ("upols", 1024, 256, 65536, "sample_major", "bench_conv1d_accel partitioned FFT convolution: 1024 tracks x 256-sample blocks x 64k-tap IR per GPU"),
+    "c4": ("upols", 512, 512, 96000, "track_major", "4096 tracks x 96k-tap IR over 8 GPUs: 512 tracks per GPU, 512-sample buffers, stereo mix-bus reduce"),
+}
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    except Exception:
+        return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Polls NVML during the timed region: SM clock, max SM clock, active throttle reasons."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.02):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.period, self._stop, self.max_mhz, self.ok = period, threading.Event(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as exc:  # NVML missing: report that rather than invent clocks
+            self.err = str(exc)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.ok:
+            self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self.ok:
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+def pct(sorted_vals, q):
+    return float(sorted_vals[min(len(sorted_vals) - 1, int(len(sorted_vals) * q))])  # nearest-rank, globals.cu:86-88
+
+
+# =================================================================================================
+# our arm
+# =================================================================================================
+def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
+    import torch
+
+    import gpuaudiobench_b200 as g
+    from gpuaudiobench_b200 import synth
+    from gpuaudiobench_b200.distributed import reduce_mix_bus
+
+    algo_name, T, B, L, layout_name, label = WORKLOADS[name]
+    algo = g.ALGO_DIRECT if algo_name == "direct" else g.ALGO_UPOLS
+    layout = g.OUT_SAMPLE_MAJOR if layout_name == "sample_major" else g.OUT_TRACK_MAJOR
+    Tg, t0 = T * world, T * rank
+    K, W = args.steps, args.warmup
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream(dev)
+
+    # --- synthetic job: reference-shaped IRs (global track index) and input stream -------------
+    ir = synth.make_ir(Tg, L, t0, t0 + T)
+    NB = 8  # distinct input buffers cycled through, resident in HBM
+    x_host = synth.make_input(NB * T * B, seed=42 + rank).reshape(NB, T, B)
+    eng = g.ConvEngine(T, B, L, algo, layout, device=local_rank, track_offset=t0, total_tracks=Tg)
+    eng.load_ir(ir)
+    del ir
+    d_x = torch.from_numpy(x_host).to(dev)
+    out_shape = (B, Tg) if layout == g.OUT_SAMPLE_MAJOR else (T, B)
+    d_y = torch.zeros(out_shape, device=dev)
+    d_mix = torch.zeros(2, B, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(k):
+        eng.process(d_x[k % NB].data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
+        if world > 1:
+            reduce_mix_bus(d_mix)
+
+    # warm-up: also fills the history / delay line with signal
+    fill = max(W, min((L + B - 1) // B + 2, 400))
+    for k in range(fill):
+        step(k)
+    torch.cuda.synchronize(dev)
+
+    # --- timed region: K steps, per-step events, L2 flushed between steps ----------------------
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches_before = eng.query()["kernel_launches"]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    with ClockSampler(local_rank) as clocks:
+        wall0 = time.perf_counter()
+        for k in range(K):
+            flush.fill_(k & 0xFF)
+            ev0[k].record(stream)
+            step(k)
+            ev1[k].record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - wall0
+    lat = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)], dtype=np.float64)  # ms
+    launches = eng.query()["kernel_launches"] - launches_before
+    total_ms = float(lat.sum())
+    if world > 1:
+        tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        total_ms = float(tmax.item())
+        lat_t = torch.from_numpy(lat).to(dev)
+        dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)  # a buffer is done when the slowest rank is done
+        lat = lat_t.cpu().numpy()
+    ms_per_step = total_ms / K
+    macs_per_step = float(Tg) * B * L
+    value = macs_per_step / (ms_per_step * 1e-3) / 1e9
+    s = np.sort(lat)
+    deadline_ms = 1000.0 * B / FS
+
+    # --- roofline of the dominant kernel: per-kernel CUDA events on the launch stream ----------
+    eng.set_profiling(True)
+    KP = min(K, 100)
+    for k in range(KP):
+        flush.fill_(k & 0xFF)
+        eng.process(d_x[k % NB].data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    q = eng.query()
+    eng.set_profiling(False)
+    dom = q["dominant_stage"]
+    stage_ms = [m / max(1, q["stage_calls"]) for m in q["stage_ms"][:q["stage_count"]]]
+    dom_ms = stage_ms[dom]
+    peaks, peak_src = measured_peaks()
+    if algo == g.ALGO_DIRECT:
+        fp32_peak, _ = g.measure_fp32_peak(local_rank)
+        achieved = q["flops_per_block"] / (dom_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32_fma", "kernel": q["stage_name"][dom], "achieved": achieved, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                    "peak_source": "FFMA microbenchmark measured in this run (b200conv_measure_fp32_peak); "
+                                   "MEASURED_PEAKS.json has no CUDA-core figure; nominal 74.4 TFLOP/s at 1965 MHz",
+                    "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
+                    "algorithmic_flops_per_launch": q["flops_per_block"]}
+    else:
+        achieved = q["alg_bytes_per_block"] / (dom_ms * 1e-3) / 1e9
+        peak = float(peaks["hbm_gbs"])
+        roofline = {"bound": "hbm", "kernel": q["stage_name"][dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": f"hbm_gbs of {peak_src} (measured copy)",
+                    "algorithmic_bytes_per_launch": q["alg_bytes_per_block"]}
+    roofline["kernel_ms"] = dom_ms
+    roofline["stage_ms"] = dict(zip(q["stage_name"][:q["stage_count"]], stage_ms))
+    roofline["kernel_share_of_step"] = dom_ms / sum(stage_ms)
+
+    # --- e2e: the same steps through the C ABI with HOST buffers (pinned), copies timed ---------
+    h_in = torch.from_numpy(x_host).pin_memory()
+    h_out = torch.zeros(out_shape).pin_memory()
+    h_mix = torch.zeros(2, B).pin_memory()
+    d_in2 = torch.zeros(T, B, device=dev)
+
+    def e2e_step(k):
+        if world == 1:
+            eng.process_host_ptr(h_in[k % NB].data_ptr(), h_out.data_ptr(), h_mix.data_ptr())
+        else:  # identical sequence, with the NCCL bus reduce between the kernels and the read-back
+            d_in2.copy_(h_in[k % NB], non_blocking=True)
+            eng.process(d_in2.data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
+            reduce_mix_bus(d_mix)
+            h_out.copy_(d_y, non_blocking=True)
+            h_mix.copy_(d_mix, non_blocking=True)
+            stream.synchronize()
+
+    for k in range(max(3, min(W, 10))):
+        e2e_step(k)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e2e_lat = np.empty(K)
+    for k in range(K):
+        flush.fill_(k & 0xFF)
+        torch.cuda.synchronize(dev)
+        t_a = time.perf_counter()
+        e2e_step(k)
+        e2e_lat[k] = (time.perf_counter() - t_a) * 1e3
+    e2e_total = float(e2e_lat.sum())
+    if world > 1:
+        tmax = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_total = float(tmax.item())
+    e2e_ms = e2e_total / K
+    es = np.sort(e2e_lat)
+    out_bytes = int(np.prod(out_shape)) * 4 if layout == g.OUT_TRACK_MAJOR else T * B * 4
+    e2e = {"value": macs_per_step / (e2e_ms * 1e-3) / 1e9, "unit": "GMAC/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": world * T * B * 4, "d2h_bytes_per_step": world * (out_bytes + 2 * B * 4),
+           "p50_ms": pct(es, 0.50), "p99_ms": pct(es, 0.99), "meets_deadline": bool(pct(es, 0.99) <= deadline_ms),
+           "api": "b200conv_process_host (C ABI, pinned host buffers)" if world == 1 else
+                  "pinned H2D + b200conv_process + NCCL mix-bus all-reduce + D2H"}
+
+    result = {
+        "metric": "conv_tracks_x_ir_taps_gmac_per_s", "value": value, "unit": "GMAC/s", "n_gpus": world, "steps": K,
+        "warmup": fill, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (mt19937 seed 42 uniform(-1,1) input; Hamming-windowed-sinc IRs scaled 1/L, as the reference generates)",
+        "config": {"workload": f"{name}: {label}", "algo": algo_name, "tracks_per_gpu": T, "total_tracks": Tg, "block": B,
+                   "ir_taps": L, "fs": FS, "out_layout": layout_name, "partitions_or_splits": q["partitions"],
+                   "l2": "flushed between steps (256 MiB write outside the event brackets)",
+                   "timing": "sum of per-step CUDA-event times on the launch stream, max over ranks",
+                   "collective": "NCCL all-reduce of the stereo mix bus float[2][B]" if world > 1 else "none (1 GPU)"},
+        "rt_tracks": value * 1e9 / (L * FS),
+        "latency_ms": {"p50": pct(s, 0.50), "p95": pct(s, 0.95), "p99": pct(s, 0.99), "max": float(s[-1]),
+                       "deadline": deadline_ms, "meets_deadline": bool(pct(s, 0.99) <= deadline_ms)},
+        "wall_ms_per_step_incl_flush": wall * 1e3 / K,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "engine_device_bytes": q["device_bytes"],
+    }
+    if want_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline(name, budget_s=12.0)
+    eng.close()
+    del d_x, d_y, flush
+    torch.cuda.empty_cache()
+    return result
+
+
+# =================================================================================================
+# CPU legs: the only places bench.py touches oracle/
+# =================================================================================================
+def _cpu_lib():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle, RefLib
+    if RefLib.available():
+        try:
+            return RefLib(), "reference"
+        except OSError:
+            pass
+    return Oracle(), "port"
+
+
+def cpu_time_block(lib, algo_name, x, h, L, B, T, threads):
+    fn = lib.time_r1 if algo_name == "direct" else lib.time_r2
+    return fn(x, h, L, B, T, threads)
+
+
+def cpu_baseline(name, budget_s, threads=None):
+    """The reference's CPU path (R1 for Conv1D, R2 for Conv1D_accel) on the host cores, bounded
+    sample: full B and L, a track subset sized to the time budget, scaled linearly in T."""
+    from gpuaudiobench_b200 import synth
+    algo_name, T, B, L, _, _ = WORKLOADS[name]
+    lib, kind = _cpu_lib()
+    cores = threads or lib.hardware_threads()
+    # R2 skips the iterations its bounds test rejects, so its loop count is what matters for time
+    iters_per_track = float(B) * L
+    rate_guess = 0.5e9 * cores
+    Ts = int(max(cores, min(T, budget_s * rate_guess / iters_per_track)))
+    Ts = max(1, min(T, Ts))
+    x = synth.make_input(Ts * B)
+    h = synth.make_ir(T, L, 0, Ts)
+    secs = cpu_time_block(lib, algo_name, x, h, L, B, Ts, cores)
+    gmacs = Ts * iters_per_track / secs / 1e9
+    return {"value": gmacs, "unit": "GMAC/s", "cores": cores, "kind": kind,
+            "sample": f"{'R1 bench_conv1d.cu:188-208' if algo_name == 'direct' else 'R2 bench_conv1d_accel.cu:234-252'} "
+                      f"on {Ts} of {T} tracks at full B={B}, L={L}, {cores} threads over contiguous track ranges, "
+                      f"{secs:.2f} s; GMAC/s counts T*B*L loop iterations (time-domain equivalent)",
+            "seconds": secs, "ms_per_block_scaled_to_T": secs * 1e3 * T / Ts,
+            "rt_tracks": gmacs * 1e9 / (L * FS)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    from gpuaudiobench_b200 import synth
+    name = args.workload
+    algo_name, T, B, L, _, label = WORKLOADS[name]
+    lib, kind = _cpu_lib()
+    cores = lib.hardware_threads()
+    K, W = args.steps, max(1, min(args.warmup, 2))
+    # bounded sample: whole run (K + W steps) within ~150 s
+    iters_per_track = float(B) * L
+    per_step_budget = 150.0 / (K + W)
+    Ts = int(max(1, min(T, per_step_budget * 0.5e9 * cores / iters_per_track)))
+    x = synth.make_input(Ts * B)
+    h = synth.make_ir(T * world, L, 0, Ts)
+    for _ in range(W):
+        cpu_time_block(lib, algo_name, x, h, L, B, Ts, cores)
+    secs = [cpu_time_block(lib, algo_name, x, h, L, B, Ts, cores) for _ in range(K)]
+    mean_s = float(np.mean(secs))
+    value = Ts * iters_per_track / mean_s / 1e9
+    ms_full = mean_s * 1e3 * (T * world) / Ts
+    sample = (f"{kind}: {'R1' if algo_name == 'direct' else 'R2'} CPU loop, {Ts} of {T * world} tracks per step at full "
+              f"B={B}, L={L}, {cores} host threads; ms_per_step is scaled linearly to all tracks")
+    return {"impl": "reference", "metric": "conv_tracks_x_ir_taps_gmac_per_s", "value": value, "unit": "GMAC/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_full, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generators as our arm)",
+            "config": {"workload": f"{name}: {label}", "algo": algo_name, "tracks_per_gpu": T, "total_tracks": T * world,
+                       "block": B, "ir_taps": L, "fs": FS},
+            "cpu_baseline": {"value": value, "unit": "GMAC/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "GMAC/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "rt_tracks": value * 1e9 / (L * FS), "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads in the default line")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the convolution engine has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    result = run_workload(args.workload, args, rank, world, local_rank, dist, want_cpu_baseline=(rank == 0 and world == 1))
+    if not args.no_also and args.workload == "c2":
+        also = {}
+        for other in ("c3", "c4"):
+            sub = argparse.Namespace(**vars(args))
+            sub.steps = min(args.steps, 100)
+            r = run_workload(other, sub, rank, world, local_rank, dist, want_cpu_baseline=False)
+            also[other] = {k: r[k] for k in ("value", "unit", "ms_per_step", "rt_tracks", "latency_ms", "roofline", "e2e",
+                                             "gpu_launches", "config")}
+        result["also"] = also
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,690 @@
+// engine.cu — libb200conv.so: the C ABI of include/b200conv.h over the sm_100a kernels.
+//
+// Engine-owned device state:
+//   direct : taps  h[T][Lc*16]   (zero padded, chunk-swizzled)       — replaces the reference's
+//            ring  x[T][cap]     (input history, chunk-swizzled)        cudaArray/texture, bench_conv1d.cu:123-157
+//            part  [S][T][B]     (tap-split partial sums)
+//   UPOLS  : H[T][P][B] float2   (partition spectra, packed bins, /N) — replaces d_ir_fft,
+//            X[T][P][B] float2   (frequency-domain delay line ring)     bench_conv1d_accel.cu:175-228
+//            prev[T][B], Ypart[S][T][B] float2, twiddle tables
+#include "../../include/b200conv.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "direct_fir.cuh"
+#include "upols.cuh"
+
+using namespace b200conv;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CU_TRY(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(B200CONV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));  \
+    } while (0)
+
+bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+int ilog2(uint32_t v) {
+    int l = 0;
+    while ((1u << l) < v) ++l;
+    return l;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = std::getenv(name);
+    return (s && *s) ? std::atoi(s) : dflt;
+}
+
+struct DirectState {
+    int A = 0, CL = 0, SPS = 0, JSb = 0, S = 1, nst = 0, Lc = 0, cap = 0, nbuf = 0, xtile_blocks = 0, ntiles = 0;
+    size_t smem = 0;
+    float* h = nullptr;
+    float* ring = nullptr;
+    float* partial = nullptr;
+    int pos = 0;
+};
+
+struct UpolsState {
+    int P = 0, M = 0, logM = 0, S = 1;
+    float2* H = nullptr;
+    float2* X = nullptr;
+    float2* Ypart = nullptr;
+    float2* tw_c = nullptr;
+    float2* tw_r = nullptr;
+    float* prev = nullptr;
+};
+
+}  // namespace
+
+struct b200conv_engine {
+    b200conv_config cfg{};
+    int T = 0, B = 0, L = 0, Tg = 0, toff = 0;
+    int sm_count = 0;
+    bool ir_loaded = false;
+    uint64_t blocks = 0, launches = 0, device_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    float* d_in_stage = nullptr;
+    float* d_out_stage = nullptr;
+    float* d_mix_stage = nullptr;
+    float* d_gains = nullptr;
+    float* d_mix_scratch = nullptr;
+    DirectState dir;
+    UpolsState up;
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[4] = {0, 0, 0, 0};
+    uint32_t stage_calls = 0;
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename Tp>
+int dev_alloc(b200conv_engine* e, Tp** out, size_t count, bool zero = true) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(Tp);
+    cudaError_t err = cudaMalloc(&p, bytes);
+    if (err != cudaSuccess)
+        return fail(B200CONV_ERR_CUDA, "cudaMalloc(" + std::to_string(bytes) + " bytes): " + cudaGetErrorString(err));
+    if (zero) {
+        err = cudaMemset(p, 0, bytes);
+        if (err != cudaSuccess) return fail(B200CONV_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(err));
+    }
+    e->allocs.push_back(p);
+    e->device_bytes += bytes;
+    *out = static_cast<Tp*>(p);
+    return B200CONV_OK;
+}
+
+// Tap-split heuristic for the direct engine: minimise waves * (stages per CTA + fixed overhead).
+int pick_direct_split(int stages_total, int ctas_base, int sm_count) {
+    const int resident = 2 * sm_count;
+    const double overhead_stages = 1.5;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int S = 1; S <= std::min(stages_total, 64); ++S) {
+        const int nst = (stages_total + S - 1) / S;
+        const long long ctas = static_cast<long long>(S) * ctas_base;
+        const long long waves = (ctas + resident - 1) / resident;
+        const double cost = static_cast<double>(waves) * (nst + overhead_stages);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = S;
+        }
+    }
+    return best;
+}
+
+int plan_direct(b200conv_engine* e) {
+    DirectState& d = e->dir;
+    const int B = e->B, L = e->L;
+    if (B >= 512) {
+        if (B % 512) return fail(B200CONV_ERR_INVALID, "direct engine: block must be 32,64,128,256 or a multiple of 512");
+        d.A = 32;
+        d.ntiles = B / 512;
+    } else {
+        if (!(B == 32 || B == 64 || B == 128 || B == 256))
+            return fail(B200CONV_ERR_INVALID, "direct engine: block must be 32,64,128,256 or a multiple of 512");
+        d.A = B / 16;
+        d.ntiles = 1;
+    }
+    d.CL = 32 / d.A;
+    d.SPS = (d.A == 2) ? 2 : 4;
+    d.JSb = kFirWarps * d.CL * d.SPS;
+    const int Lc0 = (L + 15) / 16;
+    const int stages_total = (Lc0 + d.JSb - 1) / d.JSb;
+    int S = env_int("B200CONV_DIRECT_SPLIT", 0);
+    if (S <= 0) S = pick_direct_split(stages_total, d.ntiles * e->T, e->sm_count);
+    S = std::max(1, std::min(S, stages_total));
+    d.S = S;
+    d.nst = (stages_total + S - 1) / S;
+    d.Lc = d.S * d.nst * d.JSb;
+    d.xtile_blocks = d.A + d.JSb + 8;
+    const size_t stage_bytes = static_cast<size_t>(d.JSb + d.xtile_blocks) * 64;
+    const size_t red_bytes = static_cast<size_t>(kFirWarps) * d.A * 16 * sizeof(float);
+    d.nbuf = std::min({d.nst, 4, kFirMaxStages});
+    while (d.nbuf > 1 && 128 + d.nbuf * stage_bytes + red_bytes > kFirMaxSmem) --d.nbuf;
+    d.smem = 128 + d.nbuf * stage_bytes + red_bytes;
+    if (d.smem > kFirMaxSmem) return fail(B200CONV_ERR_INVALID, "direct engine: stage does not fit shared memory");
+    const long long need = static_cast<long long>(d.Lc) * 16 + B + 128;
+    const long long unit = std::lcm<long long>(B, 128);
+    d.cap = static_cast<int>((need + unit - 1) / unit * unit);
+    return B200CONV_OK;
+}
+
+int plan_upols(b200conv_engine* e) {
+    UpolsState& u = e->up;
+    const int B = e->B;
+    if (!is_pow2(B) || B < 16 || B > 8192)
+        return fail(B200CONV_ERR_INVALID, "UPOLS engine: block must be a power of two in [16, 8192]");
+    u.M = B;
+    u.logM = ilog2(B);
+    u.P = (e->L + B - 1) / B;
+    const int KT = std::max(1, (B / 2) / 256);
+    int S = env_int("B200CONV_UPOLS_SPLIT", 0);
+    if (S <= 0) {
+        const long long base = static_cast<long long>(e->T) * KT;
+        S = static_cast<int>((4LL * e->sm_count + base - 1) / base);
+    }
+    u.S = std::max(1, std::min({S, u.P, 32}));
+    return B200CONV_OK;
+}
+
+int upload_twiddles(b200conv_engine* e) {
+    UpolsState& u = e->up;
+    const int M = u.M;
+    std::vector<float2> tc(M), tr(M / 2 + 1);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int q = 0; q < M; ++q) {
+        double a = -two_pi * q / M;
+        tc[q] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+    }
+    for (int k = 0; k <= M / 2; ++k) {
+        double a = -two_pi * k / (2.0 * M);
+        tr[k] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+    }
+    int rc;
+    if ((rc = dev_alloc(e, &u.tw_c, tc.size(), false))) return rc;
+    if ((rc = dev_alloc(e, &u.tw_r, tr.size(), false))) return rc;
+    CU_TRY(cudaMemcpy(u.tw_c, tc.data(), tc.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(u.tw_r, tr.data(), tr.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return B200CONV_OK;
+}
+
+int set_default_gains(b200conv_engine* e) {
+    std::vector<float> g(static_cast<size_t>(e->T) * 2);
+    const double half_pi = 1.5707963267948966192313216916398;
+    const double scale = 1.0 / std::sqrt(static_cast<double>(e->Tg));
+    for (int t = 0; t < e->T; ++t) {
+        double theta = (e->toff + t + 0.5) / e->Tg * half_pi;
+        g[2 * t] = static_cast<float>(std::cos(theta) * scale);
+        g[2 * t + 1] = static_cast<float>(std::sin(theta) * scale);
+    }
+    CU_TRY(cudaMemcpy(e->d_gains, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return B200CONV_OK;
+}
+
+int reset_state(b200conv_engine* e) {
+    // engine streams are non-blocking: fence explicitly around the (legacy-stream) memsets
+    CU_TRY(cudaDeviceSynchronize());
+    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+        CU_TRY(cudaMemset(e->dir.ring, 0, static_cast<size_t>(e->T) * e->dir.cap * sizeof(float)));
+        e->dir.pos = 0;
+    } else {
+        CU_TRY(cudaMemset(e->up.X, 0, static_cast<size_t>(e->T) * e->up.P * e->up.M * sizeof(float2)));
+        CU_TRY(cudaMemset(e->up.prev, 0, static_cast<size_t>(e->T) * e->B * sizeof(float)));
+    }
+    CU_TRY(cudaDeviceSynchronize());
+    e->blocks = 0;
+    return B200CONV_OK;
+}
+
+struct StageTimer {
+    b200conv_engine* e;
+    cudaStream_t st;
+    int idx = 0;
+    void mark() {
+        if (e->profiling && idx < 4) cudaEventRecord(e->ev[idx++], st);
+    }
+};
+
+int finish_profile(b200conv_engine* e, int marks) {
+    if (!e->profiling) return B200CONV_OK;
+    CU_TRY(cudaEventSynchronize(e->ev[marks - 1]));
+    for (int i = 0; i + 1 < marks; ++i) {
+        float ms = 0.0f;
+        CU_TRY(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
+        e->stage_ms[i] += ms;
+    }
+    e->stage_calls += 1;
+    return B200CONV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t b200conv_abi_version(void) { return B200CONV_ABI_VERSION; }
+
+const char* b200conv_last_error(void) { return g_last_error.c_str(); }
+
+int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]) {
+    if (!cfg || !plan || sm_count <= 0) return fail(B200CONV_ERR_INVALID, "b200conv_plan: bad argument");
+    if (cfg->tracks == 0 || cfg->block == 0 || cfg->ir_len == 0)
+        return fail(B200CONV_ERR_INVALID, "b200conv_plan: tracks, block and ir_len must be > 0");
+    b200conv_engine tmp;
+    tmp.cfg = *cfg;
+    tmp.T = static_cast<int>(cfg->tracks);
+    tmp.B = static_cast<int>(cfg->block);
+    tmp.L = static_cast<int>(cfg->ir_len);
+    tmp.sm_count = sm_count;
+    std::fill(plan, plan + 16, 0);
+    if (cfg->algo == B200CONV_ALGO_DIRECT) {
+        int rc = plan_direct(&tmp);
+        if (rc) return rc;
+        const DirectState& d = tmp.dir;
+        const int32_t v[12] = {d.A, d.CL, d.SPS, d.JSb, d.S, d.nst, d.Lc, d.cap, d.nbuf, d.xtile_blocks, d.ntiles,
+                               static_cast<int32_t>(d.smem)};
+        std::copy(v, v + 12, plan);
+    } else if (cfg->algo == B200CONV_ALGO_UPOLS) {
+        int rc = plan_upols(&tmp);
+        if (rc) return rc;
+        plan[0] = tmp.up.P;
+        plan[1] = tmp.up.M;
+        plan[2] = tmp.up.logM;
+        plan[3] = tmp.up.S;
+    } else {
+        return fail(B200CONV_ERR_INVALID, "b200conv_plan: unknown algo");
+    }
+    return B200CONV_OK;
+}
+
+int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
+    if (!cfg || !out) return fail(B200CONV_ERR_INVALID, "b200conv_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != B200CONV_ABI_VERSION)
+        return fail(B200CONV_ERR_ABI, "b200conv_create: abi_version mismatch");
+    if (cfg->tracks == 0 || cfg->block == 0 || cfg->ir_len == 0)
+        return fail(B200CONV_ERR_INVALID, "b200conv_create: tracks, block and ir_len must be > 0");
+    if (cfg->algo > B200CONV_ALGO_UPOLS || cfg->out_layout > B200CONV_OUT_SAMPLE_MAJOR)
+        return fail(B200CONV_ERR_INVALID, "b200conv_create: unknown algo or layout");
+    const uint32_t Tg = cfg->total_tracks ? cfg->total_tracks : cfg->tracks;
+    if (cfg->track_offset + cfg->tracks > Tg)
+        return fail(B200CONV_ERR_INVALID, "b200conv_create: track_offset + tracks exceeds total_tracks");
+
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0)
+        return fail(B200CONV_ERR_NO_DEVICE, std::string("no CUDA device: ") +
+                                                (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0") +
+                                                " (this engine has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(B200CONV_ERR_INVALID, "b200conv_create: bad device ordinal");
+    cudaDeviceProp prop{};
+    CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(B200CONV_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                                std::to_string(prop.minor) + "; kernels are built for sm_100a only");
+    CU_TRY(cudaSetDevice(cfg->device));
+
+    auto* e = new b200conv_engine();
+    e->cfg = *cfg;
+    e->T = static_cast<int>(cfg->tracks);
+    e->B = static_cast<int>(cfg->block);
+    e->L = static_cast<int>(cfg->ir_len);
+    e->Tg = static_cast<int>(Tg);
+    e->toff = static_cast<int>(cfg->track_offset);
+    e->sm_count = prop.multiProcessorCount;
+
+    int rc = (cfg->algo == B200CONV_ALGO_DIRECT) ? plan_direct(e) : plan_upols(e);
+    auto bail = [&](int code) {
+        b200conv_destroy(e);
+        return code;
+    };
+    if (rc) return bail(rc);
+
+    const size_t tb = static_cast<size_t>(e->T) * e->B;
+    const size_t out_elems = (cfg->out_layout == B200CONV_OUT_SAMPLE_MAJOR) ? static_cast<size_t>(e->B) * e->Tg : tb;
+    if ((rc = dev_alloc(e, &e->d_in_stage, tb))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_out_stage, out_elems))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_mix_stage, static_cast<size_t>(2) * e->B))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_gains, static_cast<size_t>(2) * e->T))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_mix_scratch, mix_scratch_floats(e->T, e->B)))) return bail(rc);
+    if ((rc = set_default_gains(e))) return bail(rc);
+
+    if (cfg->algo == B200CONV_ALGO_DIRECT) {
+        DirectState& d = e->dir;
+        if ((rc = dev_alloc(e, &d.h, static_cast<size_t>(e->T) * d.Lc * 16))) return bail(rc);
+        if ((rc = dev_alloc(e, &d.ring, static_cast<size_t>(e->T) * d.cap))) return bail(rc);
+        if ((rc = dev_alloc(e, &d.partial, static_cast<size_t>(d.S) * tb))) return bail(rc);
+    } else {
+        UpolsState& u = e->up;
+        const size_t spec = static_cast<size_t>(e->T) * u.P * u.M;
+        if ((rc = dev_alloc(e, &u.H, spec))) return bail(rc);
+        if ((rc = dev_alloc(e, &u.X, spec))) return bail(rc);
+        if ((rc = dev_alloc(e, &u.Ypart, static_cast<size_t>(u.S) * e->T * u.M))) return bail(rc);
+        if ((rc = dev_alloc(e, &u.prev, tb))) return bail(rc);
+        if ((rc = upload_twiddles(e))) return bail(rc);
+    }
+    err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) return bail(fail(B200CONV_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(err)));
+    for (auto& ev : e->ev) {
+        err = cudaEventCreate(&ev);
+        if (err != cudaSuccess) return bail(fail(B200CONV_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(err)));
+    }
+    *out = e;
+    return B200CONV_OK;
+}
+
+void b200conv_destroy(b200conv_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : e->allocs) cudaFree(p);
+    for (auto& ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
+    if (!e || !host_ir) return fail(B200CONV_ERR_INVALID, "b200conv_load_ir: null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const int T = e->T, L = e->L, B = e->B;
+    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+        DirectState& d = e->dir;
+        const size_t row = static_cast<size_t>(d.Lc) * 16;
+        const int chunk = static_cast<int>(std::max<size_t>(1, (64u << 20) / (row * sizeof(float))));
+        std::vector<float> stage(static_cast<size_t>(std::min(chunk, T)) * row);
+        for (int t0 = 0; t0 < T; t0 += chunk) {
+            const int nt = std::min(chunk, T - t0);
+            std::fill(stage.begin(), stage.begin() + static_cast<size_t>(nt) * row, 0.0f);
+            for (int t = 0; t < nt; ++t) {
+                const float* src = host_ir + static_cast<size_t>(t0 + t) * L;
+                float* dst = stage.data() + static_cast<size_t>(t) * row;
+                for (int j = 0; j < L; ++j) dst[swz_float(static_cast<uint32_t>(j))] = src[j];
+            }
+            CU_TRY(cudaMemcpy(d.h + static_cast<size_t>(t0) * row, stage.data(), static_cast<size_t>(nt) * row * sizeof(float),
+                              cudaMemcpyHostToDevice));
+        }
+    } else {
+        UpolsState& u = e->up;
+        const size_t row = static_cast<size_t>(u.P) * B;  // taps zero padded to P*B
+        const int chunk = static_cast<int>(std::max<size_t>(1, (128u << 20) / (row * sizeof(float))));
+        const int nmax = std::min(chunk, T);
+        std::vector<float> stage(static_cast<size_t>(nmax) * row);
+        float* d_pad = nullptr;
+        CU_TRY(cudaMalloc(&d_pad, static_cast<size_t>(nmax) * row * sizeof(float)));
+        int rc = B200CONV_OK;
+        for (int t0 = 0; t0 < T && rc == B200CONV_OK; t0 += chunk) {
+            const int nt = std::min(chunk, T - t0);
+            for (int t = 0; t < nt; ++t) {
+                float* dst = stage.data() + static_cast<size_t>(t) * row;
+                std::memcpy(dst, host_ir + static_cast<size_t>(t0 + t) * L, static_cast<size_t>(L) * sizeof(float));
+                std::fill(dst + L, dst + row, 0.0f);
+            }
+            cudaError_t err = cudaMemcpy(d_pad, stage.data(), static_cast<size_t>(nt) * row * sizeof(float), cudaMemcpyHostToDevice);
+            if (err == cudaSuccess) {
+                RfftParams p{};
+                p.first = d_pad;
+                p.first_stride = B;
+                p.second = nullptr;
+                p.second_stride = 0;
+                p.out = u.H + static_cast<size_t>(t0) * u.P * u.M;
+                p.out_stride = u.M;
+                p.prev_out = nullptr;
+                p.count = nt * u.P;
+                p.M = u.M;
+                p.logM = u.logM;
+                p.scale = 1.0f / static_cast<float>(2 * B);
+                p.tw_c = u.tw_c;
+                p.tw_r = u.tw_r;
+                err = launch_rfft_fwd(p, nullptr);
+                e->launches += 1;
+                if (err == cudaSuccess) err = cudaDeviceSynchronize();
+            }
+            if (err != cudaSuccess) rc = fail(B200CONV_ERR_CUDA, std::string("load_ir (UPOLS spectra): ") + cudaGetErrorString(err));
+        }
+        cudaFree(d_pad);
+        if (rc) return rc;
+    }
+    e->ir_loaded = true;
+    return reset_state(e);
+}
+
+int b200conv_reset(b200conv_engine* e) {
+    if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_reset: null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    return reset_state(e);
+}
+
+int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
+    if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_prime_history: null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    int rc = reset_state(e);
+    if (rc || !host_hist || e->L < 2) return rc;
+    const int T = e->T, L = e->L, B = e->B, H = L - 1;
+    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+        // ring position pos = 0 is the next block; history occupies the last L-1 floats of the ring.
+        DirectState& d = e->dir;
+        const size_t row = d.cap;
+        const int chunk = static_cast<int>(std::max<size_t>(1, (64u << 20) / (row * sizeof(float))));
+        std::vector<float> stage(static_cast<size_t>(std::min(chunk, T)) * row);
+        for (int t0 = 0; t0 < T; t0 += chunk) {
+            const int nt = std::min(chunk, T - t0);
+            std::fill(stage.begin(), stage.begin() + static_cast<size_t>(nt) * row, 0.0f);
+            for (int t = 0; t < nt; ++t) {
+                const float* src = host_hist + static_cast<size_t>(t0 + t) * H;
+                float* dst = stage.data() + static_cast<size_t>(t) * row;
+                for (int i = 0; i < H; ++i) dst[swz_float(static_cast<uint32_t>(d.cap - H + i))] = src[i];
+            }
+            CU_TRY(cudaMemcpy(d.ring + static_cast<size_t>(t0) * row, stage.data(), static_cast<size_t>(nt) * row * sizeof(float),
+                              cudaMemcpyHostToDevice));
+        }
+    } else {
+        // Push history blocks -(P-1) .. -1 through the forward transform into ring slots P-1 .. 1.
+        UpolsState& u = e->up;
+        const size_t row = static_cast<size_t>(u.P) * B;  // samples n = -P*B .. -1
+        std::vector<float> hb(static_cast<size_t>(T) * row, 0.0f);
+        for (int t = 0; t < T; ++t)
+            std::memcpy(hb.data() + static_cast<size_t>(t) * row + (row - H), host_hist + static_cast<size_t>(t) * H,
+                        static_cast<size_t>(H) * sizeof(float));
+        float* d_hb = nullptr;
+        CU_TRY(cudaMalloc(&d_hb, hb.size() * sizeof(float)));
+        cudaError_t err = cudaMemcpy(d_hb, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice);
+        for (int j = -(u.P - 1); j <= -1 && err == cudaSuccess; ++j) {
+            RfftParams p{};
+            p.first = d_hb + static_cast<size_t>(u.P + j - 1) * B;
+            p.first_stride = row;
+            p.second = d_hb + static_cast<size_t>(u.P + j) * B;
+            p.second_stride = row;
+            p.out = u.X + static_cast<size_t>(-j) * u.M;
+            p.out_stride = static_cast<size_t>(u.P) * u.M;
+            p.prev_out = nullptr;
+            p.count = T;
+            p.M = u.M;
+            p.logM = u.logM;
+            p.scale = 1.0f;
+            p.tw_c = u.tw_c;
+            p.tw_r = u.tw_r;
+            err = launch_rfft_fwd(p, nullptr);
+            e->launches += 1;
+        }
+        if (err == cudaSuccess)
+            err = cudaMemcpy2D(u.prev, static_cast<size_t>(B) * sizeof(float), d_hb + static_cast<size_t>(u.P - 1) * B,
+                               row * sizeof(float), static_cast<size_t>(B) * sizeof(float), T, cudaMemcpyDeviceToDevice);
+        if (err == cudaSuccess) err = cudaDeviceSynchronize();
+        cudaFree(d_hb);
+        if (err != cudaSuccess) return fail(B200CONV_ERR_CUDA, std::string("prime_history (UPOLS): ") + cudaGetErrorString(err));
+    }
+    return B200CONV_OK;
+}
+
+int b200conv_set_mix_gains(b200conv_engine* e, const float* host_gains) {
+    if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_set_mix_gains: null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    if (!host_gains) return set_default_gains(e);
+    CU_TRY(cudaMemcpy(e->d_gains, host_gains, static_cast<size_t>(2) * e->T * sizeof(float), cudaMemcpyHostToDevice));
+    return B200CONV_OK;
+}
+
+int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float* d_mix, uint32_t flags, void* stream) {
+    if (!e || !d_in || !d_out) return fail(B200CONV_ERR_INVALID, "b200conv_process: null argument");
+    if (!e->ir_loaded) return fail(B200CONV_ERR_STATE, "b200conv_process: call b200conv_load_ir first");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool commit = !(flags & B200CONV_PEEK);
+    const int sample_major = (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR);
+    StageTimer tm{e, st};
+    int marks = 0;
+
+    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+        DirectState& d = e->dir;
+        tm.mark();
+        CU_TRY(launch_ring_append(d_in, d.ring, e->T, e->B, d.cap, d.pos, st));
+        tm.mark();
+        FirParams p{};
+        p.h = d.h;
+        p.ring = d.ring;
+        p.partial = d.partial;
+        p.T = e->T;
+        p.B = e->B;
+        p.capb = d.cap / 16;
+        p.posb = d.pos / 16;
+        p.Lc = d.Lc;
+        p.JSb = d.JSb;
+        p.nst = d.nst;
+        p.SPS = d.SPS;
+        p.nbuf = d.nbuf;
+        p.xtile_blocks = d.xtile_blocks;
+        CU_TRY(launch_fir(p, d.A, d.S, d.ntiles, d.smem, st));
+        tm.mark();
+        CU_TRY(launch_fir_finish(d.partial, d_out, d.S, e->T, e->B, sample_major, e->Tg, e->toff, st));
+        e->launches += 3;
+        if (d_mix) {
+            CU_TRY(launch_mix(d_out, sample_major, e->Tg, e->toff, e->d_gains, e->d_mix_scratch, d_mix, e->T, e->B, st));
+            e->launches += 2;
+        }
+        tm.mark();
+        marks = tm.idx;
+        if (commit) d.pos = (d.pos + e->B) % d.cap;
+    } else {
+        UpolsState& u = e->up;
+        const int slot0 = static_cast<int>((u.P - (e->blocks % u.P)) % u.P);
+        tm.mark();
+        RfftParams f{};
+        f.first = u.prev;
+        f.first_stride = e->B;
+        f.second = d_in;
+        f.second_stride = e->B;
+        f.out = u.X + static_cast<size_t>(slot0) * u.M;
+        f.out_stride = static_cast<size_t>(u.P) * u.M;
+        f.prev_out = commit ? u.prev : nullptr;
+        f.count = e->T;
+        f.M = u.M;
+        f.logM = u.logM;
+        f.scale = 1.0f;
+        f.tw_c = u.tw_c;
+        f.tw_r = u.tw_r;
+        CU_TRY(launch_rfft_fwd(f, st));
+        tm.mark();
+        MacParams m{};
+        m.H = u.H;
+        m.X = u.X;
+        m.Ypart = u.Ypart;
+        m.T = e->T;
+        m.P = u.P;
+        m.M = u.M;
+        m.slot0 = slot0;
+        m.S = u.S;
+        CU_TRY(launch_fdl_mac(m, st));
+        tm.mark();
+        IrfftParams r{};
+        r.Ypart = u.Ypart;
+        r.S = u.S;
+        r.out = d_out;
+        r.T = e->T;
+        r.M = u.M;
+        r.logM = u.logM;
+        r.sample_major = sample_major;
+        r.Tg = e->Tg;
+        r.toff = e->toff;
+        r.tw_c = u.tw_c;
+        r.tw_r = u.tw_r;
+        CU_TRY(launch_irfft_ols(r, st));
+        e->launches += 3;
+        if (d_mix) {
+            CU_TRY(launch_mix(d_out, sample_major, e->Tg, e->toff, e->d_gains, e->d_mix_scratch, d_mix, e->T, e->B, st));
+            e->launches += 2;
+        }
+        tm.mark();
+        marks = tm.idx;
+    }
+    if (commit) e->blocks += 1;
+    return finish_profile(e, marks);
+}
+
+int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix, uint32_t flags) {
+    if (!e || !h_in) return fail(B200CONV_ERR_INVALID, "b200conv_process_host: null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = e->own_stream;
+    const size_t tb = static_cast<size_t>(e->T) * e->B;
+    CU_TRY(cudaMemcpyAsync(e->d_in_stage, h_in, tb * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = b200conv_process(e, e->d_in_stage, e->d_out_stage, h_mix ? e->d_mix_stage : nullptr, flags, st);
+    if (rc) return rc;
+    if (h_out) {
+        if (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR && e->Tg != e->T) {
+            CU_TRY(cudaMemcpy2DAsync(h_out + e->toff, static_cast<size_t>(e->Tg) * sizeof(float), e->d_out_stage + e->toff,
+                                     static_cast<size_t>(e->Tg) * sizeof(float), static_cast<size_t>(e->T) * sizeof(float),
+                                     e->B, cudaMemcpyDeviceToHost, st));
+        } else {
+            CU_TRY(cudaMemcpyAsync(h_out, e->d_out_stage, tb * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (h_mix) CU_TRY(cudaMemcpyAsync(h_mix, e->d_mix_stage, static_cast<size_t>(2) * e->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return B200CONV_OK;
+}
+
+int b200conv_query(b200conv_engine* e, b200conv_info* info) {
+    if (!e || !info) return fail(B200CONV_ERR_INVALID, "b200conv_query: null argument");
+    std::memset(info, 0, sizeof(*info));
+    const uint64_t T = e->T, B = e->B, L = e->L;
+    info->macs_per_block = T * B * L;
+    info->device_bytes = e->device_bytes;
+    info->blocks_processed = e->blocks;
+    info->kernel_launches = e->launches;
+    info->sm_count = e->sm_count;
+    info->stage_count = 3;
+    info->dominant_stage = 1;
+    info->stage_calls = e->stage_calls;
+    for (int i = 0; i < 4; ++i) info->stage_ms[i] = e->stage_ms[i];
+    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+        info->flops_per_block = 2 * T * B * L;
+        info->alg_bytes_per_block = 0;
+        info->partitions = e->dir.S;
+        info->fft_size = 0;
+        info->kernels_per_block = 3;
+        std::snprintf(info->stage_name[0], 24, "ring_append");
+        std::snprintf(info->stage_name[1], 24, "fir_direct");
+        std::snprintf(info->stage_name[2], 24, "fir_finish+mix");
+    } else {
+        const uint64_t P = e->up.P;
+        info->flops_per_block = 8 * T * P * (B + 1);
+        info->alg_bytes_per_block = T * 16 * P * (B + 1);
+        info->partitions = e->up.P;
+        info->fft_size = 2 * e->B;
+        info->kernels_per_block = 3;
+        std::snprintf(info->stage_name[0], 24, "rfft_fwd");
+        std::snprintf(info->stage_name[1], 24, "fdl_mac");
+        std::snprintf(info->stage_name[2], 24, "irfft_ols+mix");
+    }
+    return B200CONV_OK;
+}
+
+int b200conv_set_profiling(b200conv_engine* e, int on) {
+    if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_set_profiling: null engine");
+    e->profiling = (on != 0);
+    for (float& v : e->stage_ms) v = 0.0f;
+    e->stage_calls = 0;
+    return B200CONV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// upols.cu — uniformly-partitioned overlap-save convolution for sm_100a (no cuFFT).
+//
+// Replaces the reference's Conv1D_accel pipeline (cuda/bench_conv1d_accel.cu:258-304: memset,
+// T device-to-device memcpys, one whole-IR-length cufftExecR2C, ComplexMultiplyKernel :9-30,
+// cufftExecC2R, ExtractRealPartKernel :32-47 — stateless, FFT size nextpow2(L+B-1) per buffer)
+// with the streaming scheme of SURVEY.md App. E ("UPOLS engine"):
+//
+//   N = 2B, P = ceil(L/B);  H_p = RFFT_N([h[pB..pB+B) | 0]) / N        (setup, rfft_fwd_kernel)
+//   X_m = RFFT_N([x_{m-1} | x_m])  -> ring slot (-m mod P)              (rfft_fwd_kernel)
+//   Y_m[k] = sum_p H_p[k] * X_{m-p}[k]                                  (fdl_mac_kernel, HBM-bound)
+//   y_m = IRFFT_N(Y_m)[B..2B)                                           (irfft_ols_kernel)
+//
+// Spectra hold B packed bins: bin 0 carries {DC, Nyquist} (both real), so a partition is exactly
+// B*8 bytes — a whole number of 128 B lines for every supported B — and the MAC streams long
+// contiguous runs.  The real transforms are done as one complex FFT of size M = B on the
+// even/odd-packed signal (shared-memory Stockham autosort, radix 4 with one radix-2 pass when
+// log2 M is odd) plus a twiddle post-/pre-pass.  Twiddles are computed in double on the host.
+#include "upols.cuh"
+
+#include "common.cuh"
+
+namespace b200conv {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// ---------------------------------------------------------------------------------------------
+// Complex FFT of size M on shared memory (Stockham autosort, out-of-place between a and b).
+// Pass with sub-transform length Ns and radix R, butterfly j < M/R:
+//   v[r] = in[j + r*M/R] * W_M^{r * (j mod Ns) * M/(Ns*R)};  DFT_R(v);
+//   out[(j - j mod Ns)*R + (j mod Ns) + r*Ns] = v[r]
+// INV uses conjugate twiddles and the +i rotation (un-normalised inverse).
+// Every thread of the CTA must call this (it contains __syncthreads); `active` masks the work.
+// Returns the buffer that holds the result.
+// ---------------------------------------------------------------------------------------------
+template <bool INV>
+__device__ float2* fft_stockham(float2* a, float2* b, int M, int logM, const float2* __restrict__ tw, int tx,
+                                int TX, bool active) {
+    int Ns = 1;
+    if (logM & 1) {
+        if (active) {
+            const int half = M >> 1;
+            for (int j = tx; j < half; j += TX) {
+                float2 v0 = a[j], v1 = a[j + half];
+                b[2 * j] = cadd(v0, v1);
+                b[2 * j + 1] = csub(v0, v1);
+            }
+        }
+        __syncthreads();
+        float2* tmp = a; a = b; b = tmp;
+        Ns = 2;
+    }
+    const int quarter = M >> 2;
+    for (; Ns < M; Ns <<= 2) {
+        if (active) {
+            const int tstride = M / (4 * Ns);
+            for (int j = tx; j < quarter; j += TX) {
+                const int k = j & (Ns - 1);
+                float2 v0 = a[j];
+                float2 v1 = a[j + quarter];
+                float2 v2 = a[j + 2 * quarter];
+                float2 v3 = a[j + 3 * quarter];
+                if (k != 0) {
+                    float2 w1 = tw[k * tstride];
+                    float2 w2 = tw[2 * k * tstride];
+                    float2 w3 = tw[3 * k * tstride];
+                    if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+                    v1 = cmul(v1, w1);
+                    v2 = cmul(v2, w2);
+                    v3 = cmul(v3, w3);
+                }
+                float2 t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3), d = csub(v1, v3);
+                float2 t3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);  // (+/-) i * d
+                const int j0 = ((j - k) << 2) + k;
+                b[j0] = cadd(t0, t2);
+                b[j0 + Ns] = cadd(t1, t3);
+                b[j0 + 2 * Ns] = csub(t0, t2);
+                b[j0 + 3 * Ns] = csub(t1, t3);
+            }
+        }
+        __syncthreads();
+        float2* tmp = a; a = b; b = tmp;
+    }
+    return a;
+}
+
+// threads per window / windows per CTA for a 256-thread CTA
+static inline int fft_threads_per_window(int M) {
+    int tx = M / 4;
+    if (tx < 32) tx = 32;
+    if (tx > 256) tx = 256;
+    return tx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward: packed bins of RFFT_N([first | second]).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rfft_fwd_kernel(RfftParams p, int TX, int WPC) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const int M = p.M, half = M >> 1;
+    const int wl = threadIdx.x / TX, tx = threadIdx.x % TX;
+    const int w = blockIdx.x * WPC + wl;
+    const bool active = (w < p.count);
+    float2* a = fsm + static_cast<size_t>(wl) * 2 * M;
+    float2* b = a + M;
+
+    if (active) {
+        const float2* f2 = p.first ? reinterpret_cast<const float2*>(p.first + static_cast<size_t>(w) * p.first_stride) : nullptr;
+        const float2* s2 = p.second ? reinterpret_cast<const float2*>(p.second + static_cast<size_t>(w) * p.second_stride) : nullptr;
+        float2* prev2 = p.prev_out ? reinterpret_cast<float2*>(p.prev_out + static_cast<size_t>(w) * M) : nullptr;
+        for (int n = tx; n < M; n += TX) {
+            float2 v = make_float2(0.0f, 0.0f);
+            if (n < half) {
+                if (f2) v = f2[n];
+            } else {
+                if (s2) v = s2[n - half];
+                if (prev2) prev2[n - half] = v;
+            }
+            a[n] = v;
+        }
+    }
+    __syncthreads();
+    const float2* z = fft_stockham<false>(a, b, M, p.logM, p.tw_c, tx, TX, active);
+    if (!active) return;
+
+    float2* out = p.out + static_cast<size_t>(w) * p.out_stride;
+    const float sc = p.scale;
+    for (int k = tx; k <= half; k += TX) {
+        const float2 A = z[k];
+        const float2 Bc = cconj(z[(M - k) & (M - 1)]);
+        const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y + Bc.y));
+        const float2 D = make_float2(0.5f * (A.x - Bc.x), 0.5f * (A.y - Bc.y));
+        const float2 O = make_float2(D.y, -D.x);  // -i * D
+        const float2 WO = cmul(p.tw_r[k], O);
+        const float2 Xk = cadd(E, WO);
+        const float2 Xmk = make_float2(E.x - WO.x, -(E.y - WO.y));  // X[M-k] = conj(E - W O)
+        if (k == 0) {
+            out[0] = make_float2(sc * Xk.x, sc * Xmk.x);  // {DC, Nyquist}
+        } else {
+            out[k] = make_float2(sc * Xk.x, sc * Xk.y);
+            if (k != half) out[M - k] = make_float2(sc * Xmk.x, sc * Xmk.y);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FDL-MAC: the HBM-streaming kernel.  Each thread owns two bins (one float4) of one track and
+// walks the partitions of its split; H and the X ring are each read exactly once per block.
+// Per bin the four real products are accumulated separately (A = sum Hr Xr, B = sum Hi Xi,
+// C = sum Hr Xi, D = sum Hi Xr): re = A - B, im = C + D, and for packed bin 0 the pair (A, B) is
+// directly {DC, Nyquist} — no divergent special case, same FMA count as a complex MAC.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mac2(float (&acc)[8], const float4& h, const float4& x) {
+    acc[0] = fmaf(h.x, x.x, acc[0]);
+    acc[1] = fmaf(h.y, x.y, acc[1]);
+    acc[2] = fmaf(h.x, x.y, acc[2]);
+    acc[3] = fmaf(h.y, x.x, acc[3]);
+    acc[4] = fmaf(h.z, x.z, acc[4]);
+    acc[5] = fmaf(h.w, x.w, acc[5]);
+    acc[6] = fmaf(h.z, x.w, acc[6]);
+    acc[7] = fmaf(h.w, x.z, acc[7]);
+}
+
+__global__ void __launch_bounds__(256) fdl_mac_kernel(MacParams p, int U, int G) {
+    __shared__ float red[256 * 8];
+    const int t = blockIdx.z, s = blockIdx.y;
+    int u, g;
+    if (G == 1) {
+        u = blockIdx.x * 256 + threadIdx.x;
+        g = 0;
+    } else {
+        u = threadIdx.x % U;
+        g = threadIdx.x / U;
+    }
+    const int P = p.P;
+    const int p0 = static_cast<int>(static_cast<long long>(P) * s / p.S);
+    const int p1 = static_cast<int>(static_cast<long long>(P) * (s + 1) / p.S);
+    const float4* H4 = reinterpret_cast<const float4*>(p.H) + static_cast<size_t>(t) * P * U + u;
+    const float4* X4 = reinterpret_cast<const float4*>(p.X) + static_cast<size_t>(t) * P * U + u;
+
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+
+    int pp = p0 + g;
+    for (; pp + 3 * G < p1; pp += 4 * G) {
+        float4 h[4], x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = pp + j * G;
+            int sl = p.slot0 + q;
+            if (sl >= P) sl -= P;
+            h[j] = ldg_stream(H4 + static_cast<size_t>(q) * U);
+            x[j] = ldg_stream(X4 + static_cast<size_t>(sl) * U);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mac2(acc, h[j], x[j]);
+    }
+    for (; pp < p1; pp += G) {
+        int sl = p.slot0 + pp;
+        if (sl >= P) sl -= P;
+        float4 h = ldg_stream(H4 + static_cast<size_t>(pp) * U);
+        float4 x = ldg_stream(X4 + static_cast<size_t>(sl) * U);
+        mac2(acc, h, x);
+    }
+
+    if (G > 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+        __syncthreads();
+        if (g != 0) return;
+        for (int gg = 1; gg < G; ++gg) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += red[(gg * U + u) * 8 + i];
+        }
+    }
+    float4 y;
+    if (u == 0) {
+        y.x = acc[0];  // DC
+        y.y = acc[1];  // Nyquist
+    } else {
+        y.x = acc[0] - acc[1];
+        y.y = acc[2] + acc[3];
+    }
+    y.z = acc[4] - acc[5];
+    y.w = acc[6] + acc[7];
+    reinterpret_cast<float4*>(p.Ypart)[(static_cast<size_t>(s) * p.T + t) * U + u] = y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inverse + overlap-save: y = IRFFT_N(sum_s Ypart)[B..2B).  H carries the 1/N, so the inverse is
+// un-normalised and Z'[k] = (Y[k] + conj Y[M-k]) + i conj(W^k) (Y[k] - conj Y[M-k]).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, int WPC) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const int M = p.M, half = M >> 1;
+    const int wl = threadIdx.x / TX, tx = threadIdx.x % TX;
+    const int t = blockIdx.x * WPC + wl;
+    const bool active = (t < p.T);
+    float2* a = fsm + static_cast<size_t>(wl) * 2 * M;
+    float2* b = a + M;
+
+    if (active) {
+        const size_t split_stride = static_cast<size_t>(p.T) * M;
+        const float2* Y = p.Ypart + static_cast<size_t>(t) * M;
+        for (int k = tx; k <= half; k += TX) {
+            const int mk = (M - k) & (M - 1);
+            float2 yk = Y[k], ym = Y[mk];
+            for (int s = 1; s < p.S; ++s) {
+                yk = cadd(yk, Y[s * split_stride + k]);
+                ym = cadd(ym, Y[s * split_stride + mk]);
+            }
+            float2 A, Bm;
+            if (k == 0) {
+                A = make_float2(yk.x, 0.0f);   // DC
+                Bm = make_float2(yk.y, 0.0f);  // Nyquist = Y[M]
+            } else {
+                A = yk;
+                Bm = ym;
+            }
+            const float2 Bc = cconj(Bm);
+            const float2 E = cadd(A, Bc);
+            const float2 D = csub(A, Bc);
+            const float2 O = cmul(cconj(p.tw_r[k]), D);
+            a[k] = make_float2(E.x - O.y, E.y + O.x);
+            if (k != 0 && k != half) a[M - k] = make_float2(E.x + O.y, O.x - E.y);
+        }
+    }
+    __syncthreads();
+    const float2* z = fft_stockham<true>(a, b, M, p.logM, p.tw_c, tx, TX, active);
+    if (!active) return;
+
+    if (!p.sample_major) {
+        float2* out2 = reinterpret_cast<float2*>(p.out + static_cast<size_t>(t) * M);
+        for (int n = tx; n < half; n += TX) out2[n] = z[half + n];
+    } else {
+        float* col = p.out + p.toff + t;
+        for (int n = tx; n < half; n += TX) {
+            const float2 v = z[half + n];
+            col[static_cast<size_t>(2 * n) * p.Tg] = v.x;
+            col[static_cast<size_t>(2 * n + 1) * p.Tg] = v.y;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stereo mix bus, two fixed-order passes (deterministic; no atomics).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMixTrackChunk = 32;
+
+__global__ void mix_partial_kernel(const float* __restrict__ y, int sample_major, int Tg, int toff,
+                                   const float* __restrict__ gains, float* __restrict__ scratch, int T, int B) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.y;
+    if (n >= B) return;
+    const int t0 = chunk * kMixTrackChunk;
+    const int t1 = min(T, t0 + kMixTrackChunk);
+    float l = 0.0f, r = 0.0f;
+    for (int t = t0; t < t1; ++t) {
+        const float v = sample_major ? y[static_cast<size_t>(n) * Tg + toff + t] : y[static_cast<size_t>(t) * B + n];
+        l = fmaf(gains[2 * t], v, l);
+        r = fmaf(gains[2 * t + 1], v, r);
+    }
+    scratch[(static_cast<size_t>(chunk) * 2 + 0) * B + n] = l;
+    scratch[(static_cast<size_t>(chunk) * 2 + 1) * B + n] = r;
+}
+
+__global__ void mix_final_kernel(const float* __restrict__ scratch, float* __restrict__ mix, int nchunks, int B) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // c*B + n
+    if (idx >= 2 * B) return;
+    const int c = idx / B, n = idx - c * B;
+    float v = 0.0f;
+    for (int k = 0; k < nchunks; ++k) v += scratch[(static_cast<size_t>(k) * 2 + c) * B + n];
+    mix[idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Launchers
+// ---------------------------------------------------------------------------------------------
+static cudaError_t ensure_fft_smem(const void* fn, size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+}
+
+cudaError_t launch_rfft_fwd(const RfftParams& p, cudaStream_t st) {
+    const int TX = fft_threads_per_window(p.M);
+    const int WPC = 256 / TX;
+    const size_t smem = static_cast<size_t>(WPC) * 2 * p.M * sizeof(float2);
+    cudaError_t e = ensure_fft_smem(reinterpret_cast<const void*>(rfft_fwd_kernel), smem);
+    if (e != cudaSuccess) return e;
+    rfft_fwd_kernel<<<(p.count + WPC - 1) / WPC, 256, smem, st>>>(p, TX, WPC);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_irfft_ols(const IrfftParams& p, cudaStream_t st) {
+    const int TX = fft_threads_per_window(p.M);
+    const int WPC = 256 / TX;
+    const size_t smem = static_cast<size_t>(WPC) * 2 * p.M * sizeof(float2);
+    cudaError_t e = ensure_fft_smem(reinterpret_cast<const void*>(irfft_ols_kernel), smem);
+    if (e != cudaSuccess) return e;
+    irfft_ols_kernel<<<(p.T + WPC - 1) / WPC, 256, smem, st>>>(p, TX, WPC);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st) {
+    const int U = p.M / 2;
+    int G = 1, KT = 1;
+    if (U >= 256)
+        KT = U / 256;
+    else
+        G = 256 / U;
+    dim3 grid(KT, p.S, p.T);
+    fdl_mac_kernel<<<grid, 256, 0, st>>>(p, U, G);
+    return cudaGetLastError();
+}
+
+size_t mix_scratch_floats(int T, int B) {
+    const int nchunks = (T + kMixTrackChunk - 1) / kMixTrackChunk;
+    return static_cast<size_t>(nchunks) * 2 * B;
+}
+
+cudaError_t launch_mix(const float* y, int sample_major, int Tg, int toff, const float* gains, float* scratch,
+                       float* mix, int T, int B, cudaStream_t st) {
+    const int nchunks = (T + kMixTrackChunk - 1) / kMixTrackChunk;
+    dim3 grid((B + 127) / 128, nchunks);
+    mix_partial_kernel<<<grid, 128, 0, st>>>(y, sample_major, Tg, toff, gains, scratch, T, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    mix_final_kernel<<<(2 * B + 255) / 256, 256, 0, st>>>(scratch, mix, nchunks, B);
+    return cudaGetLastError();
+}
+
+}  // namespace b200conv

@@ -1,0 +1,59 @@
+// upols.cuh — launch interface of the uniformly-partitioned overlap-save kernels (upols.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace b200conv {
+
+// Forward real FFT of `count` windows of N = 2M samples each; window w is
+//   [ first[w*first_stride .. +M) | second[w*second_stride .. +M) ]   (a null pointer reads zeros)
+// and its M packed bins (bin 0 = {DC, Nyquist}) go to out[w*out_stride .. +M), scaled by `scale`.
+// When prev_out != null the second half is also copied to prev_out[w*M ..] (the engine's
+// "previous buffer" for the next call).
+struct RfftParams {
+    const float* first;
+    size_t first_stride;
+    const float* second;
+    size_t second_stride;
+    float2* out;
+    size_t out_stride;  // in float2
+    float* prev_out;
+    int count;
+    int M;      // complex FFT size = bins per partition = B
+    int logM;
+    float scale;
+    const float2* tw_c;  // e^{-2 pi i q / M},  q < M
+    const float2* tw_r;  // e^{-2 pi i k / 2M}, k <= M/2
+};
+
+// Y[s][t][k] = sum_{p in split s} H[t][p][k] * X[t][(slot0 + p) mod P][k]
+struct MacParams {
+    const float2* H;   // [T][P][M] partition spectra (packed bins, pre-scaled by 1/N)
+    const float2* X;   // [T][P][M] frequency-domain delay line (ring of packed spectra)
+    float2* Ypart;     // [S][T][M]
+    int T, P, M;
+    int slot0;         // ring slot of the newest block (p = 0)
+    int S;             // partition splits (grid.y)
+};
+
+struct IrfftParams {
+    const float2* Ypart;  // [S][T][M]
+    int S;
+    float* out;           // [T][B] or [B][Tg]
+    int T, M, logM;
+    int sample_major, Tg, toff;
+    const float2* tw_c;
+    const float2* tw_r;
+};
+
+cudaError_t launch_rfft_fwd(const RfftParams& p, cudaStream_t st);
+cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st);
+cudaError_t launch_irfft_ols(const IrfftParams& p, cudaStream_t st);
+
+// Deterministic stereo bus: mix[c][n] = sum_t gains[t][c] * y_t[n] over this engine's tracks.
+cudaError_t launch_mix(const float* y, int sample_major, int Tg, int toff, const float* gains, float* scratch,
+                       float* mix, int T, int B, cudaStream_t st);
+size_t mix_scratch_floats(int T, int B);
+
+}  // namespace b200conv

@@ -1,0 +1,193 @@
+"""ctypes binding of include/b200conv.h (libb200conv.so).
+
+This is harness code for tests and bench.py; the product is the shared library and the C++ plugin
+host under host/.  There is deliberately no fallback: if the library is missing or no B200 is
+present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libb200conv.so")
+
+ABI_VERSION = 1
+ALGO_DIRECT, ALGO_UPOLS = 0, 1
+OUT_TRACK_MAJOR, OUT_SAMPLE_MAJOR = 0, 1
+PEEK = 1
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_ABI = 0, -1, -2, -3, -4, -5
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("tracks", C.c_uint32),
+                ("track_offset", C.c_uint32), ("total_tracks", C.c_uint32), ("block", C.c_uint32),
+                ("ir_len", C.c_uint32), ("algo", C.c_uint32), ("out_layout", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class Info(C.Structure):
+    _fields_ = [("macs_per_block", C.c_uint64), ("flops_per_block", C.c_uint64), ("alg_bytes_per_block", C.c_uint64),
+                ("device_bytes", C.c_uint64), ("blocks_processed", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("partitions", C.c_uint32), ("fft_size", C.c_uint32), ("kernels_per_block", C.c_uint32),
+                ("sm_count", C.c_uint32), ("stage_count", C.c_uint32), ("dominant_stage", C.c_uint32),
+                ("stage_ms", C.c_float * 4), ("stage_calls", C.c_uint32), ("stage_name", (C.c_char * 24) * 4)]
+
+
+class B200ConvError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200conv error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """Load libb200conv.so (raises if it has not been built: there is no Python/CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built; run `python -m gpuaudiobench_b200.build` "
+                                "(the convolution engine has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.b200conv_abi_version.restype = C.c_uint32
+    L.b200conv_last_error.restype = C.c_char_p
+    L.b200conv_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.b200conv_destroy.argtypes = [C.c_void_p]
+    L.b200conv_destroy.restype = None
+    L.b200conv_load_ir.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200conv_prime_history.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200conv_reset.argtypes = [C.c_void_p]
+    L.b200conv_set_mix_gains.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200conv_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.b200conv_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.b200conv_query.argtypes = [C.c_void_p, C.POINTER(Info)]
+    L.b200conv_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.b200conv_plan.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_int32)]
+    L.b200conv_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise B200ConvError(rc, load_library().b200conv_last_error().decode(errors="replace"))
+
+
+def make_config(tracks, block, ir_len, algo, out_layout=OUT_TRACK_MAJOR, device=0, track_offset=0, total_tracks=0):
+    return Config(ABI_VERSION, device, tracks, track_offset, total_tracks, block, ir_len, algo, out_layout, 0)
+
+
+def plan(tracks, block, ir_len, algo, sm_count=148):
+    """The engine's launch plan (needs no GPU): dict of the fields documented in b200conv.h."""
+    cfg = make_config(tracks, block, ir_len, algo)
+    arr = (C.c_int32 * 16)()
+    _check(load_library().b200conv_plan(C.byref(cfg), sm_count, arr))
+    if algo == ALGO_DIRECT:
+        keys = ("A", "CL", "SPS", "JSb", "S", "nst", "Lc", "cap", "nbuf", "xtile_blocks", "ntiles", "smem")
+    else:
+        keys = ("P", "M", "logM", "S")
+    return dict(zip(keys, list(arr)))
+
+
+def measure_fp32_peak(device=0):
+    tf, ms = C.c_double(), C.c_double()
+    _check(load_library().b200conv_measure_fp32_peak(device, C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+def _host_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ConvEngine:
+    """One engine on one device.  Device buffers are passed as integer addresses (e.g.
+    torch.Tensor.data_ptr()); host buffers as C-contiguous float32 numpy arrays."""
+
+    def __init__(self, tracks, block, ir_len, algo, out_layout=OUT_TRACK_MAJOR, device=0, track_offset=0,
+                 total_tracks=0):
+        self.lib = load_library()
+        self.cfg = make_config(tracks, block, ir_len, algo, out_layout, device, track_offset, total_tracks)
+        self.T, self.B, self.L = tracks, block, ir_len
+        self.Tg = total_tracks or tracks
+        self.toff = track_offset
+        self.algo, self.out_layout = algo, out_layout
+        self.handle = C.c_void_p()
+        _check(self.lib.b200conv_create(C.byref(self.cfg), C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.b200conv_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def load_ir(self, host_ir):
+        h = np.ascontiguousarray(host_ir, dtype=np.float32)
+        assert h.size == self.T * self.L, (h.shape, self.T, self.L)
+        _check(self.lib.b200conv_load_ir(self.handle, _host_ptr(h)))
+
+    def prime_history(self, host_hist=None):
+        if host_hist is None:
+            _check(self.lib.b200conv_prime_history(self.handle, None))
+            return
+        h = np.ascontiguousarray(host_hist, dtype=np.float32)
+        assert h.size == self.T * (self.L - 1)
+        _check(self.lib.b200conv_prime_history(self.handle, _host_ptr(h)))
+
+    def reset(self):
+        _check(self.lib.b200conv_reset(self.handle))
+
+    def set_mix_gains(self, gains=None):
+        if gains is None:
+            _check(self.lib.b200conv_set_mix_gains(self.handle, None))
+            return
+        g = np.ascontiguousarray(gains, dtype=np.float32)
+        assert g.size == 2 * self.T
+        _check(self.lib.b200conv_set_mix_gains(self.handle, _host_ptr(g)))
+
+    def process(self, d_in, d_out, d_mix=None, flags=0, stream=0):
+        _check(self.lib.b200conv_process(self.handle, C.c_void_p(d_in), C.c_void_p(d_out),
+                                         C.c_void_p(d_mix) if d_mix else None, flags,
+                                         C.c_void_p(stream) if stream else None))
+
+    def process_host_ptr(self, h_in, h_out=None, h_mix=None, flags=0):
+        """Raw-address form (pinned torch tensors' data_ptr()); no per-call numpy work."""
+        _check(self.lib.b200conv_process_host(self.handle, C.c_void_p(h_in), C.c_void_p(h_out) if h_out else None,
+                                              C.c_void_p(h_mix) if h_mix else None, flags))
+
+    def out_shape(self):
+        return (self.B, self.Tg) if self.out_layout == OUT_SAMPLE_MAJOR else (self.T, self.B)
+
+    def process_host(self, x, flags=0, want_mix=False):
+        """x: [T][B] float32 numpy.  Returns (y, mix|None) as new numpy arrays."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.size == self.T * self.B
+        y = np.zeros(self.out_shape(), dtype=np.float32)
+        mix = np.zeros((2, self.B), dtype=np.float32) if want_mix else None
+        _check(self.lib.b200conv_process_host(self.handle, _host_ptr(x), _host_ptr(y),
+                                              _host_ptr(mix) if want_mix else None, flags))
+        return y, mix
+
+    def query(self):
+        info = Info()
+        _check(self.lib.b200conv_query(self.handle, C.byref(info)))
+        d = {k: getattr(info, k) for k, _ in Info._fields_ if k not in ("stage_ms", "stage_name")}
+        d["stage_ms"] = list(info.stage_ms)
+        d["stage_name"] = [bytes(info.stage_name[i]).split(b"\0")[0].decode() for i in range(4)]
+        return d
+
+    def set_profiling(self, on):
+        _check(self.lib.b200conv_set_profiling(self.handle, 1 if on else 0))

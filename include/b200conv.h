@@ -1,0 +1,163 @@
+/* b200conv.h — C ABI of the B200-native multichannel convolution engine (libb200conv.so).
+ *
+ * This is the drop-in boundary for the one hot path of tskare/gpuaudiobench that this repository
+ * replaces: per-track FIR convolution of streaming audio buffers, direct form (Conv1D) and
+ * partitioned-FFT form (Conv1D_accel).  Nothing like this ABI exists in the reference — its
+ * plugins call their kernels inline — so every entry point below names the reference code it
+ * stands in for (paths relative to the reference root).  INTEGRATION.md shows the
+ * lines a reference maintainer adds to bench_conv1d.cu / bench_conv1d_accel.cu to bind it.
+ *
+ * Conventions: extern "C", plain pointers and sizes, no exceptions; every call returns
+ * B200CONV_OK (0) or a negative b200conv_status and leaves a message for b200conv_last_error()
+ * (thread-local).  One engine per device, not thread-safe per handle.  The caller owns the I/O
+ * buffers; the engine owns IR tables, input history / frequency-domain delay line and workspace.
+ * All device work of b200conv_process is enqueued on the caller's cudaStream_t (passed as void*
+ * so the header needs no CUDA include).  There is no CPU fallback: without a CUDA device
+ * b200conv_create fails with B200CONV_ERR_NO_DEVICE.
+ *
+ * Data layouts:
+ *   input   float [T][B]  track-major                       (cuda/bench_base.cu:30-35 upload)
+ *   IR      float [T][L]  track-major                       (cuda/bench_conv1d.cu:159-178)
+ *   output  float [T][B]  track-major  (Conv1D,       cuda/bench_conv1d.cu:25,205)  or
+ *           float [B][Tg] sample-major (Conv1D_accel, cuda/bench_conv1d_accel.cu:44,249), where
+ *           Tg = total_tracks and this engine writes columns [track_offset, track_offset+T)
+ *   mix bus float [2][B]  (new: no reference counterpart)
+ * Streaming semantics: block m of track t continues the track's stream; after b200conv_reset the
+ * first block equals the reference oracle R2 (zero history); oracle R1's cross-track bleed is
+ * reproduced by b200conv_prime_history.
+ */
+#ifndef B200CONV_H_
+#define B200CONV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CONV_ABI_VERSION 1u
+
+typedef enum b200conv_status {
+    B200CONV_OK = 0,
+    B200CONV_ERR_INVALID = -1,     /* bad argument / unsupported size                       */
+    B200CONV_ERR_CUDA = -2,        /* a CUDA runtime call failed (message has the detail)    */
+    B200CONV_ERR_NO_DEVICE = -3,   /* no CUDA device, or not an sm_100 part                  */
+    B200CONV_ERR_STATE = -4,       /* call order violated (e.g. process before load_ir)      */
+    B200CONV_ERR_ABI = -5          /* cfg.abi_version != B200CONV_ABI_VERSION                */
+} b200conv_status;
+
+typedef enum b200conv_algo {
+    B200CONV_ALGO_DIRECT = 0, /* direct-form FIR      — replaces Conv1DTextureMemoryImplKernel, cuda/bench_conv1d.cu:7-27 */
+    B200CONV_ALGO_UPOLS = 1   /* partitioned overlap-save — replaces the cuFFT pipeline, cuda/bench_conv1d_accel.cu:258-304 */
+} b200conv_algo;
+
+typedef enum b200conv_layout {
+    B200CONV_OUT_TRACK_MAJOR = 0,
+    B200CONV_OUT_SAMPLE_MAJOR = 1
+} b200conv_layout;
+
+/* b200conv_process flags */
+#define B200CONV_PEEK 1u /* compute this block but do not advance the stream state: repeated calls
+                            are idempotent, which is what the reference's stateless iteration loop
+                            (cuda/bench_base.cu:89-94 re-submitting the same h_input) needs */
+
+typedef struct b200conv_config {
+    uint32_t abi_version;  /* B200CONV_ABI_VERSION */
+    int32_t device;        /* CUDA ordinal; the reference never calls cudaSetDevice (main.cu:309) */
+    uint32_t tracks;       /* T: tracks owned by this engine (NTRACKS, cuda/globals.cu:5) */
+    uint32_t track_offset; /* global index of local track 0 (multi-GPU track sharding; 0 on one GPU) */
+    uint32_t total_tracks; /* Tg: global track count; 0 means == tracks */
+    uint32_t block;        /* B: samples per buffer (BUFSIZE, cuda/globals.cu:6) */
+    uint32_t ir_len;       /* L: taps (ir_length_, cuda/bench_conv1d.cuh:11 / bench_conv1d_accel.cuh:11) */
+    uint32_t algo;         /* b200conv_algo */
+    uint32_t out_layout;   /* b200conv_layout */
+    uint32_t flags;        /* reserved, 0 */
+} b200conv_config;
+
+typedef struct b200conv_info {
+    uint64_t macs_per_block;      /* T*B*L, the time-domain-equivalent work           */
+    uint64_t flops_per_block;     /* algorithmic flops of the dominant kernel per block               */
+    uint64_t alg_bytes_per_block; /* UPOLS FDL-MAC compulsory reads: T*16*P*(B+1); direct: 0          */
+    uint64_t device_bytes;        /* engine-owned device memory                                       */
+    uint64_t blocks_processed;    /* committed blocks since the last reset                            */
+    uint64_t kernel_launches;     /* kernels launched by this engine since creation                   */
+    uint32_t partitions;          /* UPOLS: P = ceil(L/B); direct: tap splits S                       */
+    uint32_t fft_size;            /* UPOLS: N = 2B; direct: 0                                         */
+    uint32_t kernels_per_block;   /* launches per b200conv_process                                    */
+    uint32_t sm_count;
+    uint32_t stage_count;         /* entries valid in stage_ms / stage_name                           */
+    uint32_t dominant_stage;      /* index of the roofline kernel (direct: FIR; UPOLS: FDL-MAC)       */
+    float stage_ms[4];            /* accumulated CUDA-event time per stage while profiling is on      */
+    uint32_t stage_calls;         /* blocks accumulated into stage_ms                                 */
+    char stage_name[4][24];
+} b200conv_info;
+
+typedef struct b200conv_engine b200conv_engine;
+
+uint32_t b200conv_abi_version(void);
+const char* b200conv_last_error(void);
+
+/* Replaces the device-side half of Conv1DBenchmark::setupBenchmark / Conv1DAccelBenchmark::
+ * setupBenchmark: cudaMalloc of IR / FFT buffers, texture + cuFFT plan creation
+ * (cuda/bench_conv1d.cu:115-157, cuda/bench_conv1d_accel.cu:88-150). */
+int b200conv_create(const b200conv_config* cfg, b200conv_engine** out);
+
+/* Replaces cleanupConvBuffers/cleanupTextureMemory and cleanupAccelBuffers/cleanupFFTPlans
+ * (cuda/bench_conv1d.cu:210-227, cuda/bench_conv1d_accel.cu:339-375).  NULL is a no-op. */
+void b200conv_destroy(b200conv_engine* e);
+
+/* host_ir: float [T][L] track-major, host memory.  Replaces the IR upload + texture copy
+ * (cuda/bench_conv1d.cu:123-157,180) and precomputeImpulseResponseFFTs
+ * (cuda/bench_conv1d_accel.cu:175-228): the direct engine stores the taps in its tiled layout,
+ * the UPOLS engine computes the P partition spectra.  Resets the stream state. */
+int b200conv_load_ir(b200conv_engine* e, const float* host_ir);
+
+/* host_hist: float [T][L-1], oldest sample first (hist[t][L-2] is the sample just before the next
+ * block), or NULL for zeros.  No reference counterpart as an API: it reproduces what oracle R1's
+ * flat input index does implicitly (cuda/bench_conv1d.cu:197-199).  Resets blocks_processed. */
+int b200conv_prime_history(b200conv_engine* e, const float* host_hist);
+
+/* Zero history: the next block equals oracle R2 (cuda/bench_conv1d_accel.cu:234-252). */
+int b200conv_reset(b200conv_engine* e);
+
+/* Per-track stereo bus gains, float [T][2] (L, R), host memory; NULL restores the default
+ * constant-power pan from the global track index, scaled 1/sqrt(Tg). */
+int b200conv_set_mix_gains(b200conv_engine* e, const float* host_gains);
+
+/* One buffer of every track.  d_in float [T][B]; d_out float [T][B] or its [B][Tg] column tile
+ * (pass the base pointer of the full [B][Tg] matrix); d_mix float [2][B] or NULL (written, not
+ * accumulated).  All device pointers; work is enqueued on `stream` and not synchronised.
+ * Replaces the kernel launch of performBenchmarkIteration: cuda/bench_conv1d.cu:92-101 and
+ * cuda/bench_conv1d_accel.cu:263-299. */
+int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float* d_mix, uint32_t flags,
+                     void* stream);
+
+/* The same with HOST buffers: H2D of h_in, process, D2H of h_out / h_mix (either may be NULL),
+ * stream-synchronised on return — one whole performBenchmarkIteration
+ * (transferToDevice + launch + transferToHost, cuda/bench_conv1d.cu:82-105). Pinned host memory
+ * makes the copies asynchronous up to the final synchronise. */
+int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix,
+                          uint32_t flags);
+
+/* Work / byte accounting for roofline figures, and per-stage CUDA-event times. */
+int b200conv_query(b200conv_engine* e, b200conv_info* info);
+
+/* on != 0: bracket every kernel of b200conv_process with CUDA events on the launch stream and
+ * accumulate into info.stage_ms (synchronises at each process call: measurement mode only).
+ * Replaces launchKernelTimed / CudaEventTimer (cuda/bench_utils.cuh:320-329). */
+int b200conv_set_profiling(b200conv_engine* e, int on);
+
+/* Launch plan the engine would use for `cfg` on a device with `sm_count` SMs; needs no GPU.
+ * plan[0..15] = direct: {A, CL, SPS, JSb, S, nst, Lc, cap, nbuf, xtile_blocks, ntiles, smem_bytes, 0...}
+ *               UPOLS : {P, M, logM, S, 0...}.  Used by the host-logic tests and by capacity planning. */
+int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]);
+
+/* Measured FP32 FMA peak of `device` (dependent-free FFMA loop on every SM), TFLOP/s: the
+ * roofline denominator for the direct FIR, which MEASURED_PEAKS.json does not carry. */
+int b200conv_measure_fp32_peak(int device, double* tflops, double* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CONV_H_ */

@@ -1,0 +1,287 @@
+"""NumPy emulation of the device-side index math of the sm_100a kernels (test infrastructure).
+
+These functions mirror, statement for statement, the address arithmetic of
+gpuaudiobench_b200/csrc/direct_fir.cu (swizzle, ring/tile geometry, per-lane block walk) and
+upols.cu (Stockham passes, packed-bin real-FFT pre/post passes, FDL-MAC with the {DC, Nyquist}
+packing, ring-slot rotation).  They let the CPU test-suite prove the index conventions of
+SURVEY.md App. E without a GPU; they are NOT a product path and are never imported outside tests/.
+Arithmetic is float64 here: these check indexing, the GPU tests check fp32 values.
+"""
+import numpy as np
+
+KFIR_WARPS = 8
+
+
+def swz_chunk(f):
+    return f ^ ((f >> 2) & 7)
+
+
+def swz_float(n):
+    return (swz_chunk(n >> 2) << 2) | (n & 3)
+
+
+def load_block(tile, blk):
+    """Mirror of load_block(): 16 floats of logical block `blk` from a swizzled tile."""
+    m = blk & 3
+    hi = ((blk ^ (blk >> 2)) & 1) << 2
+    row = (blk >> 1) << 3
+    out = np.empty(16)
+    for i in range(4):
+        c = row + (hi | (i ^ m))
+        out[4 * i:4 * i + 4] = tile[4 * c:4 * c + 4]
+    return out
+
+
+def toeplitz_tile(acc, hv, lo, hi):
+    w = np.concatenate([lo, hi])
+    for s in range(16):
+        for r in range(16):
+            acc[r] += hv[s] * w[16 + r - s]
+
+
+class DirectEmu:
+    """Emulates ring_append_kernel + fir_direct_kernel<A> + fir_finish_kernel for one engine."""
+
+    def __init__(self, T, B, L, plan):
+        self.T, self.B, self.L = T, B, L
+        self.p = plan
+        self.cap = plan["cap"]
+        self.ring = np.zeros((T, self.cap))
+        self.h = np.zeros((T, plan["Lc"] * 16))
+        self.pos = 0
+
+    def load_ir(self, ir):
+        self.h[:] = 0
+        for j in range(self.L):
+            self.h[:, swz_float(j)] = ir[:, j]
+
+    def prime(self, hist):
+        self.ring[:] = 0
+        H = self.L - 1
+        for i in range(H):
+            self.ring[:, swz_float(self.cap - H + i)] = hist[:, i]
+        self.pos = 0
+
+    def process(self, x, commit=True):
+        p, T, B = self.p, self.T, self.B
+        A, CL, SPS, JSb, S, nst = p["A"], p["CL"], p["SPS"], p["JSb"], p["S"], p["nst"]
+        capb, posb = self.cap // 16, self.pos // 16
+        # ring_append_kernel
+        for f in range(B // 4):
+            pf = swz_chunk(self.pos // 4 + f)
+            self.ring[:, 4 * pf:4 * pf + 4] = x[:, 4 * f:4 * f + 4]
+        partial = np.zeros((S, T, B))
+        OT = A * 16
+        for t in range(T):
+            for ot in range(p["ntiles"]):
+                for s in range(S):
+                    a0 = ot * A
+                    cs0 = s * nst * JSb
+                    qbase = posb + capb + a0
+                    red = np.zeros((KFIR_WARPS, OT))
+                    acc = np.zeros((KFIR_WARPS, 32, 16))
+                    for k in range(nst):
+                        c0 = cs0 + k * JSb
+                        qs = (qbase - c0 - JSb) & ~7
+                        nblk = (qbase + A - 1 - c0) - qs + 1
+                        assert 0 < nblk <= p["xtile_blocks"], (nblk, p["xtile_blocks"])
+                        src_b = qs % capb
+                        first = min(nblk, capb - src_b)
+                        hs = self.h[t, c0 * 16:(c0 + JSb) * 16]
+                        xs = np.empty(nblk * 16)
+                        xs[:first * 16] = self.ring[t, src_b * 16:(src_b + first) * 16]
+                        if first < nblk:
+                            xs[first * 16:] = self.ring[t, :(nblk - first) * 16]
+                        for warp in range(KFIR_WARPS):
+                            for lane in range(32):
+                                a, g = lane & (A - 1), lane // A
+                                hb = (warp * CL + g) * SPS
+                                sb = qbase + a - (c0 + hb) - qs
+                                assert sb - SPS >= 0 and sb < nblk
+                                Q = load_block(xs, sb)
+                                for q in range(0, SPS, 2):
+                                    hv = load_block(hs, hb + q)
+                                    P = load_block(xs, sb - q - 1)
+                                    toeplitz_tile(acc[warp, lane], hv, P, Q)
+                                    hv = load_block(hs, hb + q + 1)
+                                    Q = load_block(xs, sb - q - 2)
+                                    toeplitz_tile(acc[warp, lane], hv, Q, P)
+                    for warp in range(KFIR_WARPS):
+                        for a in range(A):
+                            tot = sum(acc[warp, g * A + a] for g in range(CL))
+                            red[warp, a * 16:(a + 1) * 16] = tot
+                    partial[s, t, ot * OT:(ot + 1) * OT] = red.sum(axis=0)
+        if commit:
+            self.pos = (self.pos + B) % self.cap
+        return partial.sum(axis=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# UPOLS
+# ------------------------------------------------------------------------------------------------
+def fft_stockham(a, inverse, tw):
+    """Mirror of fft_stockham<INV>: complex FFT of a (length M = 2^k) with radix-2/4 Stockham passes."""
+    M = a.size
+    logM = M.bit_length() - 1
+    a = a.astype(np.complex128).copy()
+    b = np.empty_like(a)
+    Ns = 1
+    if logM & 1:
+        half = M >> 1
+        for j in range(half):
+            v0, v1 = a[j], a[j + half]
+            b[2 * j] = v0 + v1
+            b[2 * j + 1] = v0 - v1
+        a, b = b, a
+        Ns = 2
+    quarter = M >> 2
+    rot = 1j if inverse else -1j
+    while Ns < M:
+        tstride = M // (4 * Ns)
+        for j in range(quarter):
+            k = j & (Ns - 1)
+            v0, v1, v2, v3 = a[j], a[j + quarter], a[j + 2 * quarter], a[j + 3 * quarter]
+            if k != 0:
+                w1, w2, w3 = tw[k * tstride], tw[2 * k * tstride], tw[3 * k * tstride]
+                if inverse:
+                    w1, w2, w3 = np.conj(w1), np.conj(w2), np.conj(w3)
+                v1, v2, v3 = v1 * w1, v2 * w2, v3 * w3
+            t0, t1, t2, d = v0 + v2, v0 - v2, v1 + v3, v1 - v3
+            t3 = rot * d
+            j0 = ((j - k) << 2) + k
+            b[j0], b[j0 + Ns], b[j0 + 2 * Ns], b[j0 + 3 * Ns] = t0 + t2, t1 + t3, t0 - t2, t1 - t3
+        a, b = b, a
+        Ns <<= 2
+    return a
+
+
+def twiddles(M):
+    tw_c = np.exp(-2j * np.pi * np.arange(M) / M)
+    tw_r = np.exp(-2j * np.pi * np.arange(M // 2 + 1) / (2 * M))
+    return tw_c, tw_r
+
+
+def rfft_fwd_packed(first, second, scale, tw_c, tw_r):
+    """Mirror of rfft_fwd_kernel for one window [first | second] of 2M reals -> M packed bins."""
+    M = first.size
+    half = M >> 1
+    w = np.concatenate([first, second])
+    a = w[0::2] + 1j * w[1::2]  # a[n] = (w[2n], w[2n+1]): n < M/2 from first, else second
+    z = fft_stockham(a, False, tw_c)
+    out = np.zeros(M, dtype=np.complex128)
+    for k in range(half + 1):
+        A_ = z[k]
+        Bc = np.conj(z[(M - k) & (M - 1)])
+        E = 0.5 * (A_ + Bc)
+        D = 0.5 * (A_ - Bc)
+        O = complex(D.imag, -D.real)
+        WO = tw_r[k] * O
+        Xk = E + WO
+        Xmk = complex(E.real - WO.real, -(E.imag - WO.imag))
+        if k == 0:
+            out[0] = complex(scale * Xk.real, scale * Xmk.real)
+        else:
+            out[k] = scale * Xk
+            if k != half:
+                out[M - k] = scale * Xmk
+    return out
+
+
+def mac_packed(H, X, slot0):
+    """Mirror of fdl_mac_kernel: H, X [P][M] packed; returns packed Y[M]."""
+    P, M = H.shape
+    A_ = np.zeros(M)
+    B_ = np.zeros(M)
+    C_ = np.zeros(M)
+    D_ = np.zeros(M)
+    for p in range(P):
+        sl = slot0 + p
+        if sl >= P:
+            sl -= P
+        h, x = H[p], X[sl]
+        A_ += h.real * x.real
+        B_ += h.imag * x.imag
+        C_ += h.real * x.imag
+        D_ += h.imag * x.real
+    y = (A_ - B_) + 1j * (C_ + D_)
+    y[0] = complex(A_[0], B_[0])
+    return y
+
+
+def irfft_ols_packed(Y, tw_c, tw_r):
+    """Mirror of irfft_ols_kernel: packed Y[M] -> the B = M output samples y[B..2B)."""
+    M = Y.size
+    half = M >> 1
+    a = np.zeros(M, dtype=np.complex128)
+    for k in range(half + 1):
+        mk = (M - k) & (M - 1)
+        yk, ym = Y[k], Y[mk]
+        if k == 0:
+            A_, Bm = complex(yk.real, 0), complex(yk.imag, 0)
+        else:
+            A_, Bm = yk, ym
+        Bc = np.conj(Bm)
+        E, D = A_ + Bc, A_ - Bc
+        O = np.conj(tw_r[k]) * D
+        a[k] = complex(E.real - O.imag, E.imag + O.real)
+        if k != 0 and k != half:
+            a[M - k] = complex(E.real + O.imag, O.real - E.imag)
+    z = fft_stockham(a, True, tw_c)
+    out = np.empty(M)
+    out[0::2] = z[half:].real
+    out[1::2] = z[half:].imag
+    return out
+
+
+class UpolsEmu:
+    """Emulates load_ir / prime_history / process of the UPOLS engine for T tracks."""
+
+    def __init__(self, T, B, L):
+        self.T, self.B, self.L = T, B, L
+        self.P = (L + B - 1) // B
+        self.M = B
+        self.tw_c, self.tw_r = twiddles(B)
+        self.H = np.zeros((T, self.P, B), dtype=np.complex128)
+        self.X = np.zeros((T, self.P, B), dtype=np.complex128)
+        self.prev = np.zeros((T, B))
+        self.m = 0
+
+    def load_ir(self, ir):
+        B, P = self.B, self.P
+        pad = np.zeros((self.T, P * B))
+        pad[:, :self.L] = ir
+        zeros = np.zeros(B)
+        for t in range(self.T):
+            for p in range(P):
+                self.H[t, p] = rfft_fwd_packed(pad[t, p * B:(p + 1) * B], zeros, 1.0 / (2 * B), self.tw_c, self.tw_r)
+        self.reset()
+
+    def reset(self):
+        self.X[:] = 0
+        self.prev[:] = 0
+        self.m = 0
+
+    def prime(self, hist):
+        self.reset()
+        B, P, Hn = self.B, self.P, self.L - 1
+        row = P * B
+        hb = np.zeros((self.T, row))
+        hb[:, row - Hn:] = hist
+        for j in range(-(P - 1), 0):
+            for t in range(self.T):
+                self.X[t, -j] = rfft_fwd_packed(hb[t, (P + j - 1) * B:(P + j) * B], hb[t, (P + j) * B:(P + j + 1) * B],
+                                                1.0, self.tw_c, self.tw_r)
+        self.prev[:] = hb[:, (P - 1) * B:]
+
+    def process(self, x, commit=True):
+        P = self.P
+        slot0 = (P - (self.m % P)) % P
+        y = np.empty((self.T, self.B))
+        for t in range(self.T):
+            self.X[t, slot0] = rfft_fwd_packed(self.prev[t], x[t], 1.0, self.tw_c, self.tw_r)
+            Y = mac_packed(self.H[t], self.X[t], slot0)
+            y[t] = irfft_ols_packed(Y, self.tw_c, self.tw_r)
+        if commit:
+            self.prev[:] = x
+            self.m += 1
+        return y

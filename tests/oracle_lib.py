@@ -1,0 +1,197 @@
+"""ctypes doorway to the CPU checker under oracle/ (test infrastructure, never the product path).
+
+`Oracle` wraps oracle/liboracle.so (our restatement of the reference's CPU loops);
+`RefLib` wraps oracle/_ref/libgpuab_ref.so (the reference's own compiled functions, when built).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libgpuab_ref.so")
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+def build_oracle(with_ref=True):
+    """Compile the checker (g++) and, when /root/reference is present, oracle/_ref (nvcc)."""
+    targets = ["all"] + (["ref"] if with_ref else [])
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR] + targets, check=True)
+
+
+def fnv1a64(arr) -> str:
+    """FNV-1a-64 over the raw little-endian bytes (the tripwire hash of SURVEY.md App. A.3)."""
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(arr).tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build_oracle(with_ref=False)
+        L = self.lib = C.CDLL(ORACLE_SO)
+        L.oracle_generate_input.argtypes = [_f32p, C.c_size_t, C.c_uint]
+        for name in ("oracle_generate_ir_direct", "oracle_generate_ir_accel"):
+            getattr(L, name).argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_conv1d_r1.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.oracle_conv1d_r2.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.oracle_stream.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int64]
+        L.oracle_compare_abs.argtypes = [_f32p, _f32p, C.c_size_t, C.c_float,
+                                         C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.oracle_compare_rel.argtypes = [_f32p, _f32p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.oracle_statistics.argtypes = [_f32p, C.c_size_t, _f32p]
+        L.oracle_nearest_rank.argtypes = [_f32p, C.c_size_t, C.c_int, C.c_int, _f32p]
+        L.oracle_fnv1a64.argtypes = [C.c_void_p, C.c_size_t]
+        L.oracle_fnv1a64.restype = C.c_uint64
+        for name in ("oracle_time_r1", "oracle_time_r2"):
+            getattr(L, name).argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+            getattr(L, name).restype = C.c_double
+        L.oracle_hardware_threads.restype = C.c_int
+
+    # -- generators --------------------------------------------------------------------------
+    def generate_input(self, count, seed=42):
+        buf = np.empty(count, dtype=np.float32)
+        self.lib.oracle_generate_input(buf, count, seed)
+        return buf
+
+    def generate_ir(self, T, L, variant="direct", t_begin=0, t_end=None):
+        """IRs [t_end-t_begin][L]; the cutoff uses the global track index t and total T."""
+        t_end = T if t_end is None else t_end
+        h = np.empty((t_end - t_begin, L), dtype=np.float32)
+        fn = self.lib.oracle_generate_ir_direct if variant == "direct" else self.lib.oracle_generate_ir_accel
+        fn(h, t_begin, t_end, T, L)
+        return h
+
+    # -- oracles -----------------------------------------------------------------------------
+    def r1(self, x, h, L, B, T):
+        """Track-major [T][B]; flat-index history bleed (bench_conv1d.cu:188-208)."""
+        y = np.empty(T * B, dtype=np.float32)
+        self.lib.oracle_conv1d_r1(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T)
+        return y.reshape(T, B)
+
+    def r2(self, x, h, L, B, T):
+        """Sample-major [B][T]; per-track zero history (bench_conv1d_accel.cu:234-252)."""
+        y = np.empty(T * B, dtype=np.float32)
+        self.lib.oracle_conv1d_r2(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T)
+        return y.reshape(B, T)
+
+    def stream(self, x, h):
+        """Streaming oracle for one track: y[n] = sum_k h[k] x[n-k], n < len(x) (App. A.2)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        h = np.ascontiguousarray(h, dtype=np.float32)
+        y = np.empty_like(x)
+        self.lib.oracle_stream(x, h, y, h.size, x.size)
+        return y
+
+    # -- metrics -----------------------------------------------------------------------------
+    def compare_abs(self, gpu, cpu, tol):
+        mx, mean, over = C.c_float(), C.c_float(), C.c_int()
+        g = np.ascontiguousarray(gpu.ravel(), dtype=np.float32)
+        c = np.ascontiguousarray(cpu.ravel(), dtype=np.float32)
+        self.lib.oracle_compare_abs(g, c, g.size, tol, C.byref(mx), C.byref(mean), C.byref(over))
+        return mx.value, mean.value, over.value
+
+    def compare_rel(self, gpu, cpu):
+        mx, mean = C.c_float(), C.c_float()
+        g = np.ascontiguousarray(gpu.ravel(), dtype=np.float32)
+        c = np.ascontiguousarray(cpu.ravel(), dtype=np.float32)
+        self.lib.oracle_compare_rel(g, c, g.size, C.byref(mx), C.byref(mean))
+        return mx.value, mean.value
+
+    def statistics(self, lat):
+        lat = np.ascontiguousarray(lat, dtype=np.float32)
+        out = np.zeros(8, dtype=np.float32)
+        self.lib.oracle_statistics(lat, lat.size, out)
+        return dict(zip(("mean", "median", "std", "min", "max", "p95", "p99", "count"), out.tolist()))
+
+    def nearest_rank(self, lat, bufsize, fs):
+        lat = np.ascontiguousarray(lat, dtype=np.float32)
+        out = np.zeros(5, dtype=np.float32)
+        self.lib.oracle_nearest_rank(lat, lat.size, bufsize, fs, out)
+        return dict(zip(("p50", "p95", "p99", "threshold_ms", "meets_deadline"), out.tolist()))
+
+    # -- timing legs (bench.py) --------------------------------------------------------------
+    def time_r1(self, x, h, L, B, T, nthreads):
+        y = np.empty(T * B, dtype=np.float32)
+        return self.lib.oracle_time_r1(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T, nthreads)
+
+    def time_r2(self, x, h, L, B, T, nthreads):
+        y = np.empty(T * B, dtype=np.float32)
+        return self.lib.oracle_time_r2(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T, nthreads)
+
+    def hardware_threads(self):
+        return self.lib.oracle_hardware_threads()
+
+
+class RefLib:
+    """The reference's own compiled CPU functions (oracle/_ref). `available()` is False when the
+    library has not been built (no /root/reference at build time and no prebuilt copy)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        L = self.lib = C.CDLL(REF_SO)
+        L.ref_generate_input.argtypes = [_f32p, C.c_size_t, C.c_uint]
+        L.ref_conv1d_r1.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.ref_conv1d_r2.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.ref_generate_ir_direct.argtypes = [_f32p, C.c_int, C.c_int]
+        L.ref_generate_ir_accel.argtypes = [_f32p, C.c_int, C.c_int]
+        L.ref_statistics.argtypes = [_f32p, C.c_size_t, _f32p]
+        L.ref_json_results.argtypes = [_f32p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+        for name in ("ref_time_r1", "ref_time_r2"):
+            getattr(L, name).argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+            getattr(L, name).restype = C.c_double
+        L.ref_hardware_threads.restype = C.c_int
+
+    def generate_input(self, count, seed=42):
+        buf = np.empty(count, dtype=np.float32)
+        self.lib.ref_generate_input(buf, count, seed)
+        return buf
+
+    def generate_ir(self, T, L, variant="direct"):
+        h = np.empty((T, L), dtype=np.float32)
+        (self.lib.ref_generate_ir_direct if variant == "direct" else self.lib.ref_generate_ir_accel)(h, T, L)
+        return h
+
+    def r1(self, x, h, L, B, T):
+        y = np.empty(T * B, dtype=np.float32)
+        self.lib.ref_conv1d_r1(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T)
+        return y.reshape(T, B)
+
+    def r2(self, x, h, L, B, T):
+        y = np.empty(T * B, dtype=np.float32)
+        self.lib.ref_conv1d_r2(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T)
+        return y.reshape(B, T)
+
+    def statistics(self, lat):
+        lat = np.ascontiguousarray(lat, dtype=np.float32)
+        out = np.zeros(8, dtype=np.float32)
+        self.lib.ref_statistics(lat, lat.size, out)
+        return dict(zip(("mean", "median", "std", "min", "max", "p95", "p99", "count"), out.tolist()))
+
+    def json_results(self, lat, name, fs, bufsize, ntracks):
+        lat = np.ascontiguousarray(lat, dtype=np.float32)
+        buf = C.create_string_buffer(4096)
+        n = self.lib.ref_json_results(lat, lat.size, name.encode(), fs, bufsize, ntracks, buf, 4096)
+        assert n >= 0
+        return buf.value.decode()
+
+    def time_r1(self, x, h, L, B, T, nthreads):
+        y = np.empty(T * B, dtype=np.float32)
+        return self.lib.ref_time_r1(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T, nthreads)
+
+    def time_r2(self, x, h, L, B, T, nthreads):
+        y = np.empty(T * B, dtype=np.float32)
+        return self.lib.ref_time_r2(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T, nthreads)
+
+    def hardware_threads(self):
+        return self.lib.ref_hardware_threads()

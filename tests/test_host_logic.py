@@ -1,0 +1,131 @@
+"""CPU tests: the C-ABI library loads and exports what include/b200conv.h declares, the planner and
+the device index conventions (checked through the NumPy emulation that mirrors the kernels), and
+the engine fails loudly when there is no GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gpuaudiobench_b200 as g
+from kernel_emulation import DirectEmu, UpolsEmu, swz_chunk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "b200conv.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = sorted(set(re.findall(r"\b(b200conv_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 13, names
+    lib = ctypes.CDLL(g.engine.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"libb200conv.so does not export {n}"
+    assert g.load_library().b200conv_abi_version() == 1
+
+
+def test_ctypes_structs_match_header_sizes():
+    assert ctypes.sizeof(g.engine.Config) == 40
+    assert ctypes.sizeof(g.engine.Info) == 8 * 6 + 4 * 6 + 16 + 4 + 96 + 4  # incl. tail padding to 8
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure path")
+def test_no_gpu_fails_loudly():
+    with pytest.raises(g.B200ConvError) as ei:
+        g.ConvEngine(1, 512, 1024, g.ALGO_DIRECT)
+    assert ei.value.code == g.engine.ERR_NO_DEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_plan_rejects_bad_sizes():
+    with pytest.raises(g.B200ConvError):
+        g.plan(4, 48, 100, g.ALGO_DIRECT)  # direct: 32..256 or multiples of 512
+    with pytest.raises(g.B200ConvError):
+        g.plan(4, 480, 100, g.ALGO_UPOLS)  # UPOLS: power of two
+    with pytest.raises(g.B200ConvError):
+        g.plan(0, 512, 100, g.ALGO_UPOLS)
+
+
+@pytest.mark.parametrize("T,B,L", [(128, 512, 16384), (1, 512, 1024), (4096, 512, 96000), (128, 32, 96000),
+                                    (7, 4096, 5000), (3, 256, 17)])
+def test_direct_plan_invariants(T, B, L):
+    p = g.plan(T, B, L, g.ALGO_DIRECT)
+    assert p["A"] * p["CL"] == 32 and p["SPS"] % 2 == 0
+    assert p["JSb"] == 8 * p["CL"] * p["SPS"]
+    assert p["Lc"] == p["S"] * p["nst"] * p["JSb"] and p["Lc"] * 16 >= L
+    assert p["cap"] % B == 0 and p["cap"] % 128 == 0 and p["cap"] >= p["Lc"] * 16 + B + 128
+    assert p["smem"] <= 112 * 1024 and 1 <= p["nbuf"] <= 8
+    assert p["ntiles"] * p["A"] * 16 == B
+
+
+def test_upols_plan_c3_c4():
+    assert g.plan(1024, 256, 65536, g.ALGO_UPOLS)["P"] == 256
+    p = g.plan(512, 512, 96000, g.ALGO_UPOLS)
+    assert p["P"] == 188 and p["M"] == 512 and p["logM"] == 9
+
+
+def test_swizzle_is_a_permutation_inside_128_byte_lines():
+    f = np.arange(4096)
+    pf = swz_chunk(f)
+    assert np.array_equal(np.sort(pf), f) and np.array_equal(pf // 8, f // 8)
+    # any 8 consecutive 64 B blocks, same chunk-in-block i, hit 8 distinct 16 B bank groups
+    for start in range(0, 64):
+        for i in range(4):
+            banks = {int(swz_chunk(4 * b + i)) & 7 for b in range(start, start + 8)}
+            assert len(banks) == 8
+
+
+def _truth(xs, h, hist=None):
+    nb, T, B = xs.shape
+    out = np.zeros((nb, T, B))
+    for t in range(T):
+        pre = hist[t] if hist is not None else np.zeros(0)
+        s = np.concatenate([pre] + [xs[m, t] for m in range(nb)])
+        out[:, t, :] = np.convolve(s, h[t])[:s.size][pre.size:].reshape(nb, B)
+    return out
+
+
+@pytest.mark.parametrize("T,B,L,nb,split", [(1, 512, 1024, 2, 0), (2, 32, 100, 3, 0), (1, 256, 3000, 2, 1),
+                                             (1, 512, 16, 6, 0), (1, 128, 5000, 2, 2)])
+def test_direct_kernel_index_math(monkeypatch, T, B, L, nb, split):
+    """Swizzled ring + tile geometry + lane block walk of fir_direct_kernel (incl. multi-stage CTAs,
+    tap splits, ring wrap-around at pos -> 0, primed history read across the ring seam)."""
+    if split:
+        monkeypatch.setenv("B200CONV_DIRECT_SPLIT", str(split))
+    p = g.plan(T, B, L, g.ALGO_DIRECT)
+    rng = np.random.default_rng(1)
+    h, xs, hist = rng.standard_normal((T, L)), rng.standard_normal((nb, T, B)), rng.standard_normal((T, L - 1))
+    e = DirectEmu(T, B, L, p)
+    e.load_ir(h)
+    ys = np.stack([e.process(xs[m]) for m in range(nb)])
+    assert np.abs(ys - _truth(xs, h)).max() < 1e-11
+    e.prime(hist)
+    assert np.array_equal(e.process(xs[0], commit=False), e.process(xs[0], commit=False))  # PEEK is idempotent
+    ys = np.stack([e.process(xs[m]) for m in range(nb)])
+    assert np.abs(ys - _truth(xs, h, hist)).max() < 1e-11
+
+
+@pytest.mark.parametrize("T,B,L,nb", [(2, 16, 40, 7), (1, 32, 100, 6), (2, 64, 64, 4), (1, 16, 1, 3), (1, 128, 300, 5)])
+def test_upols_kernel_index_math(T, B, L, nb):
+    """Packed-bin real FFT pre/post passes, Stockham radix-2/4 passes, {DC,Nyquist} MAC, ring-slot
+    rotation over > 2P blocks, partial last partition, priming."""
+    rng = np.random.default_rng(2)
+    h, xs = rng.standard_normal((T, L)), rng.standard_normal((nb, T, B))
+    e = UpolsEmu(T, B, L)
+    e.load_ir(h)
+    ys = np.stack([e.process(xs[m]) for m in range(nb)])
+    assert np.abs(ys - _truth(xs, h)).max() < 1e-11
+    if L > 1:
+        hist = rng.standard_normal((T, L - 1))
+        e.prime(hist)
+        ys = np.stack([e.process(xs[m]) for m in range(nb)])
+        assert np.abs(ys - _truth(xs, h, hist)).max() < 1e-11

@@ -1,0 +1,134 @@
+"""CPU tests that pin the oracle (oracle/conv_oracle.cpp): known answers of SURVEY.md App. A.3,
+the golden fixtures generated from the reference's own compiled functions, and — when
+oracle/_ref is present — bit-for-bit equality with those functions at run time."""
+import numpy as np
+import pytest
+
+from oracle_lib import fnv1a64
+
+CASES = ["c1", "tiny", "ragged", "multi"]
+
+
+def test_input_generator_kat(oracle):
+    # cuda/bench_utils.cu:238-245, seed 42: first raw MT word 1608637542 -> -0.250919759
+    x = oracle.generate_input(512)
+    assert np.allclose(x[:4], [-0.250919759, 0.593086004, 0.90142858, -0.633130431], rtol=0, atol=1e-9)
+    assert fnv1a64(x) == "6a365ddbb6fab734"
+    u = np.random.RandomState(42).randint(0, 2 ** 32, 4, dtype=np.uint64)
+    alt = np.float32(u.astype(np.float32)) / np.float32(2 ** 32) * np.float32(2) + np.float32(-1)
+    assert np.array_equal(alt.astype(np.float32), x[:4])
+
+
+def test_ir_generators_kat(oracle):
+    hd = oracle.generate_ir(1, 1024, "direct")
+    ha = oracle.generate_ir(1, 1024, "accel")
+    assert fnv1a64(hd) == "32b5f9247ce825a5"
+    assert fnv1a64(ha) == "e621e5f6edfcc782"
+    assert np.allclose(hd[0, [0, 1, 2, 512]], [2.30965895e-07, 1.43039429e-07, 5.78042648e-12, 0.000976560405], rtol=1e-6)
+    assert (hd != ha).sum() == 503 and np.abs(hd - ha).max() < 1.2e-10
+
+
+def test_r1_r2_kat_c1(oracle):
+    x = oracle.generate_input(512)
+    y1 = oracle.r1(x, oracle.generate_ir(1, 1024, "direct"), 1024, 512, 1)
+    y2 = oracle.r2(x, oracle.generate_ir(1, 1024, "accel"), 1024, 512, 1)
+    assert fnv1a64(y1) == "d5fd95533af9b660"
+    assert fnv1a64(y2) == "de18e0ff41efd2bf"
+    assert np.isclose(y1[0, 511], 0.000269706885, rtol=1e-6)
+    assert np.isclose(y1.sum(dtype=np.float32), -0.000420333436, rtol=1e-4)
+
+
+def test_layout_and_bleed_kat(oracle):
+    # T=2, B=8, L=4: R1 is track-major with cross-track bleed, R2 is interleaved with zero history
+    x = oracle.generate_input(16)
+    y1 = oracle.r1(x, oracle.generate_ir(2, 4, "direct"), 4, 8, 2)
+    y2 = oracle.r2(x, oracle.generate_ir(2, 4, "accel"), 4, 8, 2)
+    assert fnv1a64(y1) == "5d8b5ac89a860d00"
+    assert fnv1a64(y2) == "e94a0030d67ae039"
+    assert np.allclose(y2.ravel()[:4], [-0.00379805639, -0.00875941385, -0.0362087823, -0.120610788], rtol=1e-6)
+
+
+def test_reference_defaults_hashes(oracle, golden):
+    x = oracle.generate_input(128 * 512)
+    y1 = oracle.r1(x, oracle.generate_ir(128, 1024, "direct"), 1024, 512, 128)
+    y2 = oracle.r2(x, oracle.generate_ir(128, 1024, "accel"), 1024, 512, 128)
+    assert [fnv1a64(x), fnv1a64(y1), fnv1a64(y2)] == list(golden["defaults_hashes"])
+    assert fnv1a64(y1) == "a1bca72fa8b30412" and fnv1a64(y2) == "299f6810cbd2154a"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_fixtures(oracle, golden, name):
+    """Fixtures come from the reference's own compiled code (tests/golden/make_golden.py)."""
+    T, B, L = (int(v) for v in golden[f"{name}_shape"])
+    x = oracle.generate_input(T * B)
+    assert np.array_equal(x, golden[f"{name}_x"])
+    hd = oracle.generate_ir(T, L, "direct")
+    ha = oracle.generate_ir(T, L, "accel")
+    assert np.array_equal(hd, golden[f"{name}_h_direct"])
+    assert np.array_equal(ha, golden[f"{name}_h_accel"])
+    assert np.array_equal(oracle.r1(x, hd, L, B, T), golden[f"{name}_r1"])
+    assert np.array_equal(oracle.r2(x, ha, L, B, T), golden[f"{name}_r2"])
+
+
+def test_streaming_oracle_matches_golden(oracle, golden):
+    assert np.array_equal(oracle.stream(golden["stream_x"], golden["stream_h"][0]), golden["stream_y"])
+
+
+def test_streaming_oracle_is_r2_with_one_long_buffer(oracle):
+    x = oracle.generate_input(4 * 64, seed=5)
+    h = oracle.generate_ir(1, 150, "accel")
+    assert np.array_equal(oracle.stream(x, h[0]), oracle.r2(x, h, 150, 256, 1).ravel())
+
+
+def test_ir_sharding_uses_global_track_index(oracle):
+    full = oracle.generate_ir(8, 64, "accel")
+    parts = [oracle.generate_ir(8, 64, "accel", a, b) for a, b in ((0, 3), (3, 8))]
+    assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_r1_equals_streaming_with_primed_history(oracle):
+    """R1's flat-index bleed == per-track history x_flat[tB-L+1 .. tB-1]."""
+    T, B, L = 3, 16, 40
+    x = oracle.generate_input(T * B, seed=9)
+    h = oracle.generate_ir(T, L, "direct")
+    y = oracle.r1(x, h, L, B, T)
+    padded = np.concatenate([np.zeros(L - 1, dtype=np.float32), x])
+    for t in range(T):
+        hist_and_block = padded[t * B:t * B + L - 1 + B]
+        assert np.array_equal(oracle.stream(hist_and_block, h[t])[L - 1:], y[t])
+
+
+def test_statistics_and_deadline(oracle, golden):
+    st = oracle.statistics(golden["stats_lat"])
+    got = np.array([st[k] for k in ("mean", "median", "std", "min", "max", "p95", "p99", "count")], dtype=np.float32)
+    assert np.array_equal(got, golden["stats_out"])
+    nr = oracle.nearest_rank(golden["stats_lat"], 512, 48000)
+    s = np.sort(golden["stats_lat"])
+    assert nr["p50"] == s[50] and nr["p95"] == s[95] and nr["p99"] == s[99]
+    assert np.isclose(nr["threshold_ms"], 10.6666667) and nr["meets_deadline"] == 1.0
+
+
+def test_metrics(oracle):
+    a = np.array([1.0, 2.0, 0.0, -4.0], dtype=np.float32)
+    b = np.array([1.0, 2.5, 0.25, -2.0], dtype=np.float32)
+    mx, mean, over = oracle.compare_abs(a, b, 1e-3)
+    assert mx == 2.0 and np.isclose(mean, (0.5 + 0.25 + 2.0) / 4) and over == 3
+    mx, mean = oracle.compare_rel(a, b)
+    assert mx == 1.0  # |0-0.25|/0.25 and |-4+2|/2
+
+
+# ---- run-time equality with the reference's own compiled functions (oracle/_ref) ---------------
+@pytest.mark.parametrize("T,B,L", [(1, 512, 1024), (4, 32, 100), (7, 48, 33), (16, 64, 1000)])
+def test_restatement_equals_reference_build(oracle, reflib, T, B, L):
+    x = oracle.generate_input(T * B, 42)
+    assert np.array_equal(x, reflib.generate_input(T * B, 42))
+    for variant in ("direct", "accel"):
+        assert np.array_equal(oracle.generate_ir(T, L, variant), reflib.generate_ir(T, L, variant))
+    hd, ha = oracle.generate_ir(T, L, "direct"), oracle.generate_ir(T, L, "accel")
+    assert np.array_equal(oracle.r1(x, hd, L, B, T), reflib.r1(x, hd, L, B, T))
+    assert np.array_equal(oracle.r2(x, ha, L, B, T), reflib.r2(x, ha, L, B, T))
+
+
+def test_statistics_equal_reference_build(oracle, reflib):
+    lat = (oracle.generate_input(257, 11) * 0.3 + 1.0).astype(np.float32)
+    assert oracle.statistics(lat) == reflib.statistics(lat)
