@@ -9,16 +9,24 @@
 // Work is cut into 16-sample output blocks (index a) and 16-tap blocks (index c).  For one (a, c)
 // pair the 16x16 Toeplitz product needs exactly two 16-sample input blocks, D_{a-c-1} | D_{a-c},
 // so a lane that walks c upward re-uses one of them: per 256 FMAs it loads 16 taps + 16 samples
-// (8 LDS.128).  Lanes of a warp own different output blocks (taps are a shared-memory
-// broadcast), warps own different tap ranges, and a CTA owns (track, 512-output tile, tap split).
-// Taps and history are kept PRE-SWIZZLED in HBM (common.cuh: swz_chunk) so that one elected
-// producer lane stages them with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) into a
-// multi-stage mbarrier ring while 8 consumer warps stay on the FMA pipe; the 64 B lane stride of
-// the block reads is bank-conflict free because of that swizzle.
+// (8 LDS.128).  Lanes of a warp own different output blocks (taps are then a shared-memory
+// broadcast), warps own different tap ranges inside a pipeline stage.
 //
-// Kernels: ring_append_kernel (new block -> history ring), fir_direct_kernel<A> (the hot kernel),
-// fir_finish_kernel (fixed-order sum of the tap-split partials + output layout).
+// Scheduling (v2, after the first ncu pass: 20 % of SM time idle at 0.86 waves): the job is the
+// flat list of "units" (track, 512-output tile, tap stage); a persistent grid of 2 CTAs per SM
+// splits that list into equal contiguous spans, so every SM gets the same number of stages.  A
+// span may start and end in the middle of a track: each (CTA, track-tile) segment writes one
+// partial-sum row, and fir_finish_mix_kernel adds the (static, at most MS) rows of a tile in a
+// fixed order — deterministic, no atomics.
+//
+// Data movement: taps and history are kept PRE-SWIZZLED in HBM (common.cuh: swz_chunk) so that
+// one elected producer lane stages them with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP)
+// into an mbarrier ring that runs ahead across unit and track boundaries, while 8 consumer warps
+// stay on the FMA pipe; the 64 B lane stride of the block reads is bank-conflict free because of
+// the swizzle, which costs one shift + four LOP3 per block as an XOR on the byte offset.
 #include "direct_fir.cuh"
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -37,17 +45,27 @@ __global__ void ring_append_kernel(const float4* __restrict__ in, float4* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// The FIR kernel.
+// Block loads.  A block is 16 floats (64 B).  Swizzled tiles: byte offset of chunk i of block blk
+// is (64 blk + 16 i) ^ ((blk & 7) << 4) — four conflict-free LDS.128 for 8 neighbouring lanes.
 // ---------------------------------------------------------------------------------------------
-// Load one 16-float block (index blk) of a swizzled tile into registers: four conflict-free
-// LDS.128.  Physical chunk of logical chunk 4*blk+i is 8*(blk>>1) + (hi | (i ^ m)).
-__device__ __forceinline__ void load_block(float (&v)[16], const float* tile, int blk) {
-    const uint32_t m = blk & 3;
-    const uint32_t hi = ((blk ^ (blk >> 2)) & 1) << 2;
-    const float4* row = reinterpret_cast<const float4*>(tile) + ((blk >> 1) << 3);
+__device__ __forceinline__ void load_block_swz(float (&v)[16], const unsigned char* tile, int blk) {
+    const uint32_t off = static_cast<uint32_t>(blk) << 6;
+    const uint32_t p0 = off ^ ((off >> 2) & 0x70u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float4 q = row[hi | (i ^ m)];
+        const float4 q = *reinterpret_cast<const float4*>(tile + (p0 ^ (i << 4)));
+        v[4 * i + 0] = q.x;
+        v[4 * i + 1] = q.y;
+        v[4 * i + 2] = q.z;
+        v[4 * i + 3] = q.w;
+    }
+}
+
+__device__ __forceinline__ void load_block_lin(float (&v)[16], const unsigned char* tile, int blk) {
+    const float4* p = reinterpret_cast<const float4*>(tile + (static_cast<uint32_t>(blk) << 6));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 q = p[i];
         v[4 * i + 0] = q.x;
         v[4 * i + 1] = q.y;
         v[4 * i + 2] = q.z;
@@ -69,24 +87,31 @@ __device__ __forceinline__ void toeplitz_tile(float (&acc)[16], const float (&hv
     }
 }
 
+// CTA that owns unit u when U units are split over G CTAs as [floor(i U/G), floor((i+1) U/G)).
+__host__ __device__ __forceinline__ long long fir_cta_of_unit(long long u, long long U, long long G) {
+    return ((u + 1) * G + U - 1) / U - 1;
+}
+
 template <int A>
 __global__ void __launch_bounds__(kFirThreads, 2) fir_direct_kernel(FirParams p) {
     constexpr int CL = 32 / A;  // tap groups per warp
+    constexpr int OT = A * 16;  // outputs per tile
+    constexpr bool kSwzTaps = (CL > 1);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty_bar = full_bar + kFirMaxStages;
-    float* stage_base = reinterpret_cast<float*>(smem_raw + 128);
-    const int stage_floats = (p.JSb + p.xtile_blocks) * 16;
-    float* red = stage_base + static_cast<size_t>(p.nbuf) * stage_floats;
+    unsigned char* stage_base = smem_raw + 128;
+    const uint32_t stage_bytes = static_cast<uint32_t>(p.JSb + p.xtile_blocks) * 64u;
+    float* red = reinterpret_cast<float*>(stage_base + static_cast<size_t>(p.nbuf) * stage_bytes);
 
-    const int s = blockIdx.x;   // tap split
-    const int ot = blockIdx.y;  // 16*A-output tile
-    const int t = blockIdx.z;   // track
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int a0 = ot * A;                 // first output block of this tile
-    const int cs0 = s * p.nst * p.JSb;     // first tap block of this split
-    const int qbase = p.posb + p.capb + a0;  // unwrapped ring block index of output block a0
+    const long long U = p.U, G = gridDim.x;
+    const int u_lo = static_cast<int>(static_cast<long long>(blockIdx.x) * U / G);
+    const int u_hi = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * U / G);
+    const int n_units = u_hi - u_lo;
+    const int w0 = u_lo / p.NS;        // first (track, tile) index
+    const int k0 = u_lo - w0 * p.NS;   // first tap stage inside it
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nbuf; ++i) {
@@ -98,104 +123,146 @@ __global__ void __launch_bounds__(kFirThreads, 2) fir_direct_kernel(FirParams p)
     __syncthreads();
 
     if (warp == kFirWarps) {
-        // ===== producer: one lane drives the TMA engine =====
+        // ===== producer: one lane drives the TMA engine, running ahead across units =====
         if (lane == 0) {
-            const float* hsrc = p.h + static_cast<size_t>(t) * p.Lc * 16;
-            const float* rsrc = p.ring + static_cast<size_t>(t) * p.capb * 16;
-            for (int k = 0; k < p.nst; ++k) {
-                const int slot = k % p.nbuf;
-                const int round = k / p.nbuf;
-                if (round > 0) mbar_wait(&empty_bar[slot], (round - 1) & 1);
-                const int c0 = cs0 + k * p.JSb;
+            int w = w0, k = k0, slot = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_units; ++it) {
+                if (it >= p.nbuf) mbar_wait(&empty_bar[slot], phase ^ 1);
+                const int t = w / p.ntiles;
+                const int ot = w - t * p.ntiles;
+                const int c0 = k * p.JSb;
+                const int qbase = p.posb + p.capb + ot * A;      // unwrapped ring block of output block a0
                 const int qs = (qbase - c0 - p.JSb) & ~7;        // tile start, 512 B aligned in the ring
                 const int nblk = (qbase + A - 1 - c0) - qs + 1;  // <= xtile_blocks
-                const int src_b = qs % p.capb;
+                int src_b = qs % p.capb;
                 const int first = min(nblk, p.capb - src_b);
-                float* hs = stage_base + static_cast<size_t>(slot) * stage_floats;
-                float* xs = hs + p.JSb * 16;
+                unsigned char* hs = stage_base + static_cast<size_t>(slot) * stage_bytes;
+                unsigned char* xs = hs + p.JSb * 64;
+                const float* hsrc = p.h + (static_cast<size_t>(t) * p.Lc + c0) * 16;
+                const float* rsrc = p.ring + static_cast<size_t>(t) * p.capb * 16;
                 mbar_arrive_expect_tx(&full_bar[slot], static_cast<uint32_t>((p.JSb + nblk) * 64));
-                bulk_g2s(hs, hsrc + static_cast<size_t>(c0) * 16, static_cast<uint32_t>(p.JSb * 64), &full_bar[slot]);
+                bulk_g2s(hs, hsrc, static_cast<uint32_t>(p.JSb * 64), &full_bar[slot]);
                 bulk_g2s(xs, rsrc + static_cast<size_t>(src_b) * 16, static_cast<uint32_t>(first * 64), &full_bar[slot]);
                 if (first < nblk)
-                    bulk_g2s(xs + first * 16, rsrc, static_cast<uint32_t>((nblk - first) * 64), &full_bar[slot]);
+                    bulk_g2s(xs + first * 64, rsrc, static_cast<uint32_t>((nblk - first) * 64), &full_bar[slot]);
+                if (++slot == p.nbuf) { slot = 0; phase ^= 1; }
+                if (++k == p.NS) { k = 0; ++w; }
             }
         }
-        __syncwarp();
     } else {
         // ===== consumers: 8 warps on the FMA pipe =====
         const int a = lane & (A - 1);
         const int g = lane / A;
+        const int hb0 = (warp * CL + g) * p.SPS;  // lane's first tap block inside a stage
         float acc[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) acc[r] = 0.0f;
 
-        for (int k = 0; k < p.nst; ++k) {
-            const int slot = k % p.nbuf;
-            const int round = k / p.nbuf;
-            mbar_wait(&full_bar[slot], round & 1);
-            const int c0 = cs0 + k * p.JSb;
+        int w = w0, k = k0, slot = 0;
+        uint32_t phase = 0;
+        // partial-sum row of the first segment: how many CTAs before this one share its tile
+        int seg = static_cast<int>(blockIdx.x - fir_cta_of_unit(static_cast<long long>(w0) * p.NS, U, G));
+
+        for (int it = 0; it < n_units; ++it) {
+            mbar_wait(&full_bar[slot], phase);
+            const int t = w / p.ntiles;
+            const int ot = w - t * p.ntiles;
+            const int c0 = k * p.JSb;
+            const int qbase = p.posb + p.capb + ot * A;
             const int qs = (qbase - c0 - p.JSb) & ~7;
-            const float* hs = stage_base + static_cast<size_t>(slot) * stage_floats;
-            const float* xs = hs + p.JSb * 16;
-            const int hb = (warp * CL + g) * p.SPS;     // lane's first tap block inside the stage
-            const int sb = qbase + a - (c0 + hb) - qs;  // smem block index of D_{a-c} for c = c0+hb
+            const unsigned char* hs = stage_base + static_cast<size_t>(slot) * stage_bytes;
+            const unsigned char* xs = hs + p.JSb * 64;
+            const int sb = qbase + a - (c0 + hb0) - qs;  // smem block index of D_{a-c} for c = c0 + hb0
 
             float P[16], Q[16], hv[16];
-            load_block(Q, xs, sb);
+            load_block_swz(Q, xs, sb);
             for (int q = 0; q < p.SPS; q += 2) {
-                load_block(hv, hs, hb + q);
-                load_block(P, xs, sb - q - 1);
+                if (kSwzTaps) load_block_swz(hv, hs, hb0 + q); else load_block_lin(hv, hs, hb0 + q);
+                load_block_swz(P, xs, sb - q - 1);
                 toeplitz_tile(acc, hv, P, Q);
-                load_block(hv, hs, hb + q + 1);
-                load_block(Q, xs, sb - q - 2);
+                if (kSwzTaps) load_block_swz(hv, hs, hb0 + q + 1); else load_block_lin(hv, hs, hb0 + q + 1);
+                load_block_swz(Q, xs, sb - q - 2);
                 toeplitz_tile(acc, hv, Q, P);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[slot]);
-        }
+            if (++slot == p.nbuf) { slot = 0; phase ^= 1; }
 
-        // tap groups of one warp -> lanes 0..A-1
-        if (CL > 1) {
+            const bool tile_done = (k + 1 == p.NS);
+            if (tile_done || it + 1 == n_units) {
+                // ---- flush this (CTA, tile) segment: tap groups -> warps -> one partial row ----
+                if (CL > 1) {
 #pragma unroll
-            for (int off = A; off < 32; off <<= 1) {
+                    for (int off = A; off < 32; off <<= 1) {
 #pragma unroll
-                for (int r = 0; r < 16; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+                        for (int r = 0; r < 16; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+                    }
+                }
+                if (g == 0) {
+                    float4* dst = reinterpret_cast<float4*>(red + (warp * A + a) * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                }
+                named_bar_sync(1, kFirWarps * 32);
+                float* dstrow = p.partial + (static_cast<size_t>(seg) * p.T + t) * p.B + ot * OT;
+                for (int o = threadIdx.x; o < OT; o += kFirWarps * 32) {
+                    float v = 0.0f;
+#pragma unroll
+                    for (int ww = 0; ww < kFirWarps; ++ww) v += red[ww * OT + o];
+                    dstrow[o] = v;
+                }
+                named_bar_sync(1, kFirWarps * 32);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) acc[r] = 0.0f;
+                seg = 0;  // any further tile of this CTA starts at its stage 0
             }
+            if (++k == p.NS) { k = 0; ++w; }
         }
-        if (g == 0) {
-            float4* dst = reinterpret_cast<float4*>(red + (warp * A + a) * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-        }
-    }
-    __syncthreads();
-
-    // warps -> one partial per output, summed in warp order (deterministic)
-    constexpr int OT = A * 16;
-    float* dst = p.partial + (static_cast<size_t>(s) * p.T + t) * p.B + ot * OT;
-    for (int o = threadIdx.x; o < OT; o += kFirThreads) {
-        float v = 0.0f;
-#pragma unroll
-        for (int w = 0; w < kFirWarps; ++w) v += red[w * OT + o];
-        dst[o] = v;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Finish: y = sum over tap splits (fixed order), written track-major [T][B] or as this engine's
-// column tile of the sample-major [B][Tg] matrix (bench_conv1d_accel.cu:249 layout).
+// Finish: y = sum of the tile's partial rows (fixed order), written track-major [T][B] or as this
+// engine's column tile of the sample-major [B][Tg] matrix (bench_conv1d_accel.cu:249 layout); the
+// same pass forms the stereo-bus partial of its 8-track chunk so the mix needs no second read.
 // ---------------------------------------------------------------------------------------------
-__global__ void fir_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, int S, int T, int B,
-                                  int sample_major, int Tg, int toff) {
+__global__ void __launch_bounds__(128) fir_finish_mix_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                            int MS, int T, int B, int sample_major, int Tg, int toff,
+                                                            const float* __restrict__ gains,
+                                                            float* __restrict__ mix_scratch) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int chunk = blockIdx.y;
     if (n >= B) return;
-    float v = 0.0f;
-    for (int s = 0; s < S; ++s) v += partial[(static_cast<size_t>(s) * T + t) * B + n];
-    if (sample_major)
-        out[static_cast<size_t>(n) * Tg + toff + t] = v;
-    else
-        out[static_cast<size_t>(t) * B + n] = v;
+    const int t0 = chunk * kMixChunk;
+    float v[kMixChunk];
+#pragma unroll
+    for (int j = 0; j < kMixChunk; ++j) v[j] = 0.0f;
+    for (int s = 0; s < MS; ++s) {
+#pragma unroll
+        for (int j = 0; j < kMixChunk; ++j)
+            if (t0 + j < T) v[j] += partial[(static_cast<size_t>(s) * T + t0 + j) * B + n];
+    }
+    float l = 0.0f, r = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kMixChunk; ++j) {
+        const int t = t0 + j;
+        if (t < T) {
+            if (sample_major)
+                out[static_cast<size_t>(n) * Tg + toff + t] = v[j];
+            else
+                out[static_cast<size_t>(t) * B + n] = v[j];
+            if (mix_scratch) {
+                l = fmaf(gains[2 * t], v[j], l);
+                r = fmaf(gains[2 * t + 1], v[j], r);
+            }
+        }
+    }
+    if (mix_scratch) {
+        mix_scratch[(static_cast<size_t>(chunk) * 2 + 0) * B + n] = l;
+        mix_scratch[(static_cast<size_t>(chunk) * 2 + 1) * B + n] = r;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -209,7 +276,7 @@ cudaError_t launch_ring_append(const float* d_in, float* ring, int T, int B, int
 }
 
 template <int A>
-static cudaError_t launch_fir_t(const FirParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_fir_t(const FirParams& p, size_t smem, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(fir_direct_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -217,26 +284,36 @@ static cudaError_t launch_fir_t(const FirParams& p, dim3 grid, size_t smem, cuda
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    fir_direct_kernel<A><<<grid, kFirThreads, smem, st>>>(p);
+    fir_direct_kernel<A><<<p.G, kFirThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fir(const FirParams& p, int A, int S, int ntiles, size_t smem, cudaStream_t st) {
-    dim3 grid(S, ntiles, p.T);
+cudaError_t launch_fir(const FirParams& p, int A, size_t smem, cudaStream_t st) {
     switch (A) {
-        case 32: return launch_fir_t<32>(p, grid, smem, st);
-        case 16: return launch_fir_t<16>(p, grid, smem, st);
-        case 8: return launch_fir_t<8>(p, grid, smem, st);
-        case 4: return launch_fir_t<4>(p, grid, smem, st);
-        case 2: return launch_fir_t<2>(p, grid, smem, st);
+        case 32: return launch_fir_t<32>(p, smem, st);
+        case 16: return launch_fir_t<16>(p, smem, st);
+        case 8: return launch_fir_t<8>(p, smem, st);
+        case 4: return launch_fir_t<4>(p, smem, st);
+        case 2: return launch_fir_t<2>(p, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_fir_finish(const float* partial, float* out, int S, int T, int B, int sample_major, int Tg,
-                              int toff, cudaStream_t st) {
-    dim3 grid((B + 127) / 128, T);
-    fir_finish_kernel<<<grid, 128, 0, st>>>(partial, out, S, T, B, sample_major, Tg, toff);
+int fir_max_segments(int n_tiles_total, int NS, int G) {
+    const long long U = static_cast<long long>(n_tiles_total) * NS;
+    int ms = 1;
+    for (int w = 0; w < n_tiles_total; ++w) {
+        const long long first = fir_cta_of_unit(static_cast<long long>(w) * NS, U, G);
+        const long long last = fir_cta_of_unit(static_cast<long long>(w) * NS + NS - 1, U, G);
+        ms = std::max(ms, static_cast<int>(last - first + 1));
+    }
+    return ms;
+}
+
+cudaError_t launch_fir_finish_mix(const float* partial, float* out, int MS, int T, int B, int sample_major, int Tg,
+                                  int toff, const float* gains, float* mix_scratch, cudaStream_t st) {
+    dim3 grid((B + 127) / 128, (T + kMixChunk - 1) / kMixChunk);
+    fir_finish_mix_kernel<<<grid, 128, 0, st>>>(partial, out, MS, T, B, sample_major, Tg, toff, gains, mix_scratch);
     return cudaGetLastError();
 }
 

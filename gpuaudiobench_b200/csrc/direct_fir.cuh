@@ -10,26 +10,33 @@ constexpr int kFirWarps = 8;                        // consumer warps per CTA
 constexpr int kFirThreads = (kFirWarps + 1) * 32;   // + one TMA producer warp
 constexpr int kFirMaxStages = 8;                    // mbarrier slots reserved in shared memory
 constexpr size_t kFirMaxSmem = 112 * 1024;          // per CTA; two CTAs per SM fit in 227 KB
+constexpr int kFirCtasPerSm = 2;                    // persistent grid = kFirCtasPerSm * SM count
+constexpr int kMixChunk = 8;                        // tracks per stereo-bus partial
 
 // All "block" quantities are in units of 16 floats (64 B).
 struct FirParams {
-    const float* h;     // [T][Lc*16]  taps, zero padded, chunk-swizzled
+    const float* h;     // [T][Lc*16]  taps, zero padded; chunk-swizzled iff 32/A > 1 (lanes differ in taps)
     const float* ring;  // [T][capb*16] input history ring, chunk-swizzled
-    float* partial;     // [S][T][B]   per-tap-split partial outputs
+    float* partial;     // [MS][T][B]  one row per (CTA, track-tile) segment
     int T, B;
     int capb;           // ring capacity
     int posb;           // ring block index where the current buffer starts
-    int Lc;             // padded tap blocks per track = S * nst * JSb
+    int Lc;             // padded tap blocks per track = NS * JSb
     int JSb;            // tap blocks per pipeline stage = kFirWarps * (32/A) * SPS
-    int nst;            // stages per CTA
+    int NS;             // tap stages per track-tile
     int SPS;            // 16-tap steps per lane per stage (even)
     int nbuf;           // pipeline depth (<= kFirMaxStages)
     int xtile_blocks;   // shared-memory blocks reserved for the input window of one stage
+    int ntiles;         // 512-output tiles per track
+    int U;              // units = T * ntiles * NS
+    int G;              // CTAs (persistent grid)
 };
 
 cudaError_t launch_ring_append(const float* d_in, float* ring, int T, int B, int cap, int pos, cudaStream_t st);
-cudaError_t launch_fir(const FirParams& p, int A, int S, int ntiles, size_t smem, cudaStream_t st);
-cudaError_t launch_fir_finish(const float* partial, float* out, int S, int T, int B, int sample_major, int Tg,
-                              int toff, cudaStream_t st);
+cudaError_t launch_fir(const FirParams& p, int A, size_t smem, cudaStream_t st);
+// Most partial rows any track-tile receives when U = n_tiles_total * NS units are split over G CTAs.
+int fir_max_segments(int n_tiles_total, int NS, int G);
+cudaError_t launch_fir_finish_mix(const float* partial, float* out, int MS, int T, int B, int sample_major, int Tg,
+                                  int toff, const float* gains, float* mix_scratch, cudaStream_t st);
 
 }  // namespace b200conv

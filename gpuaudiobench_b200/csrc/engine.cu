@@ -53,7 +53,7 @@ int env_int(const char* name, int dflt) {
 }
 
 struct DirectState {
-    int A = 0, CL = 0, SPS = 0, JSb = 0, S = 1, nst = 0, Lc = 0, cap = 0, nbuf = 0, xtile_blocks = 0, ntiles = 0;
+    int A = 0, CL = 0, SPS = 0, JSb = 0, NS = 0, G = 0, MS = 1, Lc = 0, cap = 0, nbuf = 0, xtile_blocks = 0, ntiles = 0;
     size_t smem = 0;
     float* h = nullptr;
     float* ring = nullptr;
@@ -113,25 +113,6 @@ int dev_alloc(b200conv_engine* e, Tp** out, size_t count, bool zero = true) {
     return B200CONV_OK;
 }
 
-// Tap-split heuristic for the direct engine: minimise waves * (stages per CTA + fixed overhead).
-int pick_direct_split(int stages_total, int ctas_base, int sm_count) {
-    const int resident = 2 * sm_count;
-    const double overhead_stages = 1.5;
-    int best = 1;
-    double best_cost = 1e300;
-    for (int S = 1; S <= std::min(stages_total, 64); ++S) {
-        const int nst = (stages_total + S - 1) / S;
-        const long long ctas = static_cast<long long>(S) * ctas_base;
-        const long long waves = (ctas + resident - 1) / resident;
-        const double cost = static_cast<double>(waves) * (nst + overhead_stages);
-        if (cost < best_cost - 1e-9) {
-            best_cost = cost;
-            best = S;
-        }
-    }
-    return best;
-}
-
 int plan_direct(b200conv_engine* e) {
     DirectState& d = e->dir;
     const int B = e->B, L = e->L;
@@ -146,20 +127,26 @@ int plan_direct(b200conv_engine* e) {
         d.ntiles = 1;
     }
     d.CL = 32 / d.A;
-    d.SPS = (d.A == 2) ? 2 : 4;
+    // steps per lane per stage: even; for A = 4 / 2 the tap groups of a quarter-warp must land on
+    // distinct 16 B bank groups, which needs SPS = 4 (mod 8) / 2 (mod 4) (see common.cuh swizzle)
+    d.SPS = (d.A >= 16) ? 8 : (d.A == 2 ? 2 : 4);
+    int sps = env_int("B200CONV_DIRECT_SPS", 0);
+    if (sps > 0 && sps % 2 == 0 && d.A >= 8) d.SPS = sps;
     d.JSb = kFirWarps * d.CL * d.SPS;
     const int Lc0 = (L + 15) / 16;
-    const int stages_total = (Lc0 + d.JSb - 1) / d.JSb;
-    int S = env_int("B200CONV_DIRECT_SPLIT", 0);
-    if (S <= 0) S = pick_direct_split(stages_total, d.ntiles * e->T, e->sm_count);
-    S = std::max(1, std::min(S, stages_total));
-    d.S = S;
-    d.nst = (stages_total + S - 1) / S;
-    d.Lc = d.S * d.nst * d.JSb;
-    d.xtile_blocks = d.A + d.JSb + 8;
+    d.NS = (Lc0 + d.JSb - 1) / d.JSb;
+    d.Lc = d.NS * d.JSb;
+    const long long units = static_cast<long long>(e->T) * d.ntiles * d.NS;
+    if (units > 0x7fffffffLL) return fail(B200CONV_ERR_INVALID, "direct engine: job too large");
+    int per_sm = env_int("B200CONV_DIRECT_CTAS_PER_SM", kFirCtasPerSm);
+    per_sm = std::max(1, std::min(per_sm, 2));
+    d.G = static_cast<int>(std::min<long long>(units, static_cast<long long>(per_sm) * e->sm_count));
+    d.MS = fir_max_segments(e->T * d.ntiles, d.NS, d.G);
+    d.xtile_blocks = (d.A + d.JSb + 8 + 7) & ~7;
     const size_t stage_bytes = static_cast<size_t>(d.JSb + d.xtile_blocks) * 64;
     const size_t red_bytes = static_cast<size_t>(kFirWarps) * d.A * 16 * sizeof(float);
-    d.nbuf = std::min({d.nst, 4, kFirMaxStages});
+    const int per_cta = static_cast<int>((units + d.G - 1) / d.G);
+    d.nbuf = std::min({per_cta, 4, kFirMaxStages});
     while (d.nbuf > 1 && 128 + d.nbuf * stage_bytes + red_bytes > kFirMaxSmem) --d.nbuf;
     d.smem = 128 + d.nbuf * stage_bytes + red_bytes;
     if (d.smem > kFirMaxSmem) return fail(B200CONV_ERR_INVALID, "direct engine: stage does not fit shared memory");
@@ -280,9 +267,9 @@ int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]) {
         int rc = plan_direct(&tmp);
         if (rc) return rc;
         const DirectState& d = tmp.dir;
-        const int32_t v[12] = {d.A, d.CL, d.SPS, d.JSb, d.S, d.nst, d.Lc, d.cap, d.nbuf, d.xtile_blocks, d.ntiles,
-                               static_cast<int32_t>(d.smem)};
-        std::copy(v, v + 12, plan);
+        const int32_t v[13] = {d.A, d.CL, d.SPS, d.JSb, d.NS, d.G, d.Lc, d.cap, d.nbuf, d.xtile_blocks, d.ntiles,
+                               static_cast<int32_t>(d.smem), d.MS};
+        std::copy(v, v + 13, plan);
     } else if (cfg->algo == B200CONV_ALGO_UPOLS) {
         int rc = plan_upols(&tmp);
         if (rc) return rc;
@@ -345,14 +332,14 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
     if ((rc = dev_alloc(e, &e->d_out_stage, out_elems))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_mix_stage, static_cast<size_t>(2) * e->B))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_gains, static_cast<size_t>(2) * e->T))) return bail(rc);
-    if ((rc = dev_alloc(e, &e->d_mix_scratch, mix_scratch_floats(e->T, e->B)))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_mix_scratch, static_cast<size_t>((e->T + kMixChunk - 1) / kMixChunk) * 2 * e->B))) return bail(rc);
     if ((rc = set_default_gains(e))) return bail(rc);
 
     if (cfg->algo == B200CONV_ALGO_DIRECT) {
         DirectState& d = e->dir;
         if ((rc = dev_alloc(e, &d.h, static_cast<size_t>(e->T) * d.Lc * 16))) return bail(rc);
         if ((rc = dev_alloc(e, &d.ring, static_cast<size_t>(e->T) * d.cap))) return bail(rc);
-        if ((rc = dev_alloc(e, &d.partial, static_cast<size_t>(d.S) * tb))) return bail(rc);
+        if ((rc = dev_alloc(e, &d.partial, static_cast<size_t>(d.MS) * tb))) return bail(rc);
     } else {
         UpolsState& u = e->up;
         const size_t spec = static_cast<size_t>(e->T) * u.P * u.M;
@@ -398,7 +385,11 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
             for (int t = 0; t < nt; ++t) {
                 const float* src = host_ir + static_cast<size_t>(t0 + t) * L;
                 float* dst = stage.data() + static_cast<size_t>(t) * row;
-                for (int j = 0; j < L; ++j) dst[swz_float(static_cast<uint32_t>(j))] = src[j];
+                if (d.CL > 1) {
+                    for (int j = 0; j < L; ++j) dst[swz_float(static_cast<uint32_t>(j))] = src[j];
+                } else {
+                    std::memcpy(dst, src, static_cast<size_t>(L) * sizeof(float));  // taps are a broadcast read
+                }
             }
             CU_TRY(cudaMemcpy(d.h + static_cast<size_t>(t0) * row, stage.data(), static_cast<size_t>(nt) * row * sizeof(float),
                               cudaMemcpyHostToDevice));
@@ -550,17 +541,21 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
         p.posb = d.pos / 16;
         p.Lc = d.Lc;
         p.JSb = d.JSb;
-        p.nst = d.nst;
+        p.NS = d.NS;
         p.SPS = d.SPS;
         p.nbuf = d.nbuf;
         p.xtile_blocks = d.xtile_blocks;
-        CU_TRY(launch_fir(p, d.A, d.S, d.ntiles, d.smem, st));
+        p.ntiles = d.ntiles;
+        p.U = e->T * d.ntiles * d.NS;
+        p.G = d.G;
+        CU_TRY(launch_fir(p, d.A, d.smem, st));
         tm.mark();
-        CU_TRY(launch_fir_finish(d.partial, d_out, d.S, e->T, e->B, sample_major, e->Tg, e->toff, st));
+        CU_TRY(launch_fir_finish_mix(d.partial, d_out, d.MS, e->T, e->B, sample_major, e->Tg, e->toff, e->d_gains,
+                                     d_mix ? e->d_mix_scratch : nullptr, st));
         e->launches += 3;
         if (d_mix) {
-            CU_TRY(launch_mix(d_out, sample_major, e->Tg, e->toff, e->d_gains, e->d_mix_scratch, d_mix, e->T, e->B, st));
-            e->launches += 2;
+            CU_TRY(launch_mix_final(e->d_mix_scratch, d_mix, (e->T + kMixChunk - 1) / kMixChunk, e->B, st));
+            e->launches += 1;
         }
         tm.mark();
         marks = tm.idx;
@@ -659,7 +654,7 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
     if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
         info->flops_per_block = 2 * T * B * L;
         info->alg_bytes_per_block = 0;
-        info->partitions = e->dir.S;
+        info->partitions = e->dir.MS;
         info->fft_size = 0;
         info->kernels_per_block = 3;
         std::snprintf(info->stage_name[0], 24, "ring_append");

@@ -54,6 +54,6 @@ cudaError_t launch_irfft_ols(const IrfftParams& p, cudaStream_t st);
 // Deterministic stereo bus: mix[c][n] = sum_t gains[t][c] * y_t[n] over this engine's tracks.
 cudaError_t launch_mix(const float* y, int sample_major, int Tg, int toff, const float* gains, float* scratch,
                        float* mix, int T, int B, cudaStream_t st);
-size_t mix_scratch_floats(int T, int B);
+cudaError_t launch_mix_final(const float* scratch, float* mix, int nchunks, int B, cudaStream_t st);
 
 }  // namespace b200conv

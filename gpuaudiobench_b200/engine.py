@@ -86,7 +86,7 @@ def plan(tracks, block, ir_len, algo, sm_count=148):
     arr = (C.c_int32 * 16)()
     _check(load_library().b200conv_plan(C.byref(cfg), sm_count, arr))
     if algo == ALGO_DIRECT:
-        keys = ("A", "CL", "SPS", "JSb", "S", "nst", "Lc", "cap", "nbuf", "xtile_blocks", "ntiles", "smem")
+        keys = ("A", "CL", "SPS", "JSb", "NS", "G", "Lc", "cap", "nbuf", "xtile_blocks", "ntiles", "smem", "MS")
     else:
         keys = ("P", "M", "logM", "S")
     return dict(zip(keys, list(arr)))

@@ -82,7 +82,7 @@ typedef struct b200conv_info {
     uint64_t device_bytes;        /* engine-owned device memory                                       */
     uint64_t blocks_processed;    /* committed blocks since the last reset                            */
     uint64_t kernel_launches;     /* kernels launched by this engine since creation                   */
-    uint32_t partitions;          /* UPOLS: P = ceil(L/B); direct: tap splits S                       */
+    uint32_t partitions;          /* UPOLS: P = ceil(L/B); direct: partial rows per track-tile (MS)   */
     uint32_t fft_size;            /* UPOLS: N = 2B; direct: 0                                         */
     uint32_t kernels_per_block;   /* launches per b200conv_process                                    */
     uint32_t sm_count;
@@ -149,7 +149,7 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info);
 int b200conv_set_profiling(b200conv_engine* e, int on);
 
 /* Launch plan the engine would use for `cfg` on a device with `sm_count` SMs; needs no GPU.
- * plan[0..15] = direct: {A, CL, SPS, JSb, S, nst, Lc, cap, nbuf, xtile_blocks, ntiles, smem_bytes, 0...}
+ * plan[0..15] = direct: {A, CL, SPS, JSb, NS, G, Lc, cap, nbuf, xtile_blocks, ntiles, smem_bytes, MS, 0...}
  *               UPOLS : {P, M, logM, S, 0...}.  Used by the host-logic tests and by capacity planning. */
 int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]);
 

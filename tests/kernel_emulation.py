@@ -39,8 +39,12 @@ def toeplitz_tile(acc, hv, lo, hi):
             acc[r] += hv[s] * w[16 + r - s]
 
 
+def fir_cta_of_unit(u, U, G):
+    return ((u + 1) * G + U - 1) // U - 1
+
+
 class DirectEmu:
-    """Emulates ring_append_kernel + fir_direct_kernel<A> + fir_finish_kernel for one engine."""
+    """Emulates ring_append_kernel + the persistent fir_direct_kernel<A> + fir_finish_mix_kernel."""
 
     def __init__(self, T, B, L, plan):
         self.T, self.B, self.L = T, B, L
@@ -52,8 +56,11 @@ class DirectEmu:
 
     def load_ir(self, ir):
         self.h[:] = 0
-        for j in range(self.L):
-            self.h[:, swz_float(j)] = ir[:, j]
+        if self.p["CL"] > 1:
+            for j in range(self.L):
+                self.h[:, swz_float(j)] = ir[:, j]
+        else:
+            self.h[:, :self.L] = ir  # taps are a broadcast read: stored linear
 
     def prime(self, hist):
         self.ring[:] = 0
@@ -62,55 +69,67 @@ class DirectEmu:
             self.ring[:, swz_float(self.cap - H + i)] = hist[:, i]
         self.pos = 0
 
+    def _load_taps(self, hs, blk):
+        return load_block(hs, blk) if self.p["CL"] > 1 else hs[16 * blk:16 * blk + 16]
+
     def process(self, x, commit=True):
         p, T, B = self.p, self.T, self.B
-        A, CL, SPS, JSb, S, nst = p["A"], p["CL"], p["SPS"], p["JSb"], p["S"], p["nst"]
+        A, CL, SPS, JSb, NS, G, MS, ntiles = p["A"], p["CL"], p["SPS"], p["JSb"], p["NS"], p["G"], p["MS"], p["ntiles"]
         capb, posb = self.cap // 16, self.pos // 16
-        # ring_append_kernel
-        for f in range(B // 4):
+        for f in range(B // 4):  # ring_append_kernel
             pf = swz_chunk(self.pos // 4 + f)
             self.ring[:, 4 * pf:4 * pf + 4] = x[:, 4 * f:4 * f + 4]
-        partial = np.zeros((S, T, B))
+        partial = np.zeros((MS, T, B))
+        written = np.zeros((MS, T, B), dtype=bool)
         OT = A * 16
-        for t in range(T):
-            for ot in range(p["ntiles"]):
-                for s in range(S):
-                    a0 = ot * A
-                    cs0 = s * nst * JSb
-                    qbase = posb + capb + a0
-                    red = np.zeros((KFIR_WARPS, OT))
-                    acc = np.zeros((KFIR_WARPS, 32, 16))
-                    for k in range(nst):
-                        c0 = cs0 + k * JSb
-                        qs = (qbase - c0 - JSb) & ~7
-                        nblk = (qbase + A - 1 - c0) - qs + 1
-                        assert 0 < nblk <= p["xtile_blocks"], (nblk, p["xtile_blocks"])
-                        src_b = qs % capb
-                        first = min(nblk, capb - src_b)
-                        hs = self.h[t, c0 * 16:(c0 + JSb) * 16]
-                        xs = np.empty(nblk * 16)
-                        xs[:first * 16] = self.ring[t, src_b * 16:(src_b + first) * 16]
-                        if first < nblk:
-                            xs[first * 16:] = self.ring[t, :(nblk - first) * 16]
-                        for warp in range(KFIR_WARPS):
-                            for lane in range(32):
-                                a, g = lane & (A - 1), lane // A
-                                hb = (warp * CL + g) * SPS
-                                sb = qbase + a - (c0 + hb) - qs
-                                assert sb - SPS >= 0 and sb < nblk
-                                Q = load_block(xs, sb)
-                                for q in range(0, SPS, 2):
-                                    hv = load_block(hs, hb + q)
-                                    P = load_block(xs, sb - q - 1)
-                                    toeplitz_tile(acc[warp, lane], hv, P, Q)
-                                    hv = load_block(hs, hb + q + 1)
-                                    Q = load_block(xs, sb - q - 2)
-                                    toeplitz_tile(acc[warp, lane], hv, Q, P)
+        U = T * ntiles * NS
+        for cta in range(G):
+            u_lo, u_hi = cta * U // G, (cta + 1) * U // G
+            w, k = divmod(u_lo, NS)
+            seg = cta - fir_cta_of_unit(w * NS, U, G)
+            assert 0 <= seg < MS
+            acc = np.zeros((KFIR_WARPS, 32, 16))
+            for it in range(u_hi - u_lo):
+                t, ot = divmod(w, ntiles)
+                c0 = k * JSb
+                qbase = posb + capb + ot * A
+                qs = (qbase - c0 - JSb) & ~7
+                nblk = (qbase + A - 1 - c0) - qs + 1
+                assert 0 < nblk <= p["xtile_blocks"], (nblk, p["xtile_blocks"])
+                src_b = qs % capb
+                first = min(nblk, capb - src_b)
+                hs = self.h[t, c0 * 16:(c0 + JSb) * 16]
+                xs = np.empty(nblk * 16)
+                xs[:first * 16] = self.ring[t, src_b * 16:(src_b + first) * 16]
+                if first < nblk:
+                    xs[first * 16:] = self.ring[t, :(nblk - first) * 16]
+                for warp in range(KFIR_WARPS):
+                    for lane in range(32):
+                        a, g = lane & (A - 1), lane // A
+                        hb0 = (warp * CL + g) * SPS
+                        sb = qbase + a - (c0 + hb0) - qs
+                        assert sb - SPS >= 0 and sb < nblk
+                        Q = load_block(xs, sb)
+                        for q in range(0, SPS, 2):
+                            hv = self._load_taps(hs, hb0 + q)
+                            P = load_block(xs, sb - q - 1)
+                            toeplitz_tile(acc[warp, lane], hv, P, Q)
+                            hv = self._load_taps(hs, hb0 + q + 1)
+                            Q = load_block(xs, sb - q - 2)
+                            toeplitz_tile(acc[warp, lane], hv, Q, P)
+                if k + 1 == NS or it + 1 == u_hi - u_lo:  # flush the (CTA, tile) segment
+                    row = np.zeros(OT)
                     for warp in range(KFIR_WARPS):
                         for a in range(A):
-                            tot = sum(acc[warp, g * A + a] for g in range(CL))
-                            red[warp, a * 16:(a + 1) * 16] = tot
-                    partial[s, t, ot * OT:(ot + 1) * OT] = red.sum(axis=0)
+                            row[a * 16:(a + 1) * 16] += sum(acc[warp, g * A + a] for g in range(CL))
+                    assert not written[seg, t, ot * OT:(ot + 1) * OT].any(), "two segments wrote one partial row"
+                    partial[seg, t, ot * OT:(ot + 1) * OT] = row
+                    written[seg, t, ot * OT:(ot + 1) * OT] = True
+                    acc[:] = 0
+                    seg = 0
+                k += 1
+                if k == NS:
+                    k, w = 0, w + 1
         if commit:
             self.pos = (self.pos + B) % self.cap
         return partial.sum(axis=0)

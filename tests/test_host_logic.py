@@ -61,7 +61,8 @@ def test_direct_plan_invariants(T, B, L):
     p = g.plan(T, B, L, g.ALGO_DIRECT)
     assert p["A"] * p["CL"] == 32 and p["SPS"] % 2 == 0
     assert p["JSb"] == 8 * p["CL"] * p["SPS"]
-    assert p["Lc"] == p["S"] * p["nst"] * p["JSb"] and p["Lc"] * 16 >= L
+    assert p["Lc"] == p["NS"] * p["JSb"] and p["Lc"] * 16 >= L
+    assert 1 <= p["G"] <= 2 * 148 and p["G"] <= T * p["ntiles"] * p["NS"] and p["MS"] >= 1
     assert p["cap"] % B == 0 and p["cap"] % 128 == 0 and p["cap"] >= p["Lc"] * 16 + B + 128
     assert p["smem"] <= 112 * 1024 and 1 <= p["nbuf"] <= 8
     assert p["ntiles"] * p["A"] * 16 == B
@@ -94,14 +95,13 @@ def _truth(xs, h, hist=None):
     return out
 
 
-@pytest.mark.parametrize("T,B,L,nb,split", [(1, 512, 1024, 2, 0), (2, 32, 100, 3, 0), (1, 256, 3000, 2, 1),
-                                             (1, 512, 16, 6, 0), (1, 128, 5000, 2, 2)])
-def test_direct_kernel_index_math(monkeypatch, T, B, L, nb, split):
-    """Swizzled ring + tile geometry + lane block walk of fir_direct_kernel (incl. multi-stage CTAs,
-    tap splits, ring wrap-around at pos -> 0, primed history read across the ring seam)."""
-    if split:
-        monkeypatch.setenv("B200CONV_DIRECT_SPLIT", str(split))
-    p = g.plan(T, B, L, g.ALGO_DIRECT)
+@pytest.mark.parametrize("T,B,L,nb,sms", [(1, 512, 1024, 2, 148), (2, 32, 100, 3, 148), (3, 256, 9000, 2, 1),
+                                           (1, 512, 16, 6, 148), (5, 128, 9000, 2, 2), (2, 1024, 2100, 2, 1)])
+def test_direct_kernel_index_math(T, B, L, nb, sms):
+    """Swizzled ring + tile geometry + lane block walk of the persistent fir_direct_kernel: spans
+    that start/end mid-track (small `sms` forces several tiles and segments per CTA), ring
+    wrap-around at pos -> 0, primed history read across the ring seam, two output tiles per track."""
+    p = g.plan(T, B, L, g.ALGO_DIRECT, sm_count=sms)
     rng = np.random.default_rng(1)
     h, xs, hist = rng.standard_normal((T, L)), rng.standard_normal((nb, T, B)), rng.standard_normal((T, L - 1))
     e = DirectEmu(T, B, L, p)

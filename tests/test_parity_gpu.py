@@ -136,18 +136,20 @@ def test_streaming_blocks_match_oracle(oracle, algo, T, B, L, M):
     assert_parity(got[:, -B:], want[:, -B:], algo, "last block")
 
 
-@pytest.mark.parametrize("split", [1, 3, 8])
-def test_direct_tap_splits_agree(oracle, monkeypatch, split):
-    monkeypatch.setenv("B200CONV_DIRECT_SPLIT", str(split))
-    T, B, L, M = 2, 512, 9000, 3
+@pytest.mark.parametrize("ctas_per_sm,sps", [(1, 8), (2, 4), (2, 8)])
+def test_direct_schedules_agree(oracle, monkeypatch, ctas_per_sm, sps):
+    """The persistent span schedule (grid size, stage depth) must not change the result beyond fp32
+    re-association: 37 tracks x 9000 taps gives spans that start and end mid-track."""
+    monkeypatch.setenv("B200CONV_DIRECT_CTAS_PER_SM", str(ctas_per_sm))
+    monkeypatch.setenv("B200CONV_DIRECT_SPS", str(sps))
+    T, B, L, M = 37, 512, 9000, 3
     xs = oracle.generate_input(M * T * B, 3).reshape(M, T, B)
     h = oracle.generate_ir(T, L, "direct")
     want = np.stack([oracle.stream(xs[:, t, :].ravel(), h[t]) for t in range(T)])
     with g.ConvEngine(T, B, L, g.ALGO_DIRECT) as e:
         e.load_ir(h)
-        assert e.query()["partitions"] == split
         got = np.concatenate([y for y, _ in run_stream(e, xs)], axis=1)
-    assert_parity(got, want, g.ALGO_DIRECT, f"split {split}")
+    assert_parity(got, want, g.ALGO_DIRECT, f"ctas/SM {ctas_per_sm} sps {sps}")
 
 
 @pytest.mark.parametrize("split", [1, 2, 5])
