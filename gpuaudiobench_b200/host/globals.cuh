@@ -1,0 +1,32 @@
+#pragma once
+// Command-line globals and the CSV / JSON result writers of the gpubench CLI.
+// Same names, defaults and output formats as the reference (cuda/globals.cuh:19-24, globals.cu:4-9,
+// CSV header globals.cu:101, JSON keys globals.cu:159-180) so table-generating scripts keep working.
+#include <string>
+#include <vector>
+
+extern int FS;                   // --fs          (48000)
+extern int NTRACKS;              // --nTracks     (128)
+extern int BUFSIZE;              // --bufferSize  (512)
+extern int NRUNS;                // --nRuns       (100)
+extern std::string OUTPUT_FILE;  // --outputfile  ("")
+extern bool JSON_OUTPUT;         // --json
+// Additions of this build (the reference has no CLI knob for them):
+extern int IR_LEN;               // --irLen   (0 = the plugin's default: 1024 direct, 512 accel)
+extern int WARMUP_RUNS;          // --warmup  (3, the value main.cu:130 hard-codes)
+extern bool STREAM_MODE;         // --mode stream: advance the convolution state every iteration
+
+struct LatencySummary {
+    float min_ms, max_ms, avg_ms, p50_ms, p95_ms, p99_ms, threshold_ms;
+    bool meets_deadline;
+    size_t count;
+};
+
+// nearest-rank percentiles sorted[n*q] and deadline 1000*BUFSIZE/FS, as globals.cu:83-89
+LatencySummary summarizeLatencies(const std::vector<float>& latencies_ms);
+
+void writeVectorToFile(const std::vector<float>& vec, const std::string& filename);
+void printVectorStats(const std::vector<float>& vec);
+void writeCSVResults(const std::vector<float>& vec, const std::string& benchmarkName, const std::string& filename);
+std::string generateJSONResults(const std::vector<float>& vec, const std::string& benchmarkName);
+void writeJSONResults(const std::vector<float>& vec, const std::string& benchmarkName, const std::string& filename = "");

@@ -1,0 +1,126 @@
+// plugin_capi.cu — include/gpubench_plugin.h over the plugin classes (libgpubench_b200.so).
+#include "gpubench_plugin.h"
+
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "bench_conv1d.cuh"
+#include "bench_conv1d_accel.cuh"
+#include "conv_common.cuh"
+#include "registry.cuh"
+
+struct gpubench_plugin {
+    std::unique_ptr<GPUABenchmark> bench;
+    Conv1DBenchmark* direct = nullptr;
+    Conv1DAccelBenchmark* accel = nullptr;
+};
+
+namespace {
+thread_local std::string g_err;
+
+template <typename F> int guarded(F&& body) {
+    try {
+        body();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char* gpubench_last_error(void) { return g_err.c_str(); }
+
+void gpubench_set_globals(int fs, int nruns, int stream_mode) {
+    if (fs > 0) FS = fs;
+    if (nruns > 0) NRUNS = nruns;
+    STREAM_MODE = (stream_mode != 0);
+}
+
+gpubench_plugin* gpubench_create(const char* name, int ir_len, int buffer_size, int track_count) {
+    if (!name) return nullptr;
+    BUFSIZE = buffer_size;
+    NTRACKS = track_count;
+    IR_LEN = ir_len > 0 ? ir_len : 0;
+    auto bench = createBenchmark(name);
+    if (!bench) {
+        g_err = std::string("Unknown benchmark: ") + name;
+        return nullptr;
+    }
+    auto* p = new gpubench_plugin();
+    p->direct = dynamic_cast<Conv1DBenchmark*>(bench.get());
+    p->accel = dynamic_cast<Conv1DAccelBenchmark*>(bench.get());
+    p->bench = std::move(bench);
+    return p;
+}
+
+void gpubench_destroy(gpubench_plugin* p) { delete p; }
+
+int gpubench_setup(gpubench_plugin* p) {
+    return guarded([&] { p->bench->setupBenchmark(); });
+}
+
+int gpubench_iterate(gpubench_plugin* p) {
+    return guarded([&] { p->bench->performBenchmarkIteration(); });
+}
+
+int gpubench_run(gpubench_plugin* p, int iterations, int warmup, float* wall_ms, float* gpu_ms) {
+    return guarded([&] {
+        auto r = p->bench->runBenchmark(iterations, warmup);
+        for (int i = 0; i < iterations; ++i) {
+            if (wall_ms) wall_ms[i] = r.latencies[i];
+            if (gpu_ms) gpu_ms[i] = i < static_cast<int>(r.gpu_latencies.size()) ? r.gpu_latencies[i] : 0.0f;
+        }
+    });
+}
+
+int gpubench_validate(gpubench_plugin* p, gpubench_validation* out, char* messages, size_t cap) {
+    return guarded([&] {
+        GPUABenchmark::ValidationData v;
+        p->bench->validate(v);
+        if (out) {
+            out->status = static_cast<int>(v.status);
+            out->max_error = v.max_error;
+            out->mean_error = v.mean_error;
+            const float* ref = p->direct ? p->direct->cpuReference() : p->accel->cpuReference();
+            const ConvCommon::Accuracy a = ConvCommon::measureAccuracy(p->bench->hostOutput(), ref, p->bench->getTotalElements());
+            out->snr_db = a.snr_db;
+            out->max_abs_err = a.max_abs_err;
+            out->ref_peak = a.ref_peak;
+        }
+        if (messages && cap) {
+            std::string joined;
+            for (const auto& m : v.messages) joined += m + "\n";
+            std::strncpy(messages, joined.c_str(), cap - 1);
+            messages[cap - 1] = '\0';
+        }
+    });
+}
+
+const float* gpubench_host_input(gpubench_plugin* p) { return p->bench->hostInput(); }
+const float* gpubench_host_ir(gpubench_plugin* p) { return p->direct ? p->direct->hostIR() : p->accel->hostIR(); }
+const float* gpubench_host_output(gpubench_plugin* p) { return p->bench->hostOutput(); }
+const float* gpubench_cpu_reference(gpubench_plugin* p) { return p->direct ? p->direct->cpuReference() : p->accel->cpuReference(); }
+
+int gpubench_json_results(const float* lat, size_t n, const char* name, int fs, int bufsize, int ntracks, char* out, size_t cap) {
+    FS = fs;
+    BUFSIZE = bufsize;
+    NTRACKS = ntracks;
+    const std::string js = generateJSONResults(std::vector<float>(lat, lat + n), name);
+    if (js.size() + 1 > cap) return -1;
+    std::memcpy(out, js.c_str(), js.size() + 1);
+    return static_cast<int>(js.size());
+}
+
+int gpubench_statistics(const float* lat, size_t n, float out8[8]) {
+    const BenchmarkUtils::Statistics s = BenchmarkUtils::calculateStatistics(std::vector<float>(lat, lat + n));
+    const float v[8] = {s.mean, s.median, s.std_dev, s.min_val, s.max_val, s.p95, s.p99, static_cast<float>(s.count)};
+    std::memcpy(out8, v, sizeof(v));
+    return 0;
+}
+
+}  // extern "C"

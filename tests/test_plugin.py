@@ -1,0 +1,124 @@
+"""The reference-shaped plugin surface: gpubench CLI + GPUABenchmark lifecycle (host/), CPU and GPU."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from gpuaudiobench_b200 import plugin
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_cli(*args):
+    return subprocess.run([plugin.GPUBENCH, *args], capture_output=True, text=True, timeout=600)
+
+
+# ---------------------------------------------------------------- CPU ------------------------
+def test_plugin_library_exports_every_declared_symbol():
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "gpubench_plugin.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(gpubench_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 14, names
+    lib = ctypes.CDLL(plugin.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_cli_list_help_and_exit_codes():
+    r = run_cli("--list")
+    assert r.returncode == 0 and r.stdout.split("\n")[:4] == ["GPGPU Audio Benchmark", "Available benchmarks:", "Conv1D", "Conv1D_accel"]
+    r = run_cli("--help")
+    assert r.returncode == 0
+    for flag in ("--benchmark", "--fs", "--bufferSize", "--nTracks", "--nRuns", "--outputfile", "--json", "--irLen"):
+        assert flag in r.stdout
+    r = run_cli("--nTracks")  # missing value: reference exits 1 (main.cu:276-279)
+    assert r.returncode == 1 and "Error: --nTracks requires an argument" in r.stdout
+
+
+def test_json_writer_matches_reference_text(golden):
+    """generateJSONResults (globals.cu:124-182): byte-identical to the reference's own output."""
+    got = plugin.json_results(golden["stats_lat"], "Conv1D", 48000, 512, 128)
+    assert got == str(golden["stats_json"][0])
+    parsed = json.loads(got)
+    assert set(parsed) == {"benchmark", "configuration", "statistics", "deadline"}
+    assert parsed["deadline"]["meets_deadline"] is True and abs(parsed["deadline"]["threshold_ms"] - 10.666667) < 1e-5
+
+
+def test_statistics_match_reference(golden, oracle):
+    st = plugin.statistics(golden["stats_lat"])
+    got = np.array([st[k] for k in ("mean", "median", "std", "min", "max", "p95", "p99", "count")], dtype=np.float32)
+    assert np.array_equal(got, golden["stats_out"])
+    lat = (oracle.generate_input(33, 5) + 2).astype(np.float32)
+    assert plugin.statistics(lat) == oracle.statistics(lat)
+
+
+def test_unknown_benchmark_is_rejected():
+    with pytest.raises(ValueError):
+        plugin.Plugin("RndMemRead")
+
+
+# ---------------------------------------------------------------- GPU ------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,B,L", [(128, 512, 1024), (1, 512, 1024), (16, 256, 3000)])
+def test_conv1d_plugin_lifecycle(oracle, T, B, L):
+    with plugin.Plugin("Conv1D", L, B, T) as p:
+        p.setup()
+        x = oracle.generate_input(T * B)
+        assert np.array_equal(p.host_input().ravel(), x)                       # generateTestData(42)
+        assert np.array_equal(p.host_ir(), oracle.generate_ir(T, L, "direct"))  # bench_conv1d.cu:159-178, bit-exact
+        ref = oracle.r1(x, p.host_ir(), L, B, T)
+        assert np.array_equal(p.cpu_reference(), ref)                          # the plugin's CPU loop == oracle R1
+        wall, gpu = p.run(5, 3)
+        assert (wall > 0).all() and (gpu > 0).all() and (gpu <= wall + 1e-3).all()
+        v = p.validate()
+        assert v["status"] == 0, v
+        assert v["snr_db"] >= 100 and v["max_abs_err"] <= 1e-5 * v["ref_peak"]
+        assert v["max_error"] <= 1e-3  # the reference's own abs check
+        out = p.host_output()
+    assert np.abs(out.astype(np.float64) - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,B,L", [(128, 512, 512), (1, 512, 1024), (64, 256, 4096)])
+def test_conv1d_accel_plugin_lifecycle(oracle, T, B, L):
+    with plugin.Plugin("Conv1D_accel", L, B, T) as p:
+        p.setup()
+        x = oracle.generate_input(T * B)
+        assert np.array_equal(p.host_ir(), oracle.generate_ir(T, L, "accel"))   # bench_conv1d_accel.cu:152-165
+        ref = oracle.r2(x, p.host_ir(), L, B, T)
+        assert np.array_equal(p.cpu_reference(), ref)                           # sample-major [B][T]
+        p.run(4, 3)
+        v = p.validate()
+        assert v["status"] == 0, v
+        assert v["snr_db"] >= 90 and v["max_abs_err"] <= 1e-4 * v["ref_peak"]
+        assert any("reference metric" in m for m in v["messages"])
+
+
+@pytest.mark.gpu
+def test_stream_mode_validates_after_streaming(oracle):
+    with plugin.Plugin("Conv1D", 2048, 512, 8, stream_mode=True) as p:
+        p.setup()
+        p.run(6, 2)
+        assert p.validate()["status"] == 0
+    plugin.load_library().gpubench_set_globals(48000, 0, 0)
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_json_and_csv(tmp_path):
+    r = run_cli("--benchmark", "Conv1D", "--nTracks", "128", "--irLen", "16384", "--nRuns", "20", "--json")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Validation passed for Conv1D" in r.stdout and "Conv1D benchmark completed successfully!" in r.stdout
+    js = json.loads(r.stdout[r.stdout.index("{\n"):r.stdout.rindex("}") + 1])
+    assert js["benchmark"] == "Conv1D" and js["configuration"] == {"fs": 48000, "bufferSize": 512, "nTracks": 128, "nRuns": 20}
+    assert js["deadline"]["meets_deadline"] is True and js["statistics"]["p99_ms"] < 10.667
+    csv = tmp_path / "out.csv"
+    r = run_cli("--benchmark", "Conv1D_accel", "--bufferSize", "256", "--nTracks", "64", "--irLen", "8192", "--nRuns", "10",
+                "--outputfile", str(csv))
+    assert r.returncode == 0 and "Validation passed for Conv1D_accel" in r.stdout
+    lines = csv.read_text().strip().split("\n")
+    assert lines[0] == "benchmark,fs,bufferSize,nTracks,nRuns,min_ms,max_ms,avg_ms,p50_ms,p95_ms,p99_ms,threshold_ms,meets_deadline"
+    assert lines[1].startswith("Conv1D_accel,48000,256,64,10,") and lines[1].endswith(",true")
+    assert os.path.exists("/tmp/Conv1D_accel_latencies.txt")
