@@ -93,7 +93,7 @@ __host__ __device__ __forceinline__ long long fir_cta_of_unit(long long u, long 
 }
 
 template <int A>
-__global__ void __launch_bounds__(kFirThreads, 2) fir_direct_kernel(FirParams p) {
+__global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(FirParams p) {
     constexpr int CL = 32 / A;  // tap groups per warp
     constexpr int OT = A * 16;  // outputs per tile
     constexpr bool kSwzTaps = (CL > 1);
@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(kFirThreads, 2) fir_direct_kernel(FirParams p)
                 const int c0 = k * p.JSb;
                 const int qbase = p.posb + p.capb + ot * A;      // unwrapped ring block of output block a0
                 const int qs = (qbase - c0 - p.JSb) & ~7;        // tile start, 512 B aligned in the ring
-                const int nblk = (qbase + A - 1 - c0) - qs + 1;  // <= xtile_blocks
+                // blocks at or after the current buffer (q >= posb + capb) are NOT in the ring yet: the
+                // consumers copy them from d_in, so the ring append is off the critical path
+                const int q_hi = min(qbase + A - 1 - c0, p.posb + p.capb - 1);
+                const int nblk = q_hi - qs + 1;  // <= xtile_blocks, >= 1 (a tile always reaches into the past)
                 int src_b = qs % p.capb;
                 const int first = min(nblk, p.capb - src_b);
                 unsigned char* hs = stage_base + static_cast<size_t>(slot) * stage_bytes;
@@ -174,6 +177,21 @@ __global__ void __launch_bounds__(kFirThreads, 2) fir_direct_kernel(FirParams p)
             const unsigned char* hs = stage_base + static_cast<size_t>(slot) * stage_bytes;
             const unsigned char* xs = hs + p.JSb * 64;
             const int sb = qbase + a - (c0 + hb0) - qs;  // smem block index of D_{a-c} for c = c0 + hb0
+
+            // current-buffer blocks of this tile: unwrapped ring blocks [cur_lo, cur_hi] <-> d_in
+            const int cur_lo = max(qs, p.posb + p.capb);
+            const int cur_hi = qbase + A - 1 - c0;
+            if (cur_lo <= cur_hi) {  // CTA-uniform; only the first tap stage(s) of a tile
+                const float4* src = reinterpret_cast<const float4*>(p.d_in + static_cast<size_t>(t) * p.B) +
+                                    (cur_lo - p.posb - p.capb) * 4;
+                const int nchunk = (cur_hi - cur_lo + 1) * 4;
+                const uint32_t f0 = static_cast<uint32_t>(cur_lo - qs) * 4;  // tile-relative chunk index
+                for (int c = threadIdx.x; c < nchunk; c += kFirWarps * 32) {
+                    const uint32_t f = f0 + c;
+                    *reinterpret_cast<float4*>(const_cast<unsigned char*>(xs) + (swz_chunk(f) << 4)) = src[c];
+                }
+                named_bar_sync(1, kFirWarps * 32);
+            }
 
             float P[16], Q[16], hv[16];
             load_block_swz(Q, xs, sb);
@@ -224,44 +242,70 @@ __global__ void __launch_bounds__(kFirThreads, 2) fir_direct_kernel(FirParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Finish: y = sum of the tile's partial rows (fixed order), written track-major [T][B] or as this
-// engine's column tile of the sample-major [B][Tg] matrix (bench_conv1d_accel.cu:249 layout); the
-// same pass forms the stereo-bus partial of its 8-track chunk so the mix needs no second read.
+// Finish (one launch does everything after the FIR):
+//   y = sum of the tile's partial rows in a fixed order, written track-major [T][B] or as this
+//       engine's column tile of the sample-major [B][Tg] matrix (bench_conv1d_accel.cu:249 layout);
+//   stereo-bus partial of this CTA's 8-track chunk; the LAST CTA to finish (ticket counter) adds
+//       the chunk partials in chunk order -> deterministic bus, no second launch, no float atomics;
+//   ring append of the buffer just consumed (skipped for PEEK): ring[t][swz(pos + n)] = in[t][n].
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) fir_finish_mix_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                                            int MS, int T, int B, int sample_major, int Tg, int toff,
-                                                            const float* __restrict__ gains,
-                                                            float* __restrict__ mix_scratch) {
+__global__ void __launch_bounds__(128) fir_finish_mix_kernel(FinishParams p) {
+    __shared__ int s_last;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = blockIdx.y;
-    if (n >= B) return;
     const int t0 = chunk * kMixChunk;
-    float v[kMixChunk];
+    const int T = p.T, B = p.B;
+    if (n < B) {
+        float v[kMixChunk];
 #pragma unroll
-    for (int j = 0; j < kMixChunk; ++j) v[j] = 0.0f;
-    for (int s = 0; s < MS; ++s) {
+        for (int j = 0; j < kMixChunk; ++j) v[j] = 0.0f;
+        for (int s = 0; s < p.MS; ++s) {
 #pragma unroll
-        for (int j = 0; j < kMixChunk; ++j)
-            if (t0 + j < T) v[j] += partial[(static_cast<size_t>(s) * T + t0 + j) * B + n];
-    }
-    float l = 0.0f, r = 0.0f;
+            for (int j = 0; j < kMixChunk; ++j)
+                if (t0 + j < T) v[j] += p.partial[(static_cast<size_t>(s) * T + t0 + j) * B + n];
+        }
+        float l = 0.0f, r = 0.0f;
+        const uint32_t ring_idx = swz_float(static_cast<uint32_t>(p.pos + n));
 #pragma unroll
-    for (int j = 0; j < kMixChunk; ++j) {
-        const int t = t0 + j;
-        if (t < T) {
-            if (sample_major)
-                out[static_cast<size_t>(n) * Tg + toff + t] = v[j];
-            else
-                out[static_cast<size_t>(t) * B + n] = v[j];
-            if (mix_scratch) {
-                l = fmaf(gains[2 * t], v[j], l);
-                r = fmaf(gains[2 * t + 1], v[j], r);
+        for (int j = 0; j < kMixChunk; ++j) {
+            const int t = t0 + j;
+            if (t < T) {
+                if (p.sample_major)
+                    p.out[static_cast<size_t>(n) * p.Tg + p.toff + t] = v[j];
+                else
+                    p.out[static_cast<size_t>(t) * B + n] = v[j];
+                if (p.mix) {
+                    l = fmaf(p.gains[2 * t], v[j], l);
+                    r = fmaf(p.gains[2 * t + 1], v[j], r);
+                }
+                if (p.ring) p.ring[static_cast<size_t>(t) * p.cap + ring_idx] = p.d_in[static_cast<size_t>(t) * B + n];
             }
         }
+        if (p.mix) {
+            p.mix_scratch[(static_cast<size_t>(chunk) * 2 + 0) * B + n] = l;
+            p.mix_scratch[(static_cast<size_t>(chunk) * 2 + 1) * B + n] = r;
+        }
     }
-    if (mix_scratch) {
-        mix_scratch[(static_cast<size_t>(chunk) * 2 + 0) * B + n] = l;
-        mix_scratch[(static_cast<size_t>(chunk) * 2 + 1) * B + n] = r;
+    if (!p.mix) return;
+    // ---- last CTA adds the chunk partials ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned ticket = atomicAdd(p.ticket, 1u);
+        s_last = (ticket == total - 1);
+        if (s_last) *p.ticket = 0;  // re-armed for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nchunks = gridDim.y;
+    for (int idx = threadIdx.x; idx < 2 * B; idx += blockDim.x) {
+        const int c = idx / B, nn = idx - c * B;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < nchunks; ++k) acc += __ldcg(&p.mix_scratch[(static_cast<size_t>(k) * 2 + c) * B + nn]);
+        p.mix[idx] = acc;
     }
 }
 
@@ -310,10 +354,9 @@ int fir_max_segments(int n_tiles_total, int NS, int G) {
     return ms;
 }
 
-cudaError_t launch_fir_finish_mix(const float* partial, float* out, int MS, int T, int B, int sample_major, int Tg,
-                                  int toff, const float* gains, float* mix_scratch, cudaStream_t st) {
-    dim3 grid((B + 127) / 128, (T + kMixChunk - 1) / kMixChunk);
-    fir_finish_mix_kernel<<<grid, 128, 0, st>>>(partial, out, MS, T, B, sample_major, Tg, toff, gains, mix_scratch);
+cudaError_t launch_fir_finish_mix(const FinishParams& p, cudaStream_t st) {
+    dim3 grid((p.B + 127) / 128, (p.T + kMixChunk - 1) / kMixChunk);
+    fir_finish_mix_kernel<<<grid, 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 

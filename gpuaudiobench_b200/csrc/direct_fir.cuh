@@ -6,17 +6,21 @@
 
 namespace b200conv {
 
-constexpr int kFirWarps = 8;                        // consumer warps per CTA
-constexpr int kFirThreads = (kFirWarps + 1) * 32;   // + one TMA producer warp
-constexpr int kFirMaxStages = 8;                    // mbarrier slots reserved in shared memory
-constexpr size_t kFirMaxSmem = 112 * 1024;          // per CTA; two CTAs per SM fit in 227 KB
-constexpr int kFirCtasPerSm = 2;                    // persistent grid = kFirCtasPerSm * SM count
-constexpr int kMixChunk = 8;                        // tracks per stereo-bus partial
+#ifndef B200CONV_FIR_CTAS_PER_SM
+#define B200CONV_FIR_CTAS_PER_SM 2
+#endif
+constexpr int kFirWarps = 8;                              // consumer warps per CTA
+constexpr int kFirThreads = (kFirWarps + 1) * 32;         // + one TMA producer warp
+constexpr int kFirMaxStages = 8;                          // mbarrier slots reserved in shared memory
+constexpr int kFirCtasPerSm = B200CONV_FIR_CTAS_PER_SM;   // persistent grid = kFirCtasPerSm * SM count
+constexpr size_t kFirMaxSmem = (kFirCtasPerSm >= 3 ? 74 : 112) * 1024;  // per CTA; kFirCtasPerSm CTAs fit in 227 KB
+constexpr int kMixChunk = 8;                              // tracks per stereo-bus partial
 
 // All "block" quantities are in units of 16 floats (64 B).
 struct FirParams {
     const float* h;     // [T][Lc*16]  taps, zero padded; chunk-swizzled iff 32/A > 1 (lanes differ in taps)
-    const float* ring;  // [T][capb*16] input history ring, chunk-swizzled
+    const float* ring;  // [T][capb*16] input history ring, chunk-swizzled (holds samples BEFORE the current buffer)
+    const float* d_in;  // [T][B]      the current buffer (read directly; appended to the ring by the finish kernel)
     float* partial;     // [MS][T][B]  one row per (CTA, track-tile) segment
     int T, B;
     int capb;           // ring capacity
@@ -36,7 +40,18 @@ cudaError_t launch_ring_append(const float* d_in, float* ring, int T, int B, int
 cudaError_t launch_fir(const FirParams& p, int A, size_t smem, cudaStream_t st);
 // Most partial rows any track-tile receives when U = n_tiles_total * NS units are split over G CTAs.
 int fir_max_segments(int n_tiles_total, int NS, int G);
-cudaError_t launch_fir_finish_mix(const float* partial, float* out, int MS, int T, int B, int sample_major, int Tg,
-                                  int toff, const float* gains, float* mix_scratch, cudaStream_t st);
+struct FinishParams {
+    const float* partial;  // [MS][T][B]
+    float* out;            // [T][B] or [B][Tg]
+    int MS, T, B, sample_major, Tg, toff;
+    const float* gains;    // [T][2]
+    float* mix_scratch;    // [ceil(T/8)][2][B]
+    float* mix;            // [2][B] or null (no bus requested)
+    unsigned* ticket;      // last-CTA counter, zero between launches
+    const float* d_in;     // [T][B]
+    float* ring;           // [T][cap] or null (PEEK: do not append)
+    int cap, pos;
+};
+cudaError_t launch_fir_finish_mix(const FinishParams& p, cudaStream_t st);
 
 }  // namespace b200conv

@@ -69,6 +69,8 @@ struct UpolsState {
     float2* tw_c = nullptr;
     float2* tw_r = nullptr;
     float* prev = nullptr;
+    unsigned* counters = nullptr;
+    bool fused = false;
 };
 
 }  // namespace
@@ -85,6 +87,7 @@ struct b200conv_engine {
     float* d_mix_stage = nullptr;
     float* d_gains = nullptr;
     float* d_mix_scratch = nullptr;
+    unsigned* d_ticket = nullptr;
     DirectState dir;
     UpolsState up;
     bool profiling = false;
@@ -139,7 +142,7 @@ int plan_direct(b200conv_engine* e) {
     const long long units = static_cast<long long>(e->T) * d.ntiles * d.NS;
     if (units > 0x7fffffffLL) return fail(B200CONV_ERR_INVALID, "direct engine: job too large");
     int per_sm = env_int("B200CONV_DIRECT_CTAS_PER_SM", kFirCtasPerSm);
-    per_sm = std::max(1, std::min(per_sm, 2));
+    per_sm = std::max(1, std::min(per_sm, kFirCtasPerSm));
     d.G = static_cast<int>(std::min<long long>(units, static_cast<long long>(per_sm) * e->sm_count));
     d.MS = fir_max_segments(e->T * d.ntiles, d.NS, d.G);
     d.xtile_blocks = (d.A + d.JSb + 8 + 7) & ~7;
@@ -171,6 +174,7 @@ int plan_upols(b200conv_engine* e) {
         S = static_cast<int>((4LL * e->sm_count + base - 1) / base);
     }
     u.S = std::max(1, std::min({S, u.P, 32}));
+    u.fused = (u.M <= kFusedMaxM) && env_int("B200CONV_UPOLS_FUSED", 1) != 0;
     return B200CONV_OK;
 }
 
@@ -333,6 +337,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
     if ((rc = dev_alloc(e, &e->d_mix_stage, static_cast<size_t>(2) * e->B))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_gains, static_cast<size_t>(2) * e->T))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_mix_scratch, static_cast<size_t>((e->T + kMixChunk - 1) / kMixChunk) * 2 * e->B))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_ticket, 4))) return bail(rc);
     if ((rc = set_default_gains(e))) return bail(rc);
 
     if (cfg->algo == B200CONV_ALGO_DIRECT) {
@@ -347,6 +352,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if ((rc = dev_alloc(e, &u.X, spec))) return bail(rc);
         if ((rc = dev_alloc(e, &u.Ypart, static_cast<size_t>(u.S) * e->T * u.M))) return bail(rc);
         if ((rc = dev_alloc(e, &u.prev, tb))) return bail(rc);
+        if ((rc = dev_alloc(e, &u.counters, static_cast<size_t>(e->T)))) return bail(rc);
         if ((rc = upload_twiddles(e))) return bail(rc);
     }
     err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
@@ -529,11 +535,10 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
     if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
         DirectState& d = e->dir;
         tm.mark();
-        CU_TRY(launch_ring_append(d_in, d.ring, e->T, e->B, d.cap, d.pos, st));
-        tm.mark();
         FirParams p{};
         p.h = d.h;
         p.ring = d.ring;
+        p.d_in = d_in;
         p.partial = d.partial;
         p.T = e->T;
         p.B = e->B;
@@ -550,61 +555,100 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
         p.G = d.G;
         CU_TRY(launch_fir(p, d.A, d.smem, st));
         tm.mark();
-        CU_TRY(launch_fir_finish_mix(d.partial, d_out, d.MS, e->T, e->B, sample_major, e->Tg, e->toff, e->d_gains,
-                                     d_mix ? e->d_mix_scratch : nullptr, st));
-        e->launches += 3;
-        if (d_mix) {
-            CU_TRY(launch_mix_final(e->d_mix_scratch, d_mix, (e->T + kMixChunk - 1) / kMixChunk, e->B, st));
-            e->launches += 1;
-        }
+        FinishParams f{};
+        f.partial = d.partial;
+        f.out = d_out;
+        f.MS = d.MS;
+        f.T = e->T;
+        f.B = e->B;
+        f.sample_major = sample_major;
+        f.Tg = e->Tg;
+        f.toff = e->toff;
+        f.gains = e->d_gains;
+        f.mix_scratch = e->d_mix_scratch;
+        f.mix = d_mix;
+        f.ticket = e->d_ticket;
+        f.d_in = d_in;
+        f.ring = commit ? d.ring : nullptr;
+        f.cap = d.cap;
+        f.pos = d.pos;
+        CU_TRY(launch_fir_finish_mix(f, st));
+        e->launches += 2;
         tm.mark();
         marks = tm.idx;
         if (commit) d.pos = (d.pos + e->B) % d.cap;
     } else {
         UpolsState& u = e->up;
         const int slot0 = static_cast<int>((u.P - (e->blocks % u.P)) % u.P);
-        tm.mark();
-        RfftParams f{};
-        f.first = u.prev;
-        f.first_stride = e->B;
-        f.second = d_in;
-        f.second_stride = e->B;
-        f.out = u.X + static_cast<size_t>(slot0) * u.M;
-        f.out_stride = static_cast<size_t>(u.P) * u.M;
-        f.prev_out = commit ? u.prev : nullptr;
-        f.count = e->T;
-        f.M = u.M;
-        f.logM = u.logM;
-        f.scale = 1.0f;
-        f.tw_c = u.tw_c;
-        f.tw_r = u.tw_r;
-        CU_TRY(launch_rfft_fwd(f, st));
-        tm.mark();
-        MacParams m{};
-        m.H = u.H;
-        m.X = u.X;
-        m.Ypart = u.Ypart;
-        m.T = e->T;
-        m.P = u.P;
-        m.M = u.M;
-        m.slot0 = slot0;
-        m.S = u.S;
-        CU_TRY(launch_fdl_mac(m, st));
-        tm.mark();
-        IrfftParams r{};
-        r.Ypart = u.Ypart;
-        r.S = u.S;
-        r.out = d_out;
-        r.T = e->T;
-        r.M = u.M;
-        r.logM = u.logM;
-        r.sample_major = sample_major;
-        r.Tg = e->Tg;
-        r.toff = e->toff;
-        r.tw_c = u.tw_c;
-        r.tw_r = u.tw_r;
-        CU_TRY(launch_irfft_ols(r, st));
-        e->launches += 3;
+        if (u.fused) {
+            tm.mark();
+            FusedParams fp{};
+            fp.d_in = d_in;
+            fp.prev = u.prev;
+            fp.H = u.H;
+            fp.X = u.X;
+            fp.Ypart = u.Ypart;
+            fp.counters = u.counters;
+            fp.out = d_out;
+            fp.T = e->T;
+            fp.P = u.P;
+            fp.M = u.M;
+            fp.logM = u.logM;
+            fp.S = u.S;
+            fp.slot0 = slot0;
+            fp.commit = commit ? 1 : 0;
+            fp.sample_major = sample_major;
+            fp.Tg = e->Tg;
+            fp.toff = e->toff;
+            fp.tw_c = u.tw_c;
+            fp.tw_r = u.tw_r;
+            CU_TRY(launch_upols_fused(fp, st));
+            e->launches += 1;
+            tm.mark();
+        } else {
+            tm.mark();
+            RfftParams f{};
+            f.first = u.prev;
+            f.first_stride = e->B;
+            f.second = d_in;
+            f.second_stride = e->B;
+            f.out = u.X + static_cast<size_t>(slot0) * u.M;
+            f.out_stride = static_cast<size_t>(u.P) * u.M;
+            f.prev_out = commit ? u.prev : nullptr;
+            f.count = e->T;
+            f.M = u.M;
+            f.logM = u.logM;
+            f.scale = 1.0f;
+            f.tw_c = u.tw_c;
+            f.tw_r = u.tw_r;
+            CU_TRY(launch_rfft_fwd(f, st));
+            tm.mark();
+            MacParams m{};
+            m.H = u.H;
+            m.X = u.X;
+            m.Ypart = u.Ypart;
+            m.T = e->T;
+            m.P = u.P;
+            m.M = u.M;
+            m.slot0 = slot0;
+            m.S = u.S;
+            CU_TRY(launch_fdl_mac(m, st));
+            tm.mark();
+            IrfftParams r{};
+            r.Ypart = u.Ypart;
+            r.S = u.S;
+            r.out = d_out;
+            r.T = e->T;
+            r.M = u.M;
+            r.logM = u.logM;
+            r.sample_major = sample_major;
+            r.Tg = e->Tg;
+            r.toff = e->toff;
+            r.tw_c = u.tw_c;
+            r.tw_r = u.tw_r;
+            CU_TRY(launch_irfft_ols(r, st));
+            e->launches += 3;
+        }
         if (d_mix) {
             CU_TRY(launch_mix(d_out, sample_major, e->Tg, e->toff, e->d_gains, e->d_mix_scratch, d_mix, e->T, e->B, st));
             e->launches += 2;
@@ -656,20 +700,29 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
         info->alg_bytes_per_block = 0;
         info->partitions = e->dir.MS;
         info->fft_size = 0;
-        info->kernels_per_block = 3;
-        std::snprintf(info->stage_name[0], 24, "ring_append");
-        std::snprintf(info->stage_name[1], 24, "fir_direct");
-        std::snprintf(info->stage_name[2], 24, "fir_finish+mix");
+        info->kernels_per_block = 2;
+        info->stage_count = 2;
+        info->dominant_stage = 0;
+        std::snprintf(info->stage_name[0], 24, "fir_direct");
+        std::snprintf(info->stage_name[1], 24, "finish+mix+append");
     } else {
         const uint64_t P = e->up.P;
         info->flops_per_block = 8 * T * P * (B + 1);
         info->alg_bytes_per_block = T * 16 * P * (B + 1);
         info->partitions = e->up.P;
         info->fft_size = 2 * e->B;
-        info->kernels_per_block = 3;
-        std::snprintf(info->stage_name[0], 24, "rfft_fwd");
-        std::snprintf(info->stage_name[1], 24, "fdl_mac");
-        std::snprintf(info->stage_name[2], 24, "irfft_ols+mix");
+        if (e->up.fused) {
+            info->kernels_per_block = 1;
+            info->stage_count = 2;
+            info->dominant_stage = 0;
+            std::snprintf(info->stage_name[0], 24, "upols_fused(fft+mac+ifft)");
+            std::snprintf(info->stage_name[1], 24, "mix");
+        } else {
+            info->kernels_per_block = 3;
+            std::snprintf(info->stage_name[0], 24, "rfft_fwd");
+            std::snprintf(info->stage_name[1], 24, "fdl_mac");
+            std::snprintf(info->stage_name[2], 24, "irfft_ols+mix");
+        }
     }
     return B200CONV_OK;
 }

@@ -289,6 +289,170 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused block kernel (M = B <= 512): forward FFT -> FDL-MAC -> inverse FFT + overlap-save in ONE
+// launch; grid (S, T), 256 threads.  The newest spectrum X_m only enters the sum through
+// partition 0, which belongs to split 0, so only that CTA transforms the input (and publishes
+// X_m to the ring for later blocks); the other splits stream older ring slots straight away.
+// Each CTA leaves its partial spectrum in Ypart and takes a ticket on the track's counter; the
+// last one adds the S partials in split order, runs the inverse transform and writes the output.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
+    extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
+    __shared__ int s_last;
+    const int M = p.M, half = M >> 1, U = M >> 1, G = 256 / U;
+    const int s = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+    float2* a = fsm;
+    float2* b = fsm + M;
+    float* red = reinterpret_cast<float*>(fsm + 2 * M);
+    const float2* xsm = nullptr;  // packed X_m in shared memory (split 0 only)
+
+    if (s == 0) {
+        const float2* in2 = reinterpret_cast<const float2*>(p.d_in + static_cast<size_t>(t) * M);
+        float2* prev2 = reinterpret_cast<float2*>(p.prev + static_cast<size_t>(t) * M);
+        for (int n = tid; n < half; n += 256) {
+            const float2 pv = prev2[n], cv = in2[n];
+            a[n] = pv;          // window = [previous buffer | current buffer], even/odd packed
+            a[n + half] = cv;
+            if (p.commit) prev2[n] = cv;
+        }
+        __syncthreads();
+        float2* z = fft_stockham<false>(a, b, M, p.logM, p.tw_c, tid, 256, true);
+        float2* xo = (z == a) ? b : a;
+        float2* ring = p.X + (static_cast<size_t>(t) * p.P + p.slot0) * M;
+        for (int k = tid; k <= half; k += 256) {
+            const float2 A = z[k];
+            const float2 Bc = cconj(z[(M - k) & (M - 1)]);
+            const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y + Bc.y));
+            const float2 D = make_float2(0.5f * (A.x - Bc.x), 0.5f * (A.y - Bc.y));
+            const float2 WO = cmul(p.tw_r[k], make_float2(D.y, -D.x));
+            const float2 Xk = cadd(E, WO);
+            const float2 Xmk = make_float2(E.x - WO.x, -(E.y - WO.y));
+            if (k == 0) {
+                xo[0] = ring[0] = make_float2(Xk.x, Xmk.x);
+            } else {
+                xo[k] = ring[k] = Xk;
+                if (k != half) xo[M - k] = ring[M - k] = Xmk;
+            }
+        }
+        __syncthreads();
+        xsm = xo;
+    }
+
+    // ---- FDL-MAC over this split's partitions (same loop as fdl_mac_kernel) ----
+    const int u = tid % U, g = tid / U;
+    const int P = p.P;
+    int p0 = static_cast<int>(static_cast<long long>(P) * s / p.S);
+    const int p1 = static_cast<int>(static_cast<long long>(P) * (s + 1) / p.S);
+    const float4* H4 = reinterpret_cast<const float4*>(p.H) + static_cast<size_t>(t) * P * U + u;
+    const float4* X4 = reinterpret_cast<const float4*>(p.X) + static_cast<size_t>(t) * P * U + u;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    if (s == 0) {  // partition 0 against the spectrum still in shared memory
+        if (g == 0) mac2(acc, ldg_stream(H4), reinterpret_cast<const float4*>(xsm)[u]);
+        p0 = 1;
+    }
+    int pp = p0 + g;
+    for (; pp + 3 * G < p1; pp += 4 * G) {
+        float4 h[4], x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = pp + j * G;
+            int sl = p.slot0 + q;
+            if (sl >= P) sl -= P;
+            h[j] = ldg_stream(H4 + static_cast<size_t>(q) * U);
+            x[j] = ldg_stream(X4 + static_cast<size_t>(sl) * U);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mac2(acc, h[j], x[j]);
+    }
+    for (; pp < p1; pp += G) {
+        int sl = p.slot0 + pp;
+        if (sl >= P) sl -= P;
+        mac2(acc, ldg_stream(H4 + static_cast<size_t>(pp) * U), ldg_stream(X4 + static_cast<size_t>(sl) * U));
+    }
+    if (G > 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[tid * 8 + i] = acc[i];
+        __syncthreads();
+        if (g == 0) {
+            for (int gg = 1; gg < G; ++gg) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += red[(gg * U + u) * 8 + i];
+            }
+        }
+    }
+    float4 y;
+    if (u == 0) {
+        y.x = acc[0];  // DC
+        y.y = acc[1];  // Nyquist
+    } else {
+        y.x = acc[0] - acc[1];
+        y.y = acc[2] + acc[3];
+    }
+    y.z = acc[4] - acc[5];
+    y.w = acc[6] + acc[7];
+
+    __syncthreads();  // everyone is done with xsm / the FFT buffers
+    float2* ysm = b;  // summed spectrum goes to b, the inverse pre-pass writes a
+    if (p.S == 1) {
+        if (g == 0) reinterpret_cast<float4*>(ysm)[u] = y;
+    } else {
+        if (g == 0) reinterpret_cast<float4*>(p.Ypart)[(static_cast<size_t>(s) * p.T + t) * U + u] = y;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned ticket = atomicAdd(&p.counters[t], 1u);
+            s_last = (ticket == static_cast<unsigned>(p.S) - 1u);
+            if (s_last) p.counters[t] = 0;  // re-armed for the next block
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (g == 0) {
+            float4 sum = __ldcg(reinterpret_cast<const float4*>(p.Ypart) + static_cast<size_t>(t) * U + u);
+            for (int ss = 1; ss < p.S; ++ss) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.Ypart) + (static_cast<size_t>(ss) * p.T + t) * U + u);
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            reinterpret_cast<float4*>(ysm)[u] = sum;
+        }
+    }
+    __syncthreads();
+
+    // ---- inverse real-FFT pre-pass, inverse FFT, overlap-save output ----
+    for (int k = tid; k <= half; k += 256) {
+        const float2 yk = ysm[k], ym = ysm[(M - k) & (M - 1)];
+        float2 A, Bm;
+        if (k == 0) {
+            A = make_float2(yk.x, 0.0f);
+            Bm = make_float2(yk.y, 0.0f);
+        } else {
+            A = yk;
+            Bm = ym;
+        }
+        const float2 Bc = cconj(Bm);
+        const float2 E = cadd(A, Bc);
+        const float2 O = cmul(cconj(p.tw_r[k]), csub(A, Bc));
+        a[k] = make_float2(E.x - O.y, E.y + O.x);
+        if (k != 0 && k != half) a[M - k] = make_float2(E.x + O.y, O.x - E.y);
+    }
+    __syncthreads();
+    const float2* z = fft_stockham<true>(a, b, M, p.logM, p.tw_c, tid, 256, true);
+    if (!p.sample_major) {
+        float2* out2 = reinterpret_cast<float2*>(p.out + static_cast<size_t>(t) * M);
+        for (int n = tid; n < half; n += 256) out2[n] = z[half + n];
+    } else {
+        float* col = p.out + p.toff + t;
+        for (int n = tid; n < half; n += 256) {
+            const float2 v = z[half + n];
+            col[static_cast<size_t>(2 * n) * p.Tg] = v.x;
+            col[static_cast<size_t>(2 * n + 1) * p.Tg] = v.y;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stereo mix bus, two fixed-order passes (deterministic; no atomics).  Pass 1 forms the partial
 // of each 8-track chunk with all eight loads in flight; pass 2 adds the chunks in order.
 // ---------------------------------------------------------------------------------------------
@@ -367,6 +531,13 @@ cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st) {
         G = 256 / U;
     dim3 grid(KT, p.S, p.T);
     fdl_mac_kernel<<<grid, 256, 0, st>>>(p, U, G);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st) {
+    dim3 grid(p.S, p.T);
+    const size_t smem = static_cast<size_t>(2) * p.M * sizeof(float2) + 256 * 8 * sizeof(float);
+    upols_fused_kernel<<<grid, 256, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -47,6 +47,23 @@ struct IrfftParams {
     const float2* tw_r;
 };
 
+// One launch per block for M = B <= 512: forward FFT (split 0) + FDL-MAC + inverse/overlap-save (last CTA).
+struct FusedParams {
+    const float* d_in;    // [T][B]
+    float* prev;          // [T][B] previous buffer (updated when commit != 0)
+    const float2* H;      // [T][P][M]
+    float2* X;            // [T][P][M] ring; slot0 receives X_m
+    float2* Ypart;        // [S][T][M]
+    unsigned* counters;   // [T], zero between launches
+    float* out;           // [T][B] or [B][Tg]
+    int T, P, M, logM, S, slot0, commit;
+    int sample_major, Tg, toff;
+    const float2* tw_c;
+    const float2* tw_r;
+};
+cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st);
+constexpr int kFusedMaxM = 512;
+
 cudaError_t launch_rfft_fwd(const RfftParams& p, cudaStream_t st);
 cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st);
 cudaError_t launch_irfft_ols(const IrfftParams& p, cudaStream_t st);

@@ -76,9 +76,6 @@ class DirectEmu:
         p, T, B = self.p, self.T, self.B
         A, CL, SPS, JSb, NS, G, MS, ntiles = p["A"], p["CL"], p["SPS"], p["JSb"], p["NS"], p["G"], p["MS"], p["ntiles"]
         capb, posb = self.cap // 16, self.pos // 16
-        for f in range(B // 4):  # ring_append_kernel
-            pf = swz_chunk(self.pos // 4 + f)
-            self.ring[:, 4 * pf:4 * pf + 4] = x[:, 4 * f:4 * f + 4]
         partial = np.zeros((MS, T, B))
         written = np.zeros((MS, T, B), dtype=bool)
         OT = A * 16
@@ -94,15 +91,26 @@ class DirectEmu:
                 c0 = k * JSb
                 qbase = posb + capb + ot * A
                 qs = (qbase - c0 - JSb) & ~7
-                nblk = (qbase + A - 1 - c0) - qs + 1
+                # producer: history part of the tile from the ring (the current buffer is not in it yet)
+                q_hi = min(qbase + A - 1 - c0, posb + capb - 1)
+                nblk = q_hi - qs + 1
                 assert 0 < nblk <= p["xtile_blocks"], (nblk, p["xtile_blocks"])
                 src_b = qs % capb
                 first = min(nblk, capb - src_b)
                 hs = self.h[t, c0 * 16:(c0 + JSb) * 16]
-                xs = np.empty(nblk * 16)
+                xs = np.full(p["xtile_blocks"] * 16, np.nan)
                 xs[:first * 16] = self.ring[t, src_b * 16:(src_b + first) * 16]
                 if first < nblk:
-                    xs[first * 16:] = self.ring[t, :(nblk - first) * 16]
+                    xs[first * 16:nblk * 16] = self.ring[t, :(nblk - first) * 16]
+                # consumers: current-buffer blocks [cur_lo, cur_hi] straight from d_in, swizzled
+                cur_lo, cur_hi = max(qs, posb + capb), qbase + A - 1 - c0
+                if cur_lo <= cur_hi:
+                    f0 = (cur_lo - qs) * 4
+                    for c in range((cur_hi - cur_lo + 1) * 4):
+                        src = (cur_lo - posb - capb) * 16 + 4 * c
+                        pf = swz_chunk(f0 + c)
+                        xs[4 * pf:4 * pf + 4] = x[t, src:src + 4]
+                nblk = cur_hi - qs + 1
                 for warp in range(KFIR_WARPS):
                     for lane in range(32):
                         a, g = lane & (A - 1), lane // A
@@ -130,8 +138,11 @@ class DirectEmu:
                 k += 1
                 if k == NS:
                     k, w = 0, w + 1
-        if commit:
+        if commit:  # fir_finish_mix_kernel appends the consumed buffer
+            for n in range(B):
+                self.ring[:, swz_float(self.pos + n)] = x[:, n]
             self.pos = (self.pos + B) % self.cap
+        assert not np.isnan(partial).any(), "a lane read a tile block nobody staged"
         return partial.sum(axis=0)
 
 
