@@ -26,6 +26,8 @@
 // the swizzle, which costs one shift + four LOP3 per block as an XOR on the byte offset.
 #include "direct_fir.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -137,7 +139,8 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
                 // blocks at or after the current buffer (q >= posb + capb) are NOT in the ring yet: the
                 // consumers copy them from d_in, so the ring append is off the critical path
                 const int q_hi = min(qbase + A - 1 - c0, p.posb + p.capb - 1);
-                const int nblk = q_hi - qs + 1;  // <= xtile_blocks, >= 1 (a tile always reaches into the past)
+                const int nblk = max(0, q_hi - qs + 1);  // <= xtile_blocks; 0 when an upper output tile's
+                                                         // first stage lies entirely inside the current buffer
                 int src_b = qs % p.capb;
                 const int first = min(nblk, p.capb - src_b);
                 unsigned char* hs = stage_base + static_cast<size_t>(slot) * stage_bytes;
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
                 const float* rsrc = p.ring + static_cast<size_t>(t) * p.capb * 16;
                 mbar_arrive_expect_tx(&full_bar[slot], static_cast<uint32_t>((p.JSb + nblk) * 64));
                 bulk_g2s(hs, hsrc, static_cast<uint32_t>(p.JSb * 64), &full_bar[slot]);
-                bulk_g2s(xs, rsrc + static_cast<size_t>(src_b) * 16, static_cast<uint32_t>(first * 64), &full_bar[slot]);
+                if (first > 0)
+                    bulk_g2s(xs, rsrc + static_cast<size_t>(src_b) * 16, static_cast<uint32_t>(first * 64), &full_bar[slot]);
                 if (first < nblk)
                     bulk_g2s(xs + first * 64, rsrc, static_cast<uint32_t>((nblk - first) * 64), &full_bar[slot]);
                 if (++slot == p.nbuf) { slot = 0; phase ^= 1; }
@@ -242,71 +246,113 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Finish (one launch does everything after the FIR):
+// Finish (one launch does everything after the FIR), as a thread-block cluster per 32-sample
+// column tile: grid (B/32, CY), cluster (1, CY), 4 warps per CTA.  Warp (rank, w) walks 8-track
+// groups (rank*4 + w) + j*4*CY and for each
 //   y = sum of the tile's partial rows in a fixed order, written track-major [T][B] or as this
 //       engine's column tile of the sample-major [B][Tg] matrix (bench_conv1d_accel.cu:249 layout);
-//   stereo-bus partial of this CTA's 8-track chunk; the LAST CTA to finish (ticket counter) adds
-//       the chunk partials in chunk order -> deterministic bus, no second launch, no float atomics;
-//   ring append of the buffer just consumed (skipped for PEEK): ring[t][swz(pos + n)] = in[t][n].
+//   ring append of the buffer just consumed (skipped for PEEK): ring[t][swz(pos + n)] = in[t][n];
+//   stereo-bus partial l/r += gain * y.
+// The bus partials are then reduced warp -> CTA (shared memory) -> cluster (rank 0 reads the other
+// CTAs' shared memory over DSMEM) in a fixed order: deterministic, no float atomics, no 2nd launch.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) fir_finish_mix_kernel(FinishParams p) {
-    __shared__ int s_last;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int chunk = blockIdx.y;
-    const int t0 = chunk * kMixChunk;
+__device__ __forceinline__ void cluster_bus_reduce(float l, float r, float* mix, int n0, int B) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float part[kBusWarps][2][32];
+    __shared__ float csum[2][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    part[warp][0][lane] = l;
+    part[warp][1][lane] = r;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x >> 5;
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kBusWarps; ++w) v += part[w][c][lane];
+        csum[c][lane] = v;
+    }
+    cluster.sync();
+    if (cluster.block_rank() == 0 && threadIdx.x < 64) {
+        const int c = threadIdx.x >> 5;
+        float v = 0.0f;
+        const unsigned nranks = cluster.num_blocks();
+        for (unsigned rk = 0; rk < nranks; ++rk) v += cluster.map_shared_rank(&csum[0][0], rk)[c * 32 + lane];
+        if (n0 + lane < B) mix[static_cast<size_t>(c) * B + n0 + lane] = v;
+    }
+    cluster.sync();  // nobody's shared memory may go away before rank 0 has read it
+}
+
+__global__ void __launch_bounds__(kBusWarps * 32) fir_finish_mix_kernel(FinishParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * 32, n = n0 + lane;
     const int T = p.T, B = p.B;
+    const int ngroups = (T + kMixChunk - 1) / kMixChunk;
+    float l = 0.0f, r = 0.0f;
     if (n < B) {
-        float v[kMixChunk];
-#pragma unroll
-        for (int j = 0; j < kMixChunk; ++j) v[j] = 0.0f;
-        for (int s = 0; s < p.MS; ++s) {
-#pragma unroll
-            for (int j = 0; j < kMixChunk; ++j)
-                if (t0 + j < T) v[j] += p.partial[(static_cast<size_t>(s) * T + t0 + j) * B + n];
-        }
-        float l = 0.0f, r = 0.0f;
         const uint32_t ring_idx = swz_float(static_cast<uint32_t>(p.pos + n));
+        for (int gi = blockIdx.y * kBusWarps + warp; gi < ngroups; gi += kBusWarps * gridDim.y) {
+            const int t0 = gi * kMixChunk;
+            float v[kMixChunk], xin[kMixChunk];
 #pragma unroll
-        for (int j = 0; j < kMixChunk; ++j) {
-            const int t = t0 + j;
-            if (t < T) {
-                if (p.sample_major)
-                    p.out[static_cast<size_t>(n) * p.Tg + p.toff + t] = v[j];
-                else
-                    p.out[static_cast<size_t>(t) * B + n] = v[j];
-                if (p.mix) {
+            for (int j = 0; j < kMixChunk; ++j) v[j] = 0.0f;
+            for (int s = 0; s < p.MS; ++s) {
+#pragma unroll
+                for (int j = 0; j < kMixChunk; ++j)
+                    if (t0 + j < T) v[j] += p.partial[(static_cast<size_t>(s) * T + t0 + j) * B + n];
+            }
+            if (p.ring) {
+#pragma unroll
+                for (int j = 0; j < kMixChunk; ++j)
+                    if (t0 + j < T) xin[j] = p.d_in[static_cast<size_t>(t0 + j) * B + n];
+            }
+#pragma unroll
+            for (int j = 0; j < kMixChunk; ++j) {
+                const int t = t0 + j;
+                if (t < T) {
+                    if (p.sample_major)
+                        p.out[static_cast<size_t>(n) * p.Tg + p.toff + t] = v[j];
+                    else
+                        p.out[static_cast<size_t>(t) * B + n] = v[j];
+                    if (p.ring) p.ring[static_cast<size_t>(t) * p.cap + ring_idx] = xin[j];
                     l = fmaf(p.gains[2 * t], v[j], l);
                     r = fmaf(p.gains[2 * t + 1], v[j], r);
                 }
-                if (p.ring) p.ring[static_cast<size_t>(t) * p.cap + ring_idx] = p.d_in[static_cast<size_t>(t) * B + n];
             }
         }
-        if (p.mix) {
-            p.mix_scratch[(static_cast<size_t>(chunk) * 2 + 0) * B + n] = l;
-            p.mix_scratch[(static_cast<size_t>(chunk) * 2 + 1) * B + n] = r;
+    }
+    if (p.mix) cluster_bus_reduce(l, r, p.mix, n0, B);  // kernel-uniform branch
+}
+
+// Stereo bus of an output that is already in memory (UPOLS path): same cluster reduction.
+__global__ void __launch_bounds__(kBusWarps * 32) mix_cluster_kernel(const float* __restrict__ y, int sample_major, int Tg,
+                                                                      int toff, const float* __restrict__ gains,
+                                                                      float* __restrict__ mix, int T, int B) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * 32, n = n0 + lane;
+    const int ngroups = (T + kMixChunk - 1) / kMixChunk;
+    float l = 0.0f, r = 0.0f;
+    if (n < B) {
+        for (int gi = blockIdx.y * kBusWarps + warp; gi < ngroups; gi += kBusWarps * gridDim.y) {
+            const int t0 = gi * kMixChunk;
+            float v[kMixChunk];
+#pragma unroll
+            for (int j = 0; j < kMixChunk; ++j) {
+                const int t = t0 + j;
+                v[j] = 0.0f;
+                if (t < T) v[j] = sample_major ? y[static_cast<size_t>(n) * Tg + toff + t] : y[static_cast<size_t>(t) * B + n];
+            }
+#pragma unroll
+            for (int j = 0; j < kMixChunk; ++j) {
+                const int t = t0 + j;
+                if (t < T) {
+                    l = fmaf(gains[2 * t], v[j], l);
+                    r = fmaf(gains[2 * t + 1], v[j], r);
+                }
+            }
         }
     }
-    if (!p.mix) return;
-    // ---- last CTA adds the chunk partials ----
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned total = gridDim.x * gridDim.y;
-        const unsigned ticket = atomicAdd(p.ticket, 1u);
-        s_last = (ticket == total - 1);
-        if (s_last) *p.ticket = 0;  // re-armed for the next launch (stream-ordered)
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int nchunks = gridDim.y;
-    for (int idx = threadIdx.x; idx < 2 * B; idx += blockDim.x) {
-        const int c = idx / B, nn = idx - c * B;
-        float acc = 0.0f;
-#pragma unroll 8
-        for (int k = 0; k < nchunks; ++k) acc += __ldcg(&p.mix_scratch[(static_cast<size_t>(k) * 2 + c) * B + nn]);
-        p.mix[idx] = acc;
-    }
+    cluster_bus_reduce(l, r, mix, n0, B);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,10 +400,40 @@ int fir_max_segments(int n_tiles_total, int NS, int G) {
     return ms;
 }
 
+// cluster height: one cluster covers all tracks of a 32-sample column tile
+static int bus_cluster_height(int T) {
+    const int ngroups = (T + kMixChunk - 1) / kMixChunk;
+    int cy = 1;
+    while (cy < 8 && cy * 2 * kBusWarps <= ngroups) cy *= 2;
+    return cy;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, int cy, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kBusWarps * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = static_cast<unsigned>(cy);
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 cudaError_t launch_fir_finish_mix(const FinishParams& p, cudaStream_t st) {
-    dim3 grid((p.B + 127) / 128, (p.T + kMixChunk - 1) / kMixChunk);
-    fir_finish_mix_kernel<<<grid, 128, 0, st>>>(p);
-    return cudaGetLastError();
+    const int cy = bus_cluster_height(p.T);
+    return launch_clustered(fir_finish_mix_kernel, dim3((p.B + 31) / 32, cy), cy, st, p);
+}
+
+cudaError_t launch_mix_cluster(const float* y, int sample_major, int Tg, int toff, const float* gains, float* mix, int T,
+                               int B, cudaStream_t st) {
+    const int cy = bus_cluster_height(T);
+    return launch_clustered(mix_cluster_kernel, dim3((B + 31) / 32, cy), cy, st, y, sample_major, Tg, toff, gains, mix, T, B);
 }
 
 }  // namespace b200conv

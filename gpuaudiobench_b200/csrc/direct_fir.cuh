@@ -14,7 +14,8 @@ constexpr int kFirThreads = (kFirWarps + 1) * 32;         // + one TMA producer 
 constexpr int kFirMaxStages = 8;                          // mbarrier slots reserved in shared memory
 constexpr int kFirCtasPerSm = B200CONV_FIR_CTAS_PER_SM;   // persistent grid = kFirCtasPerSm * SM count
 constexpr size_t kFirMaxSmem = (kFirCtasPerSm >= 3 ? 74 : 112) * 1024;  // per CTA; kFirCtasPerSm CTAs fit in 227 KB
-constexpr int kMixChunk = 8;                              // tracks per stereo-bus partial
+constexpr int kMixChunk = 8;                              // tracks a warp handles per step of the bus/finish kernels
+constexpr int kBusWarps = 4;                              // warps per CTA of the bus/finish kernels
 
 // All "block" quantities are in units of 16 floats (64 B).
 struct FirParams {
@@ -45,13 +46,14 @@ struct FinishParams {
     float* out;            // [T][B] or [B][Tg]
     int MS, T, B, sample_major, Tg, toff;
     const float* gains;    // [T][2]
-    float* mix_scratch;    // [ceil(T/8)][2][B]
     float* mix;            // [2][B] or null (no bus requested)
-    unsigned* ticket;      // last-CTA counter, zero between launches
     const float* d_in;     // [T][B]
     float* ring;           // [T][cap] or null (PEEK: do not append)
     int cap, pos;
 };
 cudaError_t launch_fir_finish_mix(const FinishParams& p, cudaStream_t st);
+// Deterministic stereo bus of an output already in memory: mix[c][n] = sum_t gains[t][c] * y_t[n].
+cudaError_t launch_mix_cluster(const float* y, int sample_major, int Tg, int toff, const float* gains, float* mix, int T,
+                               int B, cudaStream_t st);
 
 }  // namespace b200conv

@@ -86,8 +86,6 @@ struct b200conv_engine {
     float* d_out_stage = nullptr;
     float* d_mix_stage = nullptr;
     float* d_gains = nullptr;
-    float* d_mix_scratch = nullptr;
-    unsigned* d_ticket = nullptr;
     DirectState dir;
     UpolsState up;
     bool profiling = false;
@@ -336,8 +334,6 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
     if ((rc = dev_alloc(e, &e->d_out_stage, out_elems))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_mix_stage, static_cast<size_t>(2) * e->B))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_gains, static_cast<size_t>(2) * e->T))) return bail(rc);
-    if ((rc = dev_alloc(e, &e->d_mix_scratch, static_cast<size_t>((e->T + kMixChunk - 1) / kMixChunk) * 2 * e->B))) return bail(rc);
-    if ((rc = dev_alloc(e, &e->d_ticket, 4))) return bail(rc);
     if ((rc = set_default_gains(e))) return bail(rc);
 
     if (cfg->algo == B200CONV_ALGO_DIRECT) {
@@ -565,9 +561,7 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
         f.Tg = e->Tg;
         f.toff = e->toff;
         f.gains = e->d_gains;
-        f.mix_scratch = e->d_mix_scratch;
         f.mix = d_mix;
-        f.ticket = e->d_ticket;
         f.d_in = d_in;
         f.ring = commit ? d.ring : nullptr;
         f.cap = d.cap;
@@ -650,8 +644,8 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
             e->launches += 3;
         }
         if (d_mix) {
-            CU_TRY(launch_mix(d_out, sample_major, e->Tg, e->toff, e->d_gains, e->d_mix_scratch, d_mix, e->T, e->B, st));
-            e->launches += 2;
+            CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
+            e->launches += 1;
         }
         tm.mark();
         marks = tm.idx;
@@ -715,7 +709,7 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
             info->kernels_per_block = 1;
             info->stage_count = 2;
             info->dominant_stage = 0;
-            std::snprintf(info->stage_name[0], 24, "upols_fused(fft+mac+ifft)");
+            std::snprintf(info->stage_name[0], 24, "upols_fused");
             std::snprintf(info->stage_name[1], 24, "mix");
         } else {
             info->kernels_per_block = 3;

@@ -18,7 +18,6 @@
 #include "upols.cuh"
 
 #include "common.cuh"
-#include "direct_fir.cuh"  // kMixChunk
 
 namespace b200conv {
 
@@ -453,48 +452,6 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stereo mix bus, two fixed-order passes (deterministic; no atomics).  Pass 1 forms the partial
-// of each 8-track chunk with all eight loads in flight; pass 2 adds the chunks in order.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) mix_partial_kernel(const float* __restrict__ y, int sample_major, int Tg,
-                                                         int toff, const float* __restrict__ gains,
-                                                         float* __restrict__ scratch, int T, int B) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int chunk = blockIdx.y;
-    if (n >= B) return;
-    const int t0 = chunk * kMixChunk;
-    float v[kMixChunk];
-#pragma unroll
-    for (int j = 0; j < kMixChunk; ++j) {
-        const int t = t0 + j;
-        v[j] = 0.0f;
-        if (t < T) v[j] = sample_major ? y[static_cast<size_t>(n) * Tg + toff + t] : y[static_cast<size_t>(t) * B + n];
-    }
-    float l = 0.0f, r = 0.0f;
-#pragma unroll
-    for (int j = 0; j < kMixChunk; ++j) {
-        const int t = t0 + j;
-        if (t < T) {
-            l = fmaf(gains[2 * t], v[j], l);
-            r = fmaf(gains[2 * t + 1], v[j], r);
-        }
-    }
-    scratch[(static_cast<size_t>(chunk) * 2 + 0) * B + n] = l;
-    scratch[(static_cast<size_t>(chunk) * 2 + 1) * B + n] = r;
-}
-
-__global__ void __launch_bounds__(128) mix_final_kernel(const float* __restrict__ scratch, float* __restrict__ mix,
-                                                       int nchunks, int B) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // c*B + n
-    if (idx >= 2 * B) return;
-    const int c = idx / B, n = idx - c * B;
-    float v = 0.0f;
-#pragma unroll 8
-    for (int k = 0; k < nchunks; ++k) v += scratch[(static_cast<size_t>(k) * 2 + c) * B + n];
-    mix[idx] = v;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------
 static cudaError_t ensure_fft_smem(const void* fn, size_t smem) {
@@ -539,21 +496,6 @@ cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(2) * p.M * sizeof(float2) + 256 * 8 * sizeof(float);
     upols_fused_kernel<<<grid, 256, smem, st>>>(p);
     return cudaGetLastError();
-}
-
-cudaError_t launch_mix_final(const float* scratch, float* mix, int nchunks, int B, cudaStream_t st) {
-    mix_final_kernel<<<(2 * B + 127) / 128, 128, 0, st>>>(scratch, mix, nchunks, B);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_mix(const float* y, int sample_major, int Tg, int toff, const float* gains, float* scratch,
-                       float* mix, int T, int B, cudaStream_t st) {
-    const int nchunks = (T + kMixChunk - 1) / kMixChunk;
-    dim3 grid((B + 127) / 128, nchunks);
-    mix_partial_kernel<<<grid, 128, 0, st>>>(y, sample_major, Tg, toff, gains, scratch, T, B);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    return launch_mix_final(scratch, mix, nchunks, B, st);
 }
 
 }  // namespace b200conv

@@ -68,9 +68,4 @@ cudaError_t launch_rfft_fwd(const RfftParams& p, cudaStream_t st);
 cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st);
 cudaError_t launch_irfft_ols(const IrfftParams& p, cudaStream_t st);
 
-// Deterministic stereo bus: mix[c][n] = sum_t gains[t][c] * y_t[n] over this engine's tracks.
-cudaError_t launch_mix(const float* y, int sample_major, int Tg, int toff, const float* gains, float* scratch,
-                       float* mix, int T, int B, cudaStream_t st);
-cudaError_t launch_mix_final(const float* scratch, float* mix, int nchunks, int B, cudaStream_t st);
-
 }  // namespace b200conv

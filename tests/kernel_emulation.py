@@ -93,8 +93,8 @@ class DirectEmu:
                 qs = (qbase - c0 - JSb) & ~7
                 # producer: history part of the tile from the ring (the current buffer is not in it yet)
                 q_hi = min(qbase + A - 1 - c0, posb + capb - 1)
-                nblk = q_hi - qs + 1
-                assert 0 < nblk <= p["xtile_blocks"], (nblk, p["xtile_blocks"])
+                nblk = max(0, q_hi - qs + 1)  # 0: an upper output tile's first stage has no history part
+                assert nblk <= p["xtile_blocks"], (nblk, p["xtile_blocks"])
                 src_b = qs % capb
                 first = min(nblk, capb - src_b)
                 hs = self.h[t, c0 * 16:(c0 + JSb) * 16]

@@ -96,7 +96,7 @@ def _truth(xs, h, hist=None):
 
 
 @pytest.mark.parametrize("T,B,L,nb,sms", [(1, 512, 1024, 2, 148), (2, 32, 100, 3, 148), (3, 256, 9000, 2, 1),
-                                           (1, 512, 16, 6, 148), (5, 128, 9000, 2, 2), (2, 1024, 2100, 2, 1)])
+                                           (1, 512, 16, 6, 148), (5, 128, 9000, 2, 2), (2, 1024, 2100, 2, 1), (1, 2048, 300, 2, 1)])
 def test_direct_kernel_index_math(T, B, L, nb, sms):
     """Swizzled ring + tile geometry + lane block walk of the persistent fir_direct_kernel: spans
     that start/end mid-track (small `sms` forces several tiles and segments per CTA), ring
