@@ -85,6 +85,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         : "memory");
 }
 
+// Programmatic dependent launch (PDL): the primary kernel allows its dependent to be scheduled
+// early; the dependent blocks here until the primary grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // 128-bit streaming loads/stores that do not allocate in L1 (data touched once per launch).
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 v;

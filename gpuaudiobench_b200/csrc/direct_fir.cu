@@ -123,6 +123,9 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
         mbar_fence_init();
     }
     __syncthreads();
+    // PDL: let the finish kernel's CTAs be scheduled as ours retire (it waits on
+    // cudaGridDependencySynchronize before touching our partial rows)
+    pdl_launch_dependents();
 
     if (warp == kFirWarps) {
         // ===== producer: one lane drives the TMA engine, running ahead across units =====
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(kBusWarps * 32) fir_finish_mix_kernel(FinishPa
     const int T = p.T, B = p.B;
     const int ngroups = (T + kMixChunk - 1) / kMixChunk;
     float l = 0.0f, r = 0.0f;
+    pdl_wait_primary();  // partial rows come from the FIR kernel launched just before us
     if (n < B) {
         const uint32_t ring_idx = swz_float(static_cast<uint32_t>(p.pos + n));
         for (int gi = blockIdx.y * kBusWarps + warp; gi < ngroups; gi += kBusWarps * gridDim.y) {
@@ -332,6 +336,7 @@ __global__ void __launch_bounds__(kBusWarps * 32) mix_cluster_kernel(const float
     const int n0 = blockIdx.x * 32, n = n0 + lane;
     const int ngroups = (T + kMixChunk - 1) / kMixChunk;
     float l = 0.0f, r = 0.0f;
+    pdl_wait_primary();  // y comes from the kernel launched just before us
     if (n < B) {
         for (int gi = blockIdx.y * kBusWarps + warp; gi < ngroups; gi += kBusWarps * gridDim.y) {
             const int t0 = gi * kMixChunk;
@@ -415,13 +420,15 @@ static cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, int cy,
     cfg.blockDim = dim3(kBusWarps * 32);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = static_cast<unsigned>(cy);
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: overlap our launch with the primary's tail
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 

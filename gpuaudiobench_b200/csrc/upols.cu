@@ -295,6 +295,11 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 // Each CTA leaves its partial spectrum in Ypart and takes a ticket on the track's counter; the
 // last one adds the S partials in split order, runs the inverse transform and writes the output.
 // ---------------------------------------------------------------------------------------------
+#ifndef B200CONV_FUSED_UNROLL
+#define B200CONV_FUSED_UNROLL 2
+#endif
+constexpr int kFusedUnroll = B200CONV_FUSED_UNROLL;  // partitions in flight per thread (x2 loads); 32-register budget
+
 __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
     extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
     __shared__ int s_last;
@@ -304,6 +309,7 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
     float2* b = fsm + M;
     float* red = reinterpret_cast<float*>(fsm + 2 * M);
     const float2* xsm = nullptr;  // packed X_m in shared memory (split 0 only)
+    pdl_launch_dependents();      // the bus kernel may be scheduled as our CTAs retire
 
     if (s == 0) {
         const float2* in2 = reinterpret_cast<const float2*>(p.d_in + static_cast<size_t>(t) * M);
@@ -352,10 +358,10 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
         p0 = 1;
     }
     int pp = p0 + g;
-    for (; pp + 3 * G < p1; pp += 4 * G) {
-        float4 h[4], x[4];
+    for (; pp + (kFusedUnroll - 1) * G < p1; pp += kFusedUnroll * G) {
+        float4 h[kFusedUnroll], x[kFusedUnroll];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kFusedUnroll; ++j) {
             const int q = pp + j * G;
             int sl = p.slot0 + q;
             if (sl >= P) sl -= P;
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
             x[j] = ldg_stream(X4 + static_cast<size_t>(sl) * U);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mac2(acc, h[j], x[j]);
+        for (int j = 0; j < kFusedUnroll; ++j) mac2(acc, h[j], x[j]);
     }
     for (; pp < p1; pp += G) {
         int sl = p.slot0 + pp;
