@@ -111,7 +111,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
 
     import gpuaudiobench_b200 as g
     from gpuaudiobench_b200 import synth
-    from gpuaudiobench_b200.distributed import reduce_mix_bus
+    from gpuaudiobench_b200.distributed import BusAllReduce
 
     algo_name, T, B, L, layout_name, label = WORKLOADS[name]
     algo = g.ALGO_DIRECT if algo_name == "direct" else g.ALGO_UPOLS
@@ -133,11 +133,12 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     d_y = torch.zeros(out_shape, device=dev)
     d_mix = torch.zeros(2, B, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    bus_reduce = BusAllReduce(d_mix, force_nccl=bool(os.environ.get("B200CONV_BUS_NCCL")))
 
     def step(k):
         eng.process(d_x[k % NB].data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
         if world > 1:
-            reduce_mix_bus(d_mix)
+            bus_reduce(stream.cuda_stream)
 
     # warm-up: also fills the history / delay line with signal
     fill = max(W, min((L + B - 1) // B + 2, 400))
@@ -223,7 +224,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
         else:  # identical sequence, with the NCCL bus reduce between the kernels and the read-back
             d_in2.copy_(h_in[k % NB], non_blocking=True)
             eng.process(d_in2.data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
-            reduce_mix_bus(d_mix)
+            bus_reduce(stream.cuda_stream)
             h_out.copy_(d_y, non_blocking=True)
             h_mix.copy_(d_mix, non_blocking=True)
             stream.synchronize()
@@ -252,7 +253,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
            "h2d_bytes_per_step": world * T * B * 4, "d2h_bytes_per_step": world * (out_bytes + 2 * B * 4),
            "p50_ms": pct(es, 0.50), "p99_ms": pct(es, 0.99), "meets_deadline": bool(pct(es, 0.99) <= deadline_ms),
            "api": "b200conv_process_host (C ABI, pinned host buffers)" if world == 1 else
-                  "pinned H2D + b200conv_process + NCCL mix-bus all-reduce + D2H"}
+                  "pinned H2D + b200conv_process + mix-bus all-reduce + D2H"}
 
     result = {
         "metric": "conv_tracks_x_ir_taps_gmac_per_s", "value": value, "unit": "GMAC/s", "n_gpus": world, "steps": K,
@@ -262,7 +263,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
                    "ir_taps": L, "fs": FS, "out_layout": layout_name, "partitions_or_splits": q["partitions"],
                    "l2": "flushed between steps (256 MiB write outside the event brackets)",
                    "timing": "sum of per-step CUDA-event times on the launch stream, max over ranks",
-                   "collective": "NCCL all-reduce of the stereo mix bus float[2][B]" if world > 1 else "none (1 GPU)"},
+                   "collective": f"all-reduce of the stereo mix bus float[2][B]: {bus_reduce.kind}"},
         "rt_tracks": value * 1e9 / (L * FS),
         "latency_ms": {"p50": pct(s, 0.50), "p95": pct(s, 0.95), "p99": pct(s, 0.99), "max": float(s[-1]),
                        "deadline": deadline_ms, "meets_deadline": bool(pct(s, 0.99) <= deadline_ms)},
@@ -270,6 +271,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
         "engine_device_bytes": q["device_bytes"],
     }
+    bus_reduce.check()
     if want_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(name, budget_s=12.0)
     eng.close()

@@ -76,15 +76,25 @@ __device__ __forceinline__ void load_block_lin(float (&v)[16], const unsigned ch
 }
 
 // acc[r] += sum_s hv[s] * w[16 + r - s],  w = [lo | hi]  (256 FFMA, all indices static).
-__device__ __forceinline__ void toeplitz_tile(float (&acc)[16], const float (&hv)[16], const float (&lo)[16],
-                                              const float (&hi)[16]) {
+// Two accumulator sets, one per tap parity.  LDS.128 pins w[k] and hv[s] to 4-aligned register
+// quads (register parity = k & 1), and the register file has an even and an odd bank: with ONE
+// accumulator per output, x = w[16+r-s] and acc[r] have the same parity for every even s whatever
+// register acc[r] gets — a bank conflict on half of all FFMAs (ncu: FMA pipe 69 % with 87 % of
+// issued instructions being FFMA).  With accE (even taps) and accO (odd taps) the allocator can give
+// accE[r] the parity opposite to r and accO[r] the parity of r, and no FFMA reads two registers of
+// one bank (the tap operand sits in the reuse cache for 16 consecutive FFMAs).
+__device__ __forceinline__ void toeplitz_tile(float (&accE)[16], float (&accO)[16], const float (&hv)[16],
+                                              const float (&lo)[16], const float (&hi)[16]) {
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const int idx = 16 + r - s;
             const float xv = (idx >= 16) ? hi[idx - 16] : lo[idx];
-            acc[r] = fmaf(hv[s], xv, acc[r]);
+            if (s & 1)
+                accO[r] = fmaf(hv[s], xv, accO[r]);
+            else
+                accE[r] = fmaf(hv[s], xv, accE[r]);
         }
     }
 }
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nbuf; ++i) {
-            mbar_init(&full_bar[i], 1);
+            mbar_init(&full_bar[i], 2);  // TMA expect_tx arrival + staged-data arrival
             mbar_init(&empty_bar[i], kFirWarps);
         }
         mbar_fence_init();
@@ -128,26 +138,29 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
     pdl_launch_dependents();
 
     if (warp == kFirWarps) {
-        // ===== producer: one lane drives the TMA engine, running ahead across units =====
-        if (lane == 0) {
-            int w = w0, k = k0, slot = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < n_units; ++it) {
-                if (it >= p.nbuf) mbar_wait(&empty_bar[slot], phase ^ 1);
-                const int t = w / p.ntiles;
-                const int ot = w - t * p.ntiles;
-                const int c0 = k * p.JSb;
-                const int qbase = p.posb + p.capb + ot * A;      // unwrapped ring block of output block a0
-                const int qs = (qbase - c0 - p.JSb) & ~7;        // tile start, 512 B aligned in the ring
-                // blocks at or after the current buffer (q >= posb + capb) are NOT in the ring yet: the
-                // consumers copy them from d_in, so the ring append is off the critical path
-                const int q_hi = min(qbase + A - 1 - c0, p.posb + p.capb - 1);
-                const int nblk = max(0, q_hi - qs + 1);  // <= xtile_blocks; 0 when an upper output tile's
-                                                         // first stage lies entirely inside the current buffer
-                int src_b = qs % p.capb;
+        // ===== producer warp: lane 0 drives the TMA engine, running ahead across units; all 32 lanes
+        // stage the part of a tile that lies in the CURRENT buffer (not in the ring yet) from d_in,
+        // swizzled, so consumers never wait on that cold load =====
+        int w = w0, k = k0, slot = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < n_units; ++it) {
+            if (it >= p.nbuf) {
+                if (lane == 0) mbar_wait(&empty_bar[slot], phase ^ 1);
+                __syncwarp();
+            }
+            const int t = w / p.ntiles;
+            const int ot = w - t * p.ntiles;
+            const int c0 = k * p.JSb;
+            const int qbase = p.posb + p.capb + ot * A;      // unwrapped ring block of output block a0
+            const int qs = (qbase - c0 - p.JSb) & ~7;        // tile start, 512 B aligned in the ring
+            const int cur_hi = qbase + A - 1 - c0;           // last block of the tile
+            const int q_hi = min(cur_hi, p.posb + p.capb - 1);
+            const int nblk = max(0, q_hi - qs + 1);          // history part (0: tile entirely in the current buffer)
+            unsigned char* hs = stage_base + static_cast<size_t>(slot) * stage_bytes;
+            unsigned char* xs = hs + p.JSb * 64;
+            if (lane == 0) {
+                const int src_b = qs % p.capb;
                 const int first = min(nblk, p.capb - src_b);
-                unsigned char* hs = stage_base + static_cast<size_t>(slot) * stage_bytes;
-                unsigned char* xs = hs + p.JSb * 64;
                 const float* hsrc = p.h + (static_cast<size_t>(t) * p.Lc + c0) * 16;
                 const float* rsrc = p.ring + static_cast<size_t>(t) * p.capb * 16;
                 mbar_arrive_expect_tx(&full_bar[slot], static_cast<uint32_t>((p.JSb + nblk) * 64));
@@ -156,18 +169,29 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
                     bulk_g2s(xs, rsrc + static_cast<size_t>(src_b) * 16, static_cast<uint32_t>(first * 64), &full_bar[slot]);
                 if (first < nblk)
                     bulk_g2s(xs + first * 64, rsrc, static_cast<uint32_t>((nblk - first) * 64), &full_bar[slot]);
-                if (++slot == p.nbuf) { slot = 0; phase ^= 1; }
-                if (++k == p.NS) { k = 0; ++w; }
             }
+            const int cur_lo = max(qs, p.posb + p.capb);
+            if (cur_lo <= cur_hi) {  // warp-uniform; only the first tap stage(s) of a tile
+                const float4* src = reinterpret_cast<const float4*>(p.d_in + static_cast<size_t>(t) * p.B) +
+                                    (cur_lo - p.posb - p.capb) * 4;
+                const int nchunk = (cur_hi - cur_lo + 1) * 4;
+                const uint32_t f0 = static_cast<uint32_t>(cur_lo - qs) * 4;  // tile-relative chunk index
+                for (int c = lane; c < nchunk; c += 32)
+                    *reinterpret_cast<float4*>(xs + (swz_chunk(f0 + c) << 4)) = src[c];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[slot]);  // second arrival: staged data is in place
+            if (++slot == p.nbuf) { slot = 0; phase ^= 1; }
+            if (++k == p.NS) { k = 0; ++w; }
         }
     } else {
         // ===== consumers: 8 warps on the FMA pipe =====
         const int a = lane & (A - 1);
         const int g = lane / A;
         const int hb0 = (warp * CL + g) * p.SPS;  // lane's first tap block inside a stage
-        float acc[16];
+        float acc[16], accB[16];  // even-tap / odd-tap accumulators (see toeplitz_tile)
 #pragma unroll
-        for (int r = 0; r < 16; ++r) acc[r] = 0.0f;
+        for (int r = 0; r < 16; ++r) acc[r] = accB[r] = 0.0f;
 
         int w = w0, k = k0, slot = 0;
         uint32_t phase = 0;
@@ -185,30 +209,15 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
             const unsigned char* xs = hs + p.JSb * 64;
             const int sb = qbase + a - (c0 + hb0) - qs;  // smem block index of D_{a-c} for c = c0 + hb0
 
-            // current-buffer blocks of this tile: unwrapped ring blocks [cur_lo, cur_hi] <-> d_in
-            const int cur_lo = max(qs, p.posb + p.capb);
-            const int cur_hi = qbase + A - 1 - c0;
-            if (cur_lo <= cur_hi) {  // CTA-uniform; only the first tap stage(s) of a tile
-                const float4* src = reinterpret_cast<const float4*>(p.d_in + static_cast<size_t>(t) * p.B) +
-                                    (cur_lo - p.posb - p.capb) * 4;
-                const int nchunk = (cur_hi - cur_lo + 1) * 4;
-                const uint32_t f0 = static_cast<uint32_t>(cur_lo - qs) * 4;  // tile-relative chunk index
-                for (int c = threadIdx.x; c < nchunk; c += kFirWarps * 32) {
-                    const uint32_t f = f0 + c;
-                    *reinterpret_cast<float4*>(const_cast<unsigned char*>(xs) + (swz_chunk(f) << 4)) = src[c];
-                }
-                named_bar_sync(1, kFirWarps * 32);
-            }
-
             float P[16], Q[16], hv[16];
             load_block_swz(Q, xs, sb);
             for (int q = 0; q < p.SPS; q += 2) {
                 if (kSwzTaps) load_block_swz(hv, hs, hb0 + q); else load_block_lin(hv, hs, hb0 + q);
                 load_block_swz(P, xs, sb - q - 1);
-                toeplitz_tile(acc, hv, P, Q);
+                toeplitz_tile(acc, accB, hv, P, Q);
                 if (kSwzTaps) load_block_swz(hv, hs, hb0 + q + 1); else load_block_lin(hv, hs, hb0 + q + 1);
                 load_block_swz(Q, xs, sb - q - 2);
-                toeplitz_tile(acc, hv, Q, P);
+                toeplitz_tile(acc, accB, hv, Q, P);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[slot]);
@@ -217,6 +226,11 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
             const bool tile_done = (k + 1 == p.NS);
             if (tile_done || it + 1 == n_units) {
                 // ---- flush this (CTA, tile) segment: tap groups -> warps -> one partial row ----
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    acc[r] += accB[r];
+                    accB[r] = 0.0f;
+                }
                 if (CL > 1) {
 #pragma unroll
                     for (int off = A; off < 32; off <<= 1) {

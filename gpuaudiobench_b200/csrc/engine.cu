@@ -390,10 +390,11 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
             for (int t = 0; t < nt; ++t) {
                 const float* src = host_ir + static_cast<size_t>(t0 + t) * L;
                 float* dst = stage.data() + static_cast<size_t>(t) * row;
+                // swizzled only when lanes of a warp read different tap blocks (otherwise a broadcast)
                 if (d.CL > 1) {
                     for (int j = 0; j < L; ++j) dst[swz_float(static_cast<uint32_t>(j))] = src[j];
                 } else {
-                    std::memcpy(dst, src, static_cast<size_t>(L) * sizeof(float));  // taps are a broadcast read
+                    std::memcpy(dst, src, static_cast<size_t>(L) * sizeof(float));
                 }
             }
             CU_TRY(cudaMemcpy(d.h + static_cast<size_t>(t0) * row, stage.data(), static_cast<size_t>(nt) * row * sizeof(float),

@@ -44,3 +44,67 @@ def stitch_sample_major(column_tiles, total_tracks):
         out += tile
     assert out.shape[1] == total_tracks
     return out
+
+
+class BusAllReduce:
+    """All-reduce of the stereo bus [2][B] across the ranks of `group`.
+
+    Preferred path: the engine's own one-shot kernel (csrc/bus_allreduce.cu) over a symmetric
+    peer-mapped buffer obtained from torch.distributed._symmetric_memory — P2P stores + flags over
+    NVLink, one launch, fixed summation order.  If symmetric memory cannot be set up (e.g. gloo in
+    the CPU tests, no P2P), it falls back to the NCCL/gloo all-reduce and says so in `.kind`.
+    """
+
+    def __init__(self, bus, group=None, force_nccl=False):
+        import ctypes as C
+
+        self.bus = bus
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.kind = "none (1 rank)" if self.world == 1 else "NCCL all-reduce"
+        self.epoch = 0
+        self._C = C
+        if self.world == 1 or force_nccl or not bus.is_cuda:
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            from . import engine
+            lib = engine.load_library()
+            n = bus.numel()
+            nbytes = lib.b200conv_bus_buffer_bytes(self.world, n)
+            self.buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=bus.device)
+            self.buf.zero_()
+            grp = group if group is not None else dist.group.WORLD
+            self.hdl = symm_mem.rendezvous(self.buf, grp.group_name if hasattr(grp, "group_name") else grp)
+            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+            self.ptrs = (C.c_uint64 * self.world)(*ptrs)
+            self.err = torch.zeros(1, dtype=torch.int32, device=bus.device)
+            self.lib = lib
+            torch.cuda.synchronize(bus.device)
+            dist.barrier(group)  # every rank's buffer is zeroed before the first push
+            self.kind = "own one-shot P2P kernel over NVLink symmetric memory (b200conv_bus_allreduce)"
+        except Exception as exc:  # pragma: no cover - depends on the box
+            self.kind = f"NCCL all-reduce (symmetric memory unavailable: {type(exc).__name__}: {exc})"
+
+    def __call__(self, stream=None):
+        """Reduce self.bus in place on the current (or given) CUDA stream."""
+        if self.world == 1:
+            return self.bus
+        if not self.kind.startswith("own"):
+            dist.all_reduce(self.bus, op=dist.ReduceOp.SUM, group=self.group)
+            return self.bus
+        C = self._C
+        self.epoch += 1
+        st = stream if stream is not None else torch.cuda.current_stream(self.bus.device).cuda_stream
+        rc = self.lib.b200conv_bus_allreduce(C.c_void_p(self.bus.data_ptr()), C.c_void_p(self.bus.data_ptr()), self.ptrs,
+                                             self.rank, self.world, self.bus.numel(), self.epoch,
+                                             C.c_void_p(self.err.data_ptr()), C.c_void_p(st))
+        if rc != 0:
+            raise RuntimeError(f"b200conv_bus_allreduce failed: {rc}")
+        return self.bus
+
+    def check(self):
+        if self.world > 1 and self.kind.startswith("own") and int(self.err.item()) != 0:
+            raise RuntimeError("bus all-reduce: a peer did not signal within the spin bound")

@@ -67,6 +67,10 @@ def load_library():
     L.b200conv_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.b200conv_plan.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_int32)]
     L.b200conv_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.b200conv_bus_buffer_bytes.argtypes = [C.c_int, C.c_int]
+    L.b200conv_bus_buffer_bytes.restype = C.c_size_t
+    L.b200conv_bus_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
+                                         C.c_uint32, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -148,6 +148,17 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info);
  * Replaces launchKernelTimed / CudaEventTimer (cuda/bench_utils.cuh:320-329). */
 int b200conv_set_profiling(b200conv_engine* e, int on);
 
+/* ---- the one collective of the path: all-reduce of the stereo bus over NVLink peer memory ----
+ * No reference counterpart (the reference is single-GPU).  `peer_buffers[p]` is the
+ * address, valid on THIS device, of rank p's symmetric buffer of b200conv_bus_buffer_bytes(world, n)
+ * bytes (zero-initialised once; e.g. torch.distributed._symmetric_memory, or cudaIpc / cuMem
+ * fabric handles).  `epoch` starts at 1 and increases by 1 per call on every rank.  d_local / d_out:
+ * float[n] on this device (n = 2*B).  Every rank gets the bit-identical sum (fixed rank order).
+ * d_error_flag (uint32 on this device) is set to 1 if a peer did not signal within the spin bound. */
+size_t b200conv_bus_buffer_bytes(int world, int n);
+int b200conv_bus_allreduce(const float* d_local, float* d_out, const uint64_t* peer_buffers, int rank, int world,
+                           int n, uint32_t epoch, uint32_t* d_error_flag, void* stream);
+
 /* Launch plan the engine would use for `cfg` on a device with `sm_count` SMs; needs no GPU.
  * plan[0..15] = direct: {A, CL, SPS, JSb, NS, G, Lc, cap, nbuf, xtile_blocks, ntiles, smem_bytes, MS, 0...}
  *               UPOLS : {P, M, logM, S, 0...}.  Used by the host-logic tests and by capacity planning. */

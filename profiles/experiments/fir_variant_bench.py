@@ -17,6 +17,7 @@ torch.cuda.synchronize(); e.set_profiling(True)
 for k in range(100):
     flush.fill_(k & 255); e.process(x[k % 8].data_ptr(), y.data_ptr(), mix.data_ptr())
 torch.cuda.synchronize(); q = e.query()
-ms = [m / q["stage_calls"] for m in q["stage_ms"][:3]]
-print(os.path.basename(engine.LIB_PATH), {k: os.environ[k] for k in os.environ if k.startswith("B200CONV")},
-      dict(zip(q["stage_name"], [round(m * 1e3, 2) for m in ms])), "us; FIR TFLOP/s", round(q["flops_per_block"] / ms[1] / 1e9, 2))
+n = q["stage_count"]; d = q["dominant_stage"]
+ms = [m / q["stage_calls"] for m in q["stage_ms"][:n]]
+print(os.path.basename(engine.LIB_PATH), (T, B, L), {k: os.environ[k] for k in os.environ if k.startswith("B200CONV")},
+      dict(zip(q["stage_name"], [round(m * 1e3, 2) for m in ms])), "us; FIR TFLOP/s", round(q["flops_per_block"] / ms[d] / 1e9, 2))
