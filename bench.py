@@ -150,9 +150,23 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     launches_before = eng.query()["kernel_launches"]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+
+    def aligned_start():
+        """barrier + synchronize, then every rank leaves at the same instant of the node-wide
+        monotonic clock: without it the first timed collective measures how late the slowest
+        rank's CPU woke up from the barrier (ms), not the step."""
+        if world > 1:
+            dist.barrier()
+            t_go = torch.tensor([time.clock_gettime(time.CLOCK_MONOTONIC) + 0.003], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_go, op=dist.ReduceOp.MAX)
+            t_go = float(t_go.item())
+            torch.cuda.synchronize(dev)
+            while time.clock_gettime(time.CLOCK_MONOTONIC) < t_go:
+                pass
+        else:
+            torch.cuda.synchronize(dev)
+
+    aligned_start()
     with ClockSampler(local_rank) as clocks:
         wall0 = time.perf_counter()
         for k in range(K):
@@ -231,9 +245,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
 
     for k in range(max(3, min(W, 10))):
         e2e_step(k)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+    aligned_start()
     e2e_lat = np.empty(K)
     for k in range(K):
         flush.fill_(k & 0xFF)
