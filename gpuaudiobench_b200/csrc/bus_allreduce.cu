@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(1024) bus_allreduce_kernel(PeerTable peers, co
                                                              uint32_t epoch, uint32_t* __restrict__ error_flag) {
     const int slot = epoch & 1u;
     const size_t data_floats = static_cast<size_t>(2) * world * n;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: `local` is written by the kernel launched before us
     // 1. push my partial to every rank (including myself)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float v = local[i];
@@ -88,7 +89,15 @@ extern "C" int b200conv_bus_allreduce(const float* d_local, float* d_out, const 
     PeerTable t{};
     for (int p = 0; p < world; ++p) t.buf[p] = reinterpret_cast<float*>(peer_buffers[p]);
     const int threads = n >= 1024 ? 1024 : ((n + 31) / 32 * 32 < 32 ? 32 : (n + 31) / 32 * 32);
-    bus_allreduce_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(t, d_local, d_out, rank, world, n, epoch,
-                                                                             d_error_flag);
-    return cudaGetLastError() == cudaSuccess ? B200CONV_OK : B200CONV_ERR_CUDA;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // hide our launch under the primary's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, bus_allreduce_kernel, t, d_local, d_out, rank, world, n, epoch, d_error_flag);
+    return err == cudaSuccess ? B200CONV_OK : B200CONV_ERR_CUDA;
 }

@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(kBusWarps * 32) fir_finish_mix_kernel(FinishPa
     const int T = p.T, B = p.B;
     const int ngroups = (T + kMixChunk - 1) / kMixChunk;
     float l = 0.0f, r = 0.0f;
-    pdl_wait_primary();  // partial rows come from the FIR kernel launched just before us
+    pdl_launch_dependents();  // e.g. the bus all-reduce kernel of a multi-GPU job
+    pdl_wait_primary();       // partial rows come from the FIR kernel launched just before us
     if (n < B) {
         const uint32_t ring_idx = swz_float(static_cast<uint32_t>(p.pos + n));
         for (int gi = blockIdx.y * kBusWarps + warp; gi < ngroups; gi += kBusWarps * gridDim.y) {
@@ -350,6 +351,7 @@ __global__ void __launch_bounds__(kBusWarps * 32) mix_cluster_kernel(const float
     const int n0 = blockIdx.x * 32, n = n0 + lane;
     const int ngroups = (T + kMixChunk - 1) / kMixChunk;
     float l = 0.0f, r = 0.0f;
+    pdl_launch_dependents();
     pdl_wait_primary();  // y comes from the kernel launched just before us
     if (n < B) {
         for (int gi = blockIdx.y * kBusWarps + warp; gi < ngroups; gi += kBusWarps * gridDim.y) {

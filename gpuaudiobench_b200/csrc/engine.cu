@@ -658,13 +658,44 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
     return finish_profile(e, marks);
 }
 
+namespace {
+// Pinned (cudaMallocHost / cudaHostRegister) memory is mapped into the device address space under
+// UVA: kernels can read and write it directly over PCIe, which removes the copy-engine hand-offs
+// (H2D -> kernel -> D2H dependencies cost ~10 us each) from the host-buffer call.
+bool is_pinned_host(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
 int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix, uint32_t flags) {
     if (!e || !h_in) return fail(B200CONV_ERR_INVALID, "b200conv_process_host: null argument");
     CU_TRY(cudaSetDevice(e->cfg.device));
     cudaStream_t st = e->own_stream;
     const size_t tb = static_cast<size_t>(e->T) * e->B;
-    CU_TRY(cudaMemcpyAsync(e->d_in_stage, h_in, tb * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = b200conv_process(e, e->d_in_stage, e->d_out_stage, h_mix ? e->d_mix_stage : nullptr, flags, st);
+    const int zc = env_int("B200CONV_ZEROCOPY", 3);  // bit 0: read the input in place; bit 1: write results in place
+    const bool direct = (e->cfg.algo == B200CONV_ALGO_DIRECT);
+    // input: every engine reads d_in once or twice -> read it straight from pinned host memory
+    const bool in_place = (zc & 1) && is_pinned_host(h_in);
+    // results: only the direct engine produces output and bus in its last kernel without re-reading them
+    const bool out_place = (zc & 2) && direct && h_out && is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
+    const float* d_in = h_in;
+    if (!in_place) {
+        CU_TRY(cudaMemcpyAsync(e->d_in_stage, h_in, tb * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_in = e->d_in_stage;
+    }
+    if (out_place) {
+        int rc = b200conv_process(e, d_in, h_out, h_mix, flags, st);
+        if (rc) return rc;
+        CU_TRY(cudaStreamSynchronize(st));
+        return B200CONV_OK;
+    }
+    int rc = b200conv_process(e, d_in, e->d_out_stage, h_mix ? e->d_mix_stage : nullptr, flags, st);
     if (rc) return rc;
     if (h_out) {
         if (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR && e->Tg != e->T) {

@@ -270,6 +270,33 @@ def test_process_with_device_buffers_on_torch_stream(oracle, algo):
     assert_parity(got, want, algo, "device-pointer stream")
 
 
+@pytest.mark.parametrize("algo", [g.ALGO_DIRECT, g.ALGO_UPOLS])
+@pytest.mark.parametrize("layout", [g.OUT_TRACK_MAJOR, g.OUT_SAMPLE_MAJOR])
+def test_host_call_with_pinned_buffers_zero_copy(oracle, algo, layout):
+    """b200conv_process_host on PINNED host buffers: the kernels read the input (and, for the direct
+    engine, write output + bus) in place over PCIe; results must equal the staged-copy path bit for bit."""
+    import torch
+    T, B, L, M = 12, 512, 3000, 8
+    xs = oracle.generate_input(M * T * B, 9).reshape(M, T, B)
+    h = oracle.generate_ir(T, L, "accel")
+    want = np.stack([oracle.stream(xs[:, t, :].ravel(), h[t]) for t in range(T)])
+    shape = (B, T) if layout == g.OUT_SAMPLE_MAJOR else (T, B)
+    h_in = torch.from_numpy(xs).pin_memory()
+    h_out = torch.zeros((M,) + shape).pin_memory()
+    h_mix = torch.zeros(M, 2, B).pin_memory()
+    with g.ConvEngine(T, B, L, algo, layout) as e:
+        e.load_ir(h)
+        for m in range(M):
+            e.process_host_ptr(h_in[m].data_ptr(), h_out[m].data_ptr(), h_mix[m].data_ptr())
+        e.reset()
+        staged = [e.process_host(xs[m], want_mix=True) for m in range(M)]  # pageable numpy -> staged copies
+    got = h_out.numpy()
+    for m in range(M):
+        assert np.array_equal(got[m], staged[m][0]) and np.array_equal(h_mix[m].numpy(), staged[m][1])
+    got_tm = np.concatenate([(got[m].T if layout == g.OUT_SAMPLE_MAJOR else got[m]) for m in range(M)], axis=1)
+    assert_parity(got_tm, want, algo, "pinned zero-copy host call")
+
+
 # ---------------------------------------------------------------------------------------------
 # Full BASELINE sizes: size-independent properties + a track subset against the oracle
 # ---------------------------------------------------------------------------------------------
