@@ -66,8 +66,6 @@ struct UpolsState {
     float2* H = nullptr;
     float2* X = nullptr;
     float2* Ypart = nullptr;
-    float2* tw_c = nullptr;
-    float2* tw_r = nullptr;
     float* prev = nullptr;
     unsigned* counters = nullptr;
     bool fused = false;
@@ -176,27 +174,6 @@ int plan_upols(b200conv_engine* e) {
     }
     u.S = std::max(1, std::min({S, u.P, 32}));
     u.fused = (u.M <= kFusedMaxM) && env_int("B200CONV_UPOLS_FUSED", 1) != 0;
-    return B200CONV_OK;
-}
-
-int upload_twiddles(b200conv_engine* e) {
-    UpolsState& u = e->up;
-    const int M = u.M;
-    std::vector<float2> tc(M), tr(M / 2 + 1);
-    const double two_pi = 6.283185307179586476925286766559;
-    for (int q = 0; q < M; ++q) {
-        double a = -two_pi * q / M;
-        tc[q] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
-    }
-    for (int k = 0; k <= M / 2; ++k) {
-        double a = -two_pi * k / (2.0 * M);
-        tr[k] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
-    }
-    int rc;
-    if ((rc = dev_alloc(e, &u.tw_c, tc.size(), false))) return rc;
-    if ((rc = dev_alloc(e, &u.tw_r, tr.size(), false))) return rc;
-    CU_TRY(cudaMemcpy(u.tw_c, tc.data(), tc.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(u.tw_r, tr.data(), tr.size() * sizeof(float2), cudaMemcpyHostToDevice));
     return B200CONV_OK;
 }
 
@@ -352,7 +329,6 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if ((rc = dev_alloc(e, &u.Ypart, static_cast<size_t>(u.S) * e->T * u.M))) return bail(rc);
         if ((rc = dev_alloc(e, &u.prev, tb))) return bail(rc);
         if ((rc = dev_alloc(e, &u.counters, static_cast<size_t>(e->T)))) return bail(rc);
-        if ((rc = upload_twiddles(e))) return bail(rc);
     }
     err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) return bail(fail(B200CONV_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(err)));
@@ -430,8 +406,6 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
                 p.M = u.M;
                 p.logM = u.logM;
                 p.scale = 1.0f / static_cast<float>(2 * B);
-                p.tw_c = u.tw_c;
-                p.tw_r = u.tw_r;
                 err = launch_rfft_fwd(p, nullptr);
                 e->launches += 1;
                 if (err == cudaSuccess) err = cudaDeviceSynchronize();
@@ -500,8 +474,6 @@ int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
             p.M = u.M;
             p.logM = u.logM;
             p.scale = 1.0f;
-            p.tw_c = u.tw_c;
-            p.tw_r = u.tw_r;
             err = launch_rfft_fwd(p, nullptr);
             e->launches += 1;
         }
@@ -598,8 +570,6 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
             fp.sample_major = sample_major;
             fp.Tg = e->Tg;
             fp.toff = e->toff;
-            fp.tw_c = u.tw_c;
-            fp.tw_r = u.tw_r;
             CU_TRY(launch_upols_fused(fp, st));
             e->launches += 1;
             tm.mark();
@@ -617,8 +587,6 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
             f.M = u.M;
             f.logM = u.logM;
             f.scale = 1.0f;
-            f.tw_c = u.tw_c;
-            f.tw_r = u.tw_r;
             CU_TRY(launch_rfft_fwd(f, st));
             tm.mark();
             MacParams m{};
@@ -642,8 +610,6 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
             r.sample_major = sample_major;
             r.Tg = e->Tg;
             r.toff = e->toff;
-            r.tw_c = u.tw_c;
-            r.tw_r = u.tw_r;
             CU_TRY(launch_irfft_ols(r, st));
             e->launches += 3;
         }

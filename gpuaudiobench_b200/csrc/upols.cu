@@ -28,6 +28,15 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
+// e^{-2 pi i q / n} for integers 0 <= q, n a power of two: the argument of sincospif is exact, the
+// result is within 1 ulp, and — unlike a table — it costs no dependent memory access (the FFT phases
+// of the fused kernel are latency chains while HBM sits idle).
+__device__ __forceinline__ float2 twiddle(int q, float inv_n) {
+    float sn, cs;
+    sincospif(-2.0f * static_cast<float>(q) * inv_n, &sn, &cs);
+    return make_float2(cs, sn);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Complex FFT of size M on shared memory (Stockham autosort, out-of-place between a and b).
 // Pass with sub-transform length Ns and radix R, butterfly j < M/R:
@@ -38,8 +47,8 @@ __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y
 // Returns the buffer that holds the result.
 // ---------------------------------------------------------------------------------------------
 template <bool INV>
-__device__ float2* fft_stockham(float2* a, float2* b, int M, int logM, const float2* __restrict__ tw, int tx,
-                                int TX, bool active) {
+__device__ float2* fft_stockham(float2* a, float2* b, int M, int logM, int tx, int TX, bool active) {
+    const float inv_m = 1.0f / static_cast<float>(M);
     int Ns = 1;
     if (logM & 1) {
         if (active) {
@@ -65,9 +74,9 @@ __device__ float2* fft_stockham(float2* a, float2* b, int M, int logM, const flo
                 float2 v2 = a[j + 2 * quarter];
                 float2 v3 = a[j + 3 * quarter];
                 if (k != 0) {
-                    float2 w1 = tw[k * tstride];
-                    float2 w2 = tw[2 * k * tstride];
-                    float2 w3 = tw[3 * k * tstride];
+                    float2 w1 = twiddle(k * tstride, inv_m);
+                    float2 w2 = twiddle(2 * k * tstride, inv_m);
+                    float2 w3 = twiddle(3 * k * tstride, inv_m);
                     if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
                     v1 = cmul(v1, w1);
                     v2 = cmul(v2, w2);
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(256) rfft_fwd_kernel(RfftParams p, int TX, int
         }
     }
     __syncthreads();
-    const float2* z = fft_stockham<false>(a, b, M, p.logM, p.tw_c, tx, TX, active);
+    const float2* z = fft_stockham<false>(a, b, M, p.logM, tx, TX, active);
     if (!active) return;
 
     float2* out = p.out + static_cast<size_t>(w) * p.out_stride;
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__(256) rfft_fwd_kernel(RfftParams p, int TX, int
         const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y + Bc.y));
         const float2 D = make_float2(0.5f * (A.x - Bc.x), 0.5f * (A.y - Bc.y));
         const float2 O = make_float2(D.y, -D.x);  // -i * D
-        const float2 WO = cmul(p.tw_r[k], O);
+        const float2 WO = cmul(twiddle(k, 0.5f / static_cast<float>(M)), O);
         const float2 Xk = cadd(E, WO);
         const float2 Xmk = make_float2(E.x - WO.x, -(E.y - WO.y));  // X[M-k] = conj(E - W O)
         if (k == 0) {
@@ -265,13 +274,13 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
             const float2 Bc = cconj(Bm);
             const float2 E = cadd(A, Bc);
             const float2 D = csub(A, Bc);
-            const float2 O = cmul(cconj(p.tw_r[k]), D);
+            const float2 O = cmul(cconj(twiddle(k, 0.5f / static_cast<float>(M))), D);
             a[k] = make_float2(E.x - O.y, E.y + O.x);
             if (k != 0 && k != half) a[M - k] = make_float2(E.x + O.y, O.x - E.y);
         }
     }
     __syncthreads();
-    const float2* z = fft_stockham<true>(a, b, M, p.logM, p.tw_c, tx, TX, active);
+    const float2* z = fft_stockham<true>(a, b, M, p.logM, tx, TX, active);
     if (!active) return;
 
     if (!p.sample_major) {
@@ -298,7 +307,11 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 #ifndef B200CONV_FUSED_UNROLL
 #define B200CONV_FUSED_UNROLL 2
 #endif
-constexpr int kFusedUnroll = B200CONV_FUSED_UNROLL;  // partitions in flight per thread (x2 loads); 32-register budget
+constexpr int kFusedUnroll = B200CONV_FUSED_UNROLL;
+#ifndef B200CONV_FUSED_PREFETCH
+#define B200CONV_FUSED_PREFETCH 8
+#endif
+constexpr int kPrefetchParts = B200CONV_FUSED_PREFETCH;  // partitions pulled into L2 under the forward FFT  // partitions in flight per thread (x2 loads); 32-register budget
 
 __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
     extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
@@ -311,6 +324,25 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
     const float2* xsm = nullptr;  // packed X_m in shared memory (split 0 only)
     pdl_launch_dependents();      // the bus kernel may be scheduled as our CTAs retire
 
+    // Keep HBM busy while this CTA runs its forward FFT: pull the first kPrefetchParts partitions of
+    // its H rows and ring slots into L2 (no registers, no waiting); the MAC loop then finds them there.
+    {
+        const int Pp = p.P, Up = M >> 1;
+        const int pf0 = static_cast<int>(static_cast<long long>(Pp) * s / p.S);
+        const int pf1 = static_cast<int>(static_cast<long long>(Pp) * (s + 1) / p.S);
+        const int lines_per_row = (Up * 16) >> 7;  // 128-byte lines per partition row (M*8 bytes)
+        const int total = min(kPrefetchParts, pf1 - pf0) * lines_per_row;
+        for (int i = tid; i < total; i += 256) {
+            const int q = pf0 + i / lines_per_row, ln = i - (i / lines_per_row) * lines_per_row;
+            int sl = p.slot0 + q;
+            if (sl >= Pp) sl -= Pp;
+            const char* hrow = reinterpret_cast<const char*>(p.H + (static_cast<size_t>(t) * Pp + q) * M) + ln * 128;
+            const char* xrow = reinterpret_cast<const char*>(p.X + (static_cast<size_t>(t) * Pp + sl) * M) + ln * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(hrow));
+            if (q != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow));  // slot0 itself is written below
+        }
+    }
+
     if (s == 0) {
         const float2* in2 = reinterpret_cast<const float2*>(p.d_in + static_cast<size_t>(t) * M);
         float2* prev2 = reinterpret_cast<float2*>(p.prev + static_cast<size_t>(t) * M);
@@ -321,7 +353,7 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
             if (p.commit) prev2[n] = cv;
         }
         __syncthreads();
-        float2* z = fft_stockham<false>(a, b, M, p.logM, p.tw_c, tid, 256, true);
+        float2* z = fft_stockham<false>(a, b, M, p.logM, tid, 256, true);
         float2* xo = (z == a) ? b : a;
         float2* ring = p.X + (static_cast<size_t>(t) * p.P + p.slot0) * M;
         for (int k = tid; k <= half; k += 256) {
@@ -329,7 +361,7 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
             const float2 Bc = cconj(z[(M - k) & (M - 1)]);
             const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y + Bc.y));
             const float2 D = make_float2(0.5f * (A.x - Bc.x), 0.5f * (A.y - Bc.y));
-            const float2 WO = cmul(p.tw_r[k], make_float2(D.y, -D.x));
+            const float2 WO = cmul(twiddle(k, 0.5f / static_cast<float>(M)), make_float2(D.y, -D.x));
             const float2 Xk = cadd(E, WO);
             const float2 Xmk = make_float2(E.x - WO.x, -(E.y - WO.y));
             if (k == 0) {
@@ -438,12 +470,12 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
         }
         const float2 Bc = cconj(Bm);
         const float2 E = cadd(A, Bc);
-        const float2 O = cmul(cconj(p.tw_r[k]), csub(A, Bc));
+        const float2 O = cmul(cconj(twiddle(k, 0.5f / static_cast<float>(M))), csub(A, Bc));
         a[k] = make_float2(E.x - O.y, E.y + O.x);
         if (k != 0 && k != half) a[M - k] = make_float2(E.x + O.y, O.x - E.y);
     }
     __syncthreads();
-    const float2* z = fft_stockham<true>(a, b, M, p.logM, p.tw_c, tid, 256, true);
+    const float2* z = fft_stockham<true>(a, b, M, p.logM, tid, 256, true);
     if (!p.sample_major) {
         float2* out2 = reinterpret_cast<float2*>(p.out + static_cast<size_t>(t) * M);
         for (int n = tid; n < half; n += 256) out2[n] = z[half + n];

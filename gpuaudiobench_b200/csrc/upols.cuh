@@ -23,8 +23,6 @@ struct RfftParams {
     int M;      // complex FFT size = bins per partition = B
     int logM;
     float scale;
-    const float2* tw_c;  // e^{-2 pi i q / M},  q < M
-    const float2* tw_r;  // e^{-2 pi i k / 2M}, k <= M/2
 };
 
 // Y[s][t][k] = sum_{p in split s} H[t][p][k] * X[t][(slot0 + p) mod P][k]
@@ -43,8 +41,6 @@ struct IrfftParams {
     float* out;           // [T][B] or [B][Tg]
     int T, M, logM;
     int sample_major, Tg, toff;
-    const float2* tw_c;
-    const float2* tw_r;
 };
 
 // One launch per block for M = B <= 512: forward FFT (split 0) + FDL-MAC + inverse/overlap-save (last CTA).
@@ -58,8 +54,6 @@ struct FusedParams {
     float* out;           // [T][B] or [B][Tg]
     int T, P, M, logM, S, slot0, commit;
     int sample_major, Tg, toff;
-    const float2* tw_c;
-    const float2* tw_r;
 };
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st);
 constexpr int kFusedMaxM = 512;
