@@ -223,6 +223,14 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
         roofline = {"bound": "hbm", "kernel": q["stage_name"][dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": f"hbm_gbs of {peak_src} (measured copy)",
                     "algorithmic_bytes_per_launch": q["alg_bytes_per_block"]}
+    try:  # per-launch DRAM traffic of the dominant kernel, from the committed ncu capture (null if none for this workload)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f).get(name)
+        if tr and tr["kernel"] == q["stage_name"][dom]:
+            roofline["traffic"] = tr["bytes"]
+            roofline["traffic_source"] = "profiles/r01_traffic.json (ncu --set full, one launch)"
+    except Exception:
+        pass
     roofline["kernel_ms"] = dom_ms
     roofline["stage_ms"] = dict(zip(q["stage_name"][:q["stage_count"]], stage_ms))
     roofline["kernel_share_of_step"] = dom_ms / sum(stage_ms)
@@ -373,6 +381,26 @@ def run_reference(args, rank, world):
             "rt_tracks": value * 1e9 / (L * FS), "gpu_launches": 0}
 
 
+def run_sweep(args, rank, world, local_rank, dist):
+    """BASELINE config 5: buffer-size sweep 32..4096 at C4's per-GPU tracks and IR length (UPOLS) and
+    at C2's (direct): throughput vs p50/p99 per-buffer latency vs the B/fs deadline."""
+    rows = []
+    for algo_name, T, L, sizes in (("upols", 512, 96000, (32, 64, 128, 256, 512, 1024, 2048, 4096)),
+                                   ("direct", 128, 16384, (32, 64, 128, 256, 512, 1024, 2048, 4096))):
+        for B in sizes:
+            key = f"sweep_{algo_name}_{B}"
+            WORKLOADS[key] = (algo_name, T, B, L, "track_major", f"sweep: {algo_name} {T} tracks/GPU x {B}-sample buffers x {L}-tap IR")
+            sub = argparse.Namespace(**vars(args))
+            sub.steps = min(args.steps, 100)
+            r = run_workload(key, sub, rank, world, local_rank, dist, want_cpu_baseline=False)
+            rows.append({"algo": algo_name, "block": B, "tracks_per_gpu": T, "ir_taps": L, "n_gpus": world,
+                         "ms_per_step": r["ms_per_step"], "gmac_per_s": r["value"], "rt_tracks": r["rt_tracks"],
+                         "p50_ms": r["latency_ms"]["p50"], "p99_ms": r["latency_ms"]["p99"], "deadline_ms": r["latency_ms"]["deadline"],
+                         "meets_deadline": r["latency_ms"]["meets_deadline"], "e2e_ms": r["e2e"]["ms_per_step"],
+                         "roofline_frac": r["roofline"]["frac"], "roofline_bound": r["roofline"]["bound"]})
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -381,6 +409,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads in the default line")
+    ap.add_argument("--sweep", action="store_true", help="buffer-size sweep (BASELINE config 5): one JSON line with a table")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -402,6 +431,14 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.sweep:
+        rows = run_sweep(args, rank, world, local_rank, dist)
+        if rank == 0:
+            print(json.dumps({"sweep": rows, "n_gpus": world, "fs": FS}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     result = run_workload(args.workload, args, rank, world, local_rank, dist, want_cpu_baseline=(rank == 0 and world == 1))
     if not args.no_also and args.workload == "c2":
         also = {}
