@@ -21,7 +21,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 ENGINE_SRCS = ["engine.cu", "direct_fir.cu", "upols.cu", "peak.cu", "bus_allreduce.cu"]
 HOST_SRCS = ["bench_utils.cu", "globals.cu", "bench_base.cu", "conv_common.cu", "bench_conv1d.cu", "bench_conv1d_accel.cu",
-             "registry.cu", "plugin_capi.cu"]
+             "bench_fft.cu", "registry.cu", "plugin_capi.cu"]
 
 
 def _newer(target, sources):

@@ -722,6 +722,28 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
     return B200CONV_OK;
 }
 
+int b200conv_rfft(const float* d_in, void* d_out, int count, int n, void* stream) {
+    if (!d_in || !d_out || count < 1) return fail(B200CONV_ERR_INVALID, "b200conv_rfft: bad argument");
+    if (!is_pow2(static_cast<uint32_t>(n)) || n < 32 || n > 8192)
+        return fail(B200CONV_ERR_INVALID, "b200conv_rfft: n must be a power of two in [32, 8192]");
+    RfftParams p{};
+    const int M = n / 2;
+    p.first = d_in;  // window = [first half | second half] of each row
+    p.first_stride = n;
+    p.second = d_in + M;
+    p.second_stride = n;
+    p.out = static_cast<float2*>(d_out);
+    p.out_stride = M + 1;
+    p.prev_out = nullptr;
+    p.count = count;
+    p.M = M;
+    p.logM = ilog2(static_cast<uint32_t>(M));
+    p.scale = 1.0f;
+    p.unpacked = 1;
+    CU_TRY(launch_rfft_fwd(p, static_cast<cudaStream_t>(stream)));
+    return B200CONV_OK;
+}
+
 int b200conv_set_profiling(b200conv_engine* e, int on) {
     if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_set_profiling: null engine");
     e->profiling = (on != 0);

@@ -148,7 +148,12 @@ __global__ void __launch_bounds__(256) rfft_fwd_kernel(RfftParams p, int TX, int
         const float2 Xk = cadd(E, WO);
         const float2 Xmk = make_float2(E.x - WO.x, -(E.y - WO.y));  // X[M-k] = conj(E - W O)
         if (k == 0) {
-            out[0] = make_float2(sc * Xk.x, sc * Xmk.x);  // {DC, Nyquist}
+            if (p.unpacked) {
+                out[0] = make_float2(sc * Xk.x, 0.0f);   // DC
+                out[M] = make_float2(sc * Xmk.x, 0.0f);  // Nyquist
+            } else {
+                out[0] = make_float2(sc * Xk.x, sc * Xmk.x);  // {DC, Nyquist}
+            }
         } else {
             out[k] = make_float2(sc * Xk.x, sc * Xk.y);
             if (k != half) out[M - k] = make_float2(sc * Xmk.x, sc * Xmk.y);

@@ -23,6 +23,7 @@ struct RfftParams {
     int M;      // complex FFT size = bins per partition = B
     int logM;
     float scale;
+    int unpacked;  // 0: M packed bins (bin 0 = {DC, Nyquist}); 1: M+1 plain complex bins (cuFFT R2C layout)
 };
 
 // Y[s][t][k] = sum_{p in split s} H[t][p][k] * X[t][(slot0 + p) mod P][k]

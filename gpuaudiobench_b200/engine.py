@@ -67,6 +67,7 @@ def load_library():
     L.b200conv_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.b200conv_plan.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_int32)]
     L.b200conv_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.b200conv_rfft.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200conv_bus_buffer_bytes.argtypes = [C.c_int, C.c_int]
     L.b200conv_bus_buffer_bytes.restype = C.c_size_t
     L.b200conv_bus_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
@@ -100,6 +101,11 @@ def measure_fp32_peak(device=0):
     tf, ms = C.c_double(), C.c_double()
     _check(load_library().b200conv_measure_fp32_peak(device, C.byref(tf), C.byref(ms)))
     return tf.value, ms.value
+
+
+def rfft(d_in, d_out, count, n, stream=0):
+    """Batched R2C FFT on device buffers (addresses): d_out float2 [count][n/2+1]."""
+    _check(load_library().b200conv_rfft(C.c_void_p(d_in), C.c_void_p(d_out), count, n, C.c_void_p(stream) if stream else None))
 
 
 def _host_ptr(a):

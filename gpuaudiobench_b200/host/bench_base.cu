@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <iomanip>
 #include <iostream>
+#include <memory>
 #include <stdexcept>
 
 GPUABenchmark::GPUABenchmark(const std::string& name, size_t buffer_size, size_t track_count)
@@ -65,6 +66,15 @@ GPUABenchmark::BenchmarkResult GPUABenchmark::runWithIteration(int iterations, i
     res.track_count = track_count_;
     res.iterations = iterations;
 
+    // DAW-style pacing: after every iteration (warm-up included) wait for the next buffer period,
+    // as the Metal port does (GPUABenchmark.swift:371-390)
+    std::unique_ptr<BenchmarkUtils::DAWSimulator> daw;
+    if (DAWSIM)
+        daw = std::make_unique<BenchmarkUtils::DAWSimulator>(
+            static_cast<double>(buffer_size_) / FS,
+            DAWSIM_SLEEP ? BenchmarkUtils::DAWSimulator::Mode::SLEEP : BenchmarkUtils::DAWSimulator::Mode::SPIN,
+            DAWSIM_JITTER_US * 1e-6);
+
     if (warmupIterations > 0) {
         std::printf("Running %d warmup iterations...\n", warmupIterations);
         for (int w = 1; w <= warmupIterations; ++w) {
@@ -75,6 +85,7 @@ GPUABenchmark::BenchmarkResult GPUABenchmark::runWithIteration(int iterations, i
             } catch (const std::exception& ex) {  // the reference reports and carries on
                 std::printf("  Warmup iteration %d failed: %s\n", w, ex.what());
             }
+            if (daw) daw->wait();
         }
         std::printf("Warmup complete, starting timed iterations...\n");
     }
@@ -86,6 +97,7 @@ GPUABenchmark::BenchmarkResult GPUABenchmark::runWithIteration(int iterations, i
         resetGpuIterationMetrics();
         res.latencies.push_back(static_cast<float>(BenchmarkUtils::BenchmarkTimer::measureKernel(iterationBody)));
         device_ms.push_back(current_iteration_gpu_ms_);
+        if (daw) daw->wait();
     }
     res.statistics = BenchmarkUtils::calculateStatistics(res.latencies);
     if (std::any_of(device_ms.begin(), device_ms.end(), [](float v) { return v > 0.0f; })) {

@@ -8,6 +8,7 @@
 #include <numeric>
 #include <random>
 #include <stdexcept>
+#include <thread>
 
 namespace BenchmarkUtils {
 
@@ -125,6 +126,36 @@ void collectLatencies(std::vector<float>& latencies, std::function<void()> bench
     latencies.assign(0, 0.0f);
     latencies.reserve(iterations);
     for (int i = 0; i < iterations; ++i) latencies.push_back(static_cast<float>(BenchmarkTimer::measureKernel(benchmark)));
+}
+
+DAWSimulator::DAWSimulator(double buffer_duration_s, Mode mode, double jitter_s, unsigned seed)
+    : period_(buffer_duration_s), jitter_(jitter_s), mode_(mode), rng_(0x9E3779B97F4A7C15ull ^ seed) {}
+
+void DAWSimulator::wait() {
+    using clock = std::chrono::steady_clock;
+    const auto period = std::chrono::duration_cast<clock::duration>(std::chrono::duration<double>(period_));
+    const auto now = clock::now();
+    if (!armed_) {
+        next_start_ = now + period;
+        armed_ = true;
+    }
+    double jitter = 0.0;
+    if (jitter_ > 0.0) {  // xorshift64*: uniform in [-jitter, +jitter]
+        rng_ ^= rng_ >> 12;
+        rng_ ^= rng_ << 25;
+        rng_ ^= rng_ >> 27;
+        const double u = static_cast<double>((rng_ * 0x2545F4914F6CDD1Dull) >> 11) / 9007199254740992.0;
+        jitter = (2.0 * u - 1.0) * jitter_;
+    }
+    const auto target = next_start_ + std::chrono::duration_cast<clock::duration>(std::chrono::duration<double>(jitter));
+    if (target > now) {
+        if (mode_ == Mode::SLEEP)
+            std::this_thread::sleep_until(target);
+        else
+            while (clock::now() < target) {
+            }
+    }
+    next_start_ += period;
 }
 
 // ---- data ---------------------------------------------------------------------------------------

@@ -63,6 +63,26 @@ private:
 
 void collectLatencies(std::vector<float>& latencies, std::function<void()> benchmark, int iterations);
 
+// Paces iterations like an audio callback: wait() returns at the next multiple of the buffer period
+// (optionally jittered), spinning or sleeping.  Semantics of the reference's Metal DAWSimulator
+// (BenchmarkUtilities.swift:151-178): the first call arms nextStart = now + period; every call waits
+// until nextStart (+ uniform jitter in [-j, +j]) if that is still in the future, then advances
+// nextStart by one period — an iteration that overruns its period is not waited for.
+class DAWSimulator {
+public:
+    enum class Mode { SPIN, SLEEP };
+    DAWSimulator(double buffer_duration_s, Mode mode, double jitter_s, unsigned seed = 1);
+    void wait();
+    double bufferDuration() const { return period_; }
+
+private:
+    double period_, jitter_;
+    Mode mode_;
+    bool armed_ = false;
+    std::chrono::steady_clock::time_point next_start_{};
+    uint64_t rng_;
+};
+
 // ---- data ---------------------------------------------------------------------------------------
 // std::mt19937(seed) + uniform_real_distribution<float>(-1, 1), one sequential draw (bench_utils.cu:238-245)
 void generateRandomAudioData(float* buffer, size_t samples, unsigned int seed = 42);

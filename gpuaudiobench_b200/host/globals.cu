@@ -15,6 +15,9 @@ bool JSON_OUTPUT = false;
 int IR_LEN = 0;
 int WARMUP_RUNS = 3;
 bool STREAM_MODE = false;
+bool DAWSIM = false;
+bool DAWSIM_SLEEP = false;
+double DAWSIM_JITTER_US = 0.0;
 
 LatencySummary summarizeLatencies(const std::vector<float>& lat) {
     LatencySummary s{};

@@ -15,6 +15,12 @@ extern bool JSON_OUTPUT;         // --json
 extern int IR_LEN;               // --irLen   (0 = the plugin's default: 1024 direct, 512 accel)
 extern int WARMUP_RUNS;          // --warmup  (3, the value main.cu:130 hard-codes)
 extern bool STREAM_MODE;         // --mode stream: advance the convolution state every iteration
+// DAW-style periodic submission.  The reference's CUDA port only has unused compile-time stubs
+// (cuda/globals.cuh:28-30 ENABLE_DAWSIM_SLEEP / SLEEP_MS / ENABLE_DAWSIM_SPIN); the behaviour follows
+// its Metal port (metal-swift/.../Core/BenchmarkUtilities.swift:140-178, flags main.swift:110-132).
+extern bool DAWSIM;              // --dawsim: wait for the next buffer period after every iteration
+extern bool DAWSIM_SLEEP;        // --dawsim-mode sleep|spin (default spin)
+extern double DAWSIM_JITTER_US;  // --dawsim-jitter-us: uniform +/- jitter on each wake-up
 
 struct LatencySummary {
     float min_ms, max_ms, avg_ms, p50_ms, p95_ms, p99_ms, threshold_ms;

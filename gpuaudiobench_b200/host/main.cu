@@ -38,10 +38,14 @@ static void printHelp() {
     std::printf("  --irLen [taps]      Impulse response length (default: 1024 Conv1D, 512 Conv1D_accel)\n");
     std::printf("  --warmup [count]    Warm-up iterations before timing (default: 3)\n");
     std::printf("  --mode [stateless|stream]  stateless re-submits one buffer (reference behaviour, default);\n");
-    std::printf("                      stream advances the convolution state every iteration\n\n");
+    std::printf("                      stream advances the convolution state every iteration\n");
+    std::printf("  --dawsim            Pace iterations at the buffer period bufferSize/fs (DAW-style submission)\n");
+    std::printf("  --dawsim-mode [spin|sleep]   how to wait for the next period (default: spin)\n");
+    std::printf("  --dawsim-jitter-us [us]      uniform +/- jitter on every wake-up (default: 0)\n\n");
     std::printf("Digital Signal Processing:\n");
     std::printf("  Conv1D           - 1D convolution (direct form, FP32 FMA bound)\n");
-    std::printf("  Conv1D_accel     - Accelerated 1D convolution (partitioned overlap-save FFT, HBM bound)\n\n");
+    std::printf("  Conv1D_accel     - Accelerated 1D convolution (partitioned overlap-save FFT, HBM bound)\n");
+    std::printf("  FFT1D            - 1D Fast Fourier Transform (1024-point R2C per track, shared-memory Stockham)\n\n");
     std::printf("Examples:\n");
     std::printf("  gpubench --benchmark Conv1D --nTracks 128 --irLen 16384\n");
     std::printf("  gpubench --benchmark Conv1D_accel --bufferSize 256 --nTracks 1024 --irLen 65536 --json\n\n");
@@ -97,6 +101,20 @@ int main(int argc, char** argv) {
             if (!need_value("--outputfile")) return 1;
             OUTPUT_FILE = argv[++i];
             std::printf("Output file set to: %s\n", OUTPUT_FILE.c_str());
+            continue;
+        }
+        if (!std::strcmp(arg, "--dawsim")) {
+            DAWSIM = true;
+            continue;
+        }
+        if (!std::strcmp(arg, "--dawsim-mode")) {
+            if (!need_value("--dawsim-mode")) return 1;
+            DAWSIM_SLEEP = !std::strcmp(argv[++i], "sleep");
+            continue;
+        }
+        if (!std::strcmp(arg, "--dawsim-jitter-us")) {
+            if (!need_value("--dawsim-jitter-us")) return 1;
+            DAWSIM_JITTER_US = std::atof(argv[++i]);
             continue;
         }
         if (!std::strcmp(arg, "--mode")) {

@@ -1,6 +1,7 @@
 // plugin_capi.cu — include/gpubench_plugin.h over the plugin classes (libgpubench_b200.so).
 #include "gpubench_plugin.h"
 
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -8,6 +9,7 @@
 
 #include "bench_conv1d.cuh"
 #include "bench_conv1d_accel.cuh"
+#include "bench_fft.cuh"
 #include "conv_common.cuh"
 #include "registry.cuh"
 
@@ -15,6 +17,7 @@ struct gpubench_plugin {
     std::unique_ptr<GPUABenchmark> bench;
     Conv1DBenchmark* direct = nullptr;
     Conv1DAccelBenchmark* accel = nullptr;
+    FFTBenchmark* fft = nullptr;
 };
 
 namespace {
@@ -41,6 +44,23 @@ void gpubench_set_globals(int fs, int nruns, int stream_mode) {
     STREAM_MODE = (stream_mode != 0);
 }
 
+void gpubench_set_dawsim(int enable, int sleep_mode, double jitter_us) {
+    DAWSIM = (enable != 0);
+    DAWSIM_SLEEP = (sleep_mode != 0);
+    DAWSIM_JITTER_US = jitter_us;
+}
+
+int gpubench_dawsim_probe(double period_s, int sleep_mode, double jitter_us, int n, double* wake_times_s) {
+    BenchmarkUtils::DAWSimulator sim(period_s, sleep_mode ? BenchmarkUtils::DAWSimulator::Mode::SLEEP
+                                                           : BenchmarkUtils::DAWSimulator::Mode::SPIN, jitter_us * 1e-6);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; ++i) {
+        sim.wait();
+        wake_times_s[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return 0;
+}
+
 gpubench_plugin* gpubench_create(const char* name, int ir_len, int buffer_size, int track_count) {
     if (!name) return nullptr;
     BUFSIZE = buffer_size;
@@ -54,6 +74,7 @@ gpubench_plugin* gpubench_create(const char* name, int ir_len, int buffer_size, 
     auto* p = new gpubench_plugin();
     p->direct = dynamic_cast<Conv1DBenchmark*>(bench.get());
     p->accel = dynamic_cast<Conv1DAccelBenchmark*>(bench.get());
+    p->fft = dynamic_cast<FFTBenchmark*>(bench.get());
     p->bench = std::move(bench);
     return p;
 }
@@ -86,11 +107,17 @@ int gpubench_validate(gpubench_plugin* p, gpubench_validation* out, char* messag
             out->status = static_cast<int>(v.status);
             out->max_error = v.max_error;
             out->mean_error = v.mean_error;
-            const float* ref = p->direct ? p->direct->cpuReference() : p->accel->cpuReference();
-            const ConvCommon::Accuracy a = ConvCommon::measureAccuracy(p->bench->hostOutput(), ref, p->bench->getTotalElements());
-            out->snr_db = a.snr_db;
-            out->max_abs_err = a.max_abs_err;
-            out->ref_peak = a.ref_peak;
+            if (p->fft) {
+                out->snr_db = p->fft->lastSnrDb();
+                out->max_abs_err = v.max_error;
+                out->ref_peak = 0.0;
+            } else {
+                const float* ref = p->direct ? p->direct->cpuReference() : p->accel->cpuReference();
+                const ConvCommon::Accuracy a = ConvCommon::measureAccuracy(p->bench->hostOutput(), ref, p->bench->getTotalElements());
+                out->snr_db = a.snr_db;
+                out->max_abs_err = a.max_abs_err;
+                out->ref_peak = a.ref_peak;
+            }
         }
         if (messages && cap) {
             std::string joined;
@@ -105,6 +132,10 @@ const float* gpubench_host_input(gpubench_plugin* p) { return p->bench->hostInpu
 const float* gpubench_host_ir(gpubench_plugin* p) { return p->direct ? p->direct->hostIR() : p->accel->hostIR(); }
 const float* gpubench_host_output(gpubench_plugin* p) { return p->bench->hostOutput(); }
 const float* gpubench_cpu_reference(gpubench_plugin* p) { return p->direct ? p->direct->cpuReference() : p->accel->cpuReference(); }
+
+const float* gpubench_fft_input(gpubench_plugin* p) { return p->fft ? p->fft->hostInputFFT() : nullptr; }
+const float* gpubench_fft_output(gpubench_plugin* p) { return p->fft ? reinterpret_cast<const float*>(p->fft->hostOutputFFT()) : nullptr; }
+const float* gpubench_fft_reference(gpubench_plugin* p) { return p->fft ? reinterpret_cast<const float*>(p->fft->cpuReferenceFFT()) : nullptr; }
 
 int gpubench_json_results(const float* lat, size_t n, const char* name, int fs, int bufsize, int ntracks, char* out, size_t cap) {
     FS = fs;

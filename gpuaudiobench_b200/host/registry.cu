@@ -5,6 +5,7 @@
 
 #include "bench_conv1d.cuh"
 #include "bench_conv1d_accel.cuh"
+#include "bench_fft.cuh"
 
 namespace {
 struct Entry {
@@ -19,6 +20,7 @@ const std::vector<Entry>& registry() {
         {"Conv1D", [] { return std::make_unique<Conv1DBenchmark>(IR_LEN > 0 ? IR_LEN : Conv1DBenchmark::DEFAULT_IR_LEN); }},
         {"Conv1D_accel",
          [] { return std::make_unique<Conv1DAccelBenchmark>(IR_LEN > 0 ? IR_LEN : Conv1DAccelBenchmark::DEFAULT_IR_LEN); }},
+        {"FFT1D", [] { return std::make_unique<FFTBenchmark>(); }},  // first step beyond the conv path
     };
     return entries;
 }

@@ -1,7 +1,7 @@
 #pragma once
 // Benchmark registry of the gpubench CLI: name -> factory (reference cuda/main.cu:68-115).
-// Only the two plugins of the convolution path exist in this build; the other 15 names of the
-// reference are out of scope and are reported as unknown.
+// The two plugins of the convolution path plus FFT1D (the first "next" row of SURVEY.md §8f) exist
+// in this build; the other 14 names of the reference are out of scope and are reported as unknown.
 #include <memory>
 #include <string>
 #include <vector>

@@ -37,11 +37,15 @@ def load_library():
         getattr(L, name).argtypes = [C.c_void_p]
     L.gpubench_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.gpubench_validate.argtypes = [C.c_void_p, C.POINTER(Validation), C.c_char_p, C.c_size_t]
-    for name in ("gpubench_host_input", "gpubench_host_ir", "gpubench_host_output", "gpubench_cpu_reference"):
+    for name in ("gpubench_host_input", "gpubench_host_ir", "gpubench_host_output", "gpubench_cpu_reference",
+                 "gpubench_fft_input", "gpubench_fft_output", "gpubench_fft_reference"):
         getattr(L, name).argtypes = [C.c_void_p]
         getattr(L, name).restype = C.POINTER(C.c_float)
     L.gpubench_json_results.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     L.gpubench_statistics.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.gpubench_set_dawsim.argtypes = [C.c_int, C.c_int, C.c_double]
+    L.gpubench_set_dawsim.restype = None
+    L.gpubench_dawsim_probe.argtypes = [C.c_double, C.c_int, C.c_double, C.c_int, C.c_void_p]
     _lib = L
     return L
 
@@ -59,6 +63,16 @@ def statistics(latencies_ms):
     out = np.zeros(8, dtype=np.float32)
     load_library().gpubench_statistics(lat.ctypes.data, lat.size, out.ctypes.data)
     return dict(zip(("mean", "median", "std", "min", "max", "p95", "p99", "count"), out.tolist()))
+
+
+def set_dawsim(enable, sleep_mode=False, jitter_us=0.0):
+    load_library().gpubench_set_dawsim(1 if enable else 0, 1 if sleep_mode else 0, float(jitter_us))
+
+
+def dawsim_probe(period_s, n, sleep_mode=False, jitter_us=0.0):
+    out = np.zeros(n, dtype=np.float64)
+    load_library().gpubench_dawsim_probe(period_s, 1 if sleep_mode else 0, float(jitter_us), n, out.ctypes.data)
+    return out
 
 
 class Plugin:
@@ -126,3 +140,15 @@ class Plugin:
 
     def cpu_reference(self):
         return self._view(self.lib.gpubench_cpu_reference, self._out_shape())
+
+    # FFT1D plugin views
+    def fft_input(self):
+        return self._view(self.lib.gpubench_fft_input, (self.T, 1024))
+
+    def fft_output(self):
+        v = self._view(self.lib.gpubench_fft_output, (self.T, 513, 2))
+        return v[..., 0] + 1j * v[..., 1]
+
+    def fft_reference(self):
+        v = self._view(self.lib.gpubench_fft_reference, (self.T, 513, 2))
+        return v[..., 0] + 1j * v[..., 1]

@@ -148,6 +148,12 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info);
  * Replaces launchKernelTimed / CudaEventTimer (cuda/bench_utils.cuh:320-329). */
 int b200conv_set_profiling(b200conv_engine* e, int on);
 
+/* Batched real-to-complex FFT of `count` rows of n real samples (n a power of two, 32..8192) with the
+ * engine's shared-memory Stockham transform: d_out is float2 [count][n/2+1], un-normalised, the
+ * layout of cufftExecR2C.  Stateless; runs on the current device.  Replaces cufftPlan1d(R2C) +
+ * cufftExecR2C of the reference's FFT1D benchmark (cuda/bench_fft.cu:63,105) — SURVEY.md §8(f) #3. */
+int b200conv_rfft(const float* d_in, void* d_out, int count, int n, void* stream);
+
 /* ---- the one collective of the path: all-reduce of the stereo bus over NVLink peer memory ----
  * No reference counterpart (the reference is single-GPU).  `peer_buffers[p]` is the
  * address, valid on THIS device, of rank p's symmetric buffer of b200conv_bus_buffer_bytes(world, n)

@@ -31,6 +31,11 @@ const char* gpubench_last_error(void);
 /* The CLI globals (cuda/globals.cu:4-9): --fs, --nRuns; stream != 0 is --mode stream. */
 void gpubench_set_globals(int fs, int nruns, int stream_mode);
 
+/* DAW-style pacing of runBenchmark (--dawsim, --dawsim-mode, --dawsim-jitter-us); enable = 0 turns it off. */
+void gpubench_set_dawsim(int enable, int sleep_mode, double jitter_us);
+/* Drive a DAWSimulator alone: call wait() n times, return the wake-up times in seconds since the first call. */
+int gpubench_dawsim_probe(double period_s, int sleep_mode, double jitter_us, int n, double* wake_times_s);
+
 /* createBenchmark(name) (main.cu:105-115) with explicit sizes; name is "Conv1D" or "Conv1D_accel";
  * ir_len <= 0 selects the plugin default (1024 / 512). NULL on unknown name. */
 gpubench_plugin* gpubench_create(const char* name, int ir_len, int buffer_size, int track_count);
@@ -49,6 +54,12 @@ const float* gpubench_host_input(gpubench_plugin* p);
 const float* gpubench_host_ir(gpubench_plugin* p);
 const float* gpubench_host_output(gpubench_plugin* p);
 const float* gpubench_cpu_reference(gpubench_plugin* p);
+
+/* FFT1D plugin views: input float [T][1024]; output / float-DFT reference as interleaved complex
+ * float [T][513][2]; gpubench_validate's snr_db is then the SNR against the plugin's fp64 DFT. */
+const float* gpubench_fft_input(gpubench_plugin* p);
+const float* gpubench_fft_output(gpubench_plugin* p);
+const float* gpubench_fft_reference(gpubench_plugin* p);
 
 /* The reference's result writers (globals.cu:69-182) for a latency vector. */
 int gpubench_json_results(const float* latencies_ms, size_t n, const char* name, int fs, int bufsize, int ntracks,

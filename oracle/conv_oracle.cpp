@@ -158,6 +158,26 @@ void oracle_stream(const float* x, const float* h, float* y, int L, int64_t nsam
 }
 
 // ---------------------------------------------------------------------------------------------
+// FFT1D oracle.  cuda/bench_fft.cu:149-168 (FFTBenchmark::cpuFFTReference):
+// naive O(N^2) DFT, k = 0..N/2, everything in float INCLUDING the angle -2*PI*k*n/size (so the
+// oracle itself loses ~2.4e-4 rad at k*n ~ 5e5: it is a coarse reference, the fp64 DFT in the tests
+// is the truth), `sum += input[n] * cosf/sinf(angle)`.
+// ---------------------------------------------------------------------------------------------
+void oracle_fft_reference(const float* input, float* real_output, float* imag_output, int size) {
+    const float PI = 3.14159265358979323846f;
+    for (int k = 0; k < size / 2 + 1; k++) {
+        float sum_real = 0.0f, sum_imag = 0.0f;
+        for (int n = 0; n < size; n++) {
+            float angle = -2.0f * PI * k * n / size;
+            sum_real += input[n] * cosf(angle);
+            sum_imag += input[n] * sinf(angle);
+        }
+        real_output[k] = sum_real;
+        imag_output[k] = sum_imag;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Validation metrics.
 // Absolute: cuda/bench_base.cu:193-222 (compareWithReference) — float running sum of |diff|,
 // max |diff|, count of elements over tolerance.  Conv1D uses tol 1e-3 (bench_conv1d.cu:108).

@@ -27,6 +27,7 @@
 #define protected public
 #include "bench_conv1d.cuh"        // /root/reference/cuda/bench_conv1d.cuh
 #include "bench_conv1d_accel.cuh"  // /root/reference/cuda/bench_conv1d_accel.cuh
+#include "bench_fft.cuh"           // /root/reference/cuda/bench_fft.cuh
 #undef private
 #undef protected
 
@@ -99,6 +100,12 @@ int ref_generate_ir_accel(float* h, int T, int L) {
     b->h_ir_buf = nullptr;
     b->d_ir_buf = nullptr;
     return rc;
+}
+
+// cuda/bench_fft.cu:149-168
+void ref_fft_reference(const float* input, float* re, float* im, int size) {
+    static FFTBenchmark* inst = new FFTBenchmark(1, 1);
+    inst->cpuFFTReference(input, re, im, size);
 }
 
 // cuda/bench_utils.cu:358-414; out8 = {mean, median, std, min, max, p95, p99, count}

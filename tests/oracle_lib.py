@@ -43,6 +43,7 @@ class Oracle:
         L.oracle_conv1d_r1.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
         L.oracle_conv1d_r2.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
         L.oracle_stream.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int64]
+        L.oracle_fft_reference.argtypes = [_f32p, _f32p, _f32p, C.c_int]
         L.oracle_compare_abs.argtypes = [_f32p, _f32p, C.c_size_t, C.c_float,
                                          C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.oracle_compare_rel.argtypes = [_f32p, _f32p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -89,6 +90,14 @@ class Oracle:
         y = np.empty_like(x)
         self.lib.oracle_stream(x, h, y, h.size, x.size)
         return y
+
+    def fft_reference(self, x):
+        """Naive float DFT of one row (bench_fft.cu:149-168): complex64 [n/2+1]."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        re = np.empty(x.size // 2 + 1, dtype=np.float32)
+        im = np.empty_like(re)
+        self.lib.oracle_fft_reference(x, re, im, x.size)
+        return re + 1j * im
 
     # -- metrics -----------------------------------------------------------------------------
     def compare_abs(self, gpu, cpu, tol):
@@ -146,6 +155,7 @@ class RefLib:
         L.ref_generate_ir_direct.argtypes = [_f32p, C.c_int, C.c_int]
         L.ref_generate_ir_accel.argtypes = [_f32p, C.c_int, C.c_int]
         L.ref_statistics.argtypes = [_f32p, C.c_size_t, _f32p]
+        L.ref_fft_reference.argtypes = [_f32p, _f32p, _f32p, C.c_int]
         L.ref_json_results.argtypes = [_f32p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         for name in ("ref_time_r1", "ref_time_r2"):
             getattr(L, name).argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -171,6 +181,13 @@ class RefLib:
         y = np.empty(T * B, dtype=np.float32)
         self.lib.ref_conv1d_r2(np.ascontiguousarray(x.ravel()), np.ascontiguousarray(h.ravel()), y, L, B, T)
         return y.reshape(B, T)
+
+    def fft_reference(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        re = np.empty(x.size // 2 + 1, dtype=np.float32)
+        im = np.empty_like(re)
+        self.lib.ref_fft_reference(x, re, im, x.size)
+        return re + 1j * im
 
     def statistics(self, lat):
         lat = np.ascontiguousarray(lat, dtype=np.float32)

@@ -29,10 +29,11 @@ def test_plugin_library_exports_every_declared_symbol():
 
 def test_cli_list_help_and_exit_codes():
     r = run_cli("--list")
-    assert r.returncode == 0 and r.stdout.split("\n")[:4] == ["GPGPU Audio Benchmark", "Available benchmarks:", "Conv1D", "Conv1D_accel"]
+    assert r.returncode == 0 and r.stdout.split("\n")[:5] == ["GPGPU Audio Benchmark", "Available benchmarks:", "Conv1D", "Conv1D_accel", "FFT1D"]
     r = run_cli("--help")
     assert r.returncode == 0
-    for flag in ("--benchmark", "--fs", "--bufferSize", "--nTracks", "--nRuns", "--outputfile", "--json", "--irLen"):
+    for flag in ("--benchmark", "--fs", "--bufferSize", "--nTracks", "--nRuns", "--outputfile", "--json", "--irLen",
+                 "--dawsim", "--dawsim-mode", "--dawsim-jitter-us"):
         assert flag in r.stdout
     r = run_cli("--nTracks")  # missing value: reference exits 1 (main.cu:276-279)
     assert r.returncode == 1 and "Error: --nTracks requires an argument" in r.stdout
@@ -58,6 +59,27 @@ def test_statistics_match_reference(golden, oracle):
 def test_unknown_benchmark_is_rejected():
     with pytest.raises(ValueError):
         plugin.Plugin("RndMemRead")
+
+
+@pytest.mark.parametrize("sleep_mode", [False, True])
+def test_dawsim_paces_at_the_buffer_period(sleep_mode):
+    """DAWSimulator (Metal BenchmarkUtilities.swift:151-178): wake-ups land on multiples of the period."""
+    period = 512 / 48000 / 4  # 2.67 ms
+    t = plugin.dawsim_probe(period, 12, sleep_mode=sleep_mode)
+    ideal = period * np.arange(1, 13)
+    late = t - ideal
+    assert np.all(late >= -1e-5), late                     # never early
+    assert np.median(late) <= (1e-3 if sleep_mode else 1e-4), late  # on a shared CI box single wake-ups may be late
+    assert np.all(np.diff(t) <= 3 * period)                # ... but the pace never collapses
+
+
+def test_dawsim_jitter_is_bounded():
+    period, jitter_us = 2e-3, 300.0
+    t = plugin.dawsim_probe(period, 40, jitter_us=jitter_us)
+    dev = t - period * np.arange(1, 41)
+    assert np.all(dev >= -jitter_us * 1e-6 - 1e-5)                    # never earlier than -jitter
+    assert np.percentile(dev, 80) <= jitter_us * 1e-6 + 1e-4, dev     # late only when the OS pre-empts the spinner
+    assert dev.std() > 50e-6  # it does jitter
 
 
 # ---------------------------------------------------------------- GPU ------------------------
@@ -98,12 +120,72 @@ def test_conv1d_accel_plugin_lifecycle(oracle, T, B, L):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("T,B", [(128, 512), (3, 1024), (16, 100)])
+def test_fft1d_plugin_lifecycle(oracle, T, B):
+    """FFT1D on the engine's Stockham R2C: the plugin's float DFT equals the oracle restatement of
+    bench_fft.cu:149-168 bit for bit; the GPU result is judged against an fp64 FFT."""
+    with plugin.Plugin("FFT1D", 0, B, T) as p:
+        p.setup()
+        x = p.fft_input()
+        assert not x[:, min(B, 1024):].any() and x[:, :min(B, 1024)].any()  # zero padding of short buffers
+        ref = p.fft_reference()
+        for t in (0, T - 1):
+            assert np.array_equal(ref[t].astype(np.complex64), oracle.fft_reference(x[t]).astype(np.complex64))
+        wall, gpu = p.run(5, 3)
+        assert (gpu > 0).all()
+        v = p.validate()
+        assert v["status"] == 0 and v["snr_db"] >= 110, v
+        out = p.fft_output()
+    truth = np.fft.rfft(x.astype(np.float64), axis=1)
+    err = np.abs(out - truth).max()
+    assert err <= 2e-5 * np.abs(truth).max(), err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [32, 256, 1024, 8192])
+def test_rfft_abi_matches_fp64_fft(n):
+    """b200conv_rfft for every supported radix mix (log2(n/2) odd and even), cuFFT R2C layout."""
+    import torch
+    import gpuaudiobench_b200 as g
+    count = 37
+    x = torch.rand(count, n, device="cuda") * 2 - 1
+    out = torch.zeros(count, n // 2 + 1, 2, device="cuda")
+    g.rfft(x.data_ptr(), out.data_ptr(), count, n)
+    torch.cuda.synchronize()
+    got = out[..., 0].cpu().numpy() + 1j * out[..., 1].cpu().numpy()
+    truth = np.fft.rfft(x.cpu().numpy().astype(np.float64), axis=1)
+    snr = 10 * np.log10((np.abs(truth) ** 2).sum() / (np.abs(got - truth) ** 2).sum())
+    assert snr >= 110, snr
+    assert np.abs(got - truth).max() <= 3e-5 * np.abs(truth).max()
+    assert not got[:, 0].imag.any() and not got[:, n // 2].imag.any()  # DC and Nyquist are real
+
+
+@pytest.mark.gpu
 def test_stream_mode_validates_after_streaming(oracle):
     with plugin.Plugin("Conv1D", 2048, 512, 8, stream_mode=True) as p:
         p.setup()
         p.run(6, 2)
         assert p.validate()["status"] == 0
     plugin.load_library().gpubench_set_globals(48000, 0, 0)
+
+
+@pytest.mark.gpu
+def test_dawsim_run_is_paced_and_meets_deadline():
+    """128 tracks x 16k taps submitted every 10.67 ms: the loop takes ~n periods, p99 stays under it."""
+    import time
+    plugin.set_dawsim(True, sleep_mode=False, jitter_us=100.0)
+    try:
+        with plugin.Plugin("Conv1D", 16384, 512, 128) as p:
+            p.setup()
+            t0 = time.perf_counter()
+            wall, gpu = p.run(20, 3)
+            elapsed = time.perf_counter() - t0
+            assert p.validate()["status"] == 0
+    finally:
+        plugin.set_dawsim(False)
+    period = 512 / 48000
+    assert 22 * period <= elapsed <= 24.5 * period, elapsed
+    assert np.sort(wall)[-1] < period * 1e3  # every buffer inside its 10.67 ms period
 
 
 @pytest.mark.gpu
