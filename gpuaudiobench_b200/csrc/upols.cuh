@@ -53,6 +53,8 @@ struct FusedParams {
     float2* Ypart;        // [S][T][M]
     unsigned* counters;   // [T], zero between launches
     float* out;           // [T][B] or [B][Tg]
+    float* out2;          // optional second copy of the output, same layout (pinned host memory: the
+                          // last CTA of each track posts its PCIe writes while other CTAs still stream)
     int T, P, M, logM, S, slot0, commit;
     int sample_major, Tg, toff;
 };
