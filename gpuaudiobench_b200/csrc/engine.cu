@@ -80,6 +80,8 @@ struct b200conv_engine {
     bool ir_loaded = false;
     uint64_t blocks = 0, launches = 0, device_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t last_stream = nullptr;  // stream of the latest process(): state (ring, delay line) is ordered on it
+    bool has_last_stream = false;
     float* d_in_stage = nullptr;
     float* d_out_stage = nullptr;
     float* d_mix_stage = nullptr;
@@ -508,6 +510,11 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
     if (!e || !d_in || !d_out) return fail(B200CONV_ERR_INVALID, "b200conv_process: null argument");
     if (!e->ir_loaded) return fail(B200CONV_ERR_STATE, "b200conv_process: call b200conv_load_ir first");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the engine's state lives on whatever stream the previous block ran on: switching streams is
+    // allowed, but the new stream must see the old one's work (cheap: only when the stream changes)
+    if (e->has_last_stream && e->last_stream != st) CU_TRY(cudaStreamSynchronize(e->last_stream));
+    e->last_stream = st;
+    e->has_last_stream = true;
     const bool commit = !(flags & B200CONV_PEEK);
     const int sample_major = (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR);
     StageTimer tm{e, st};

@@ -31,7 +31,30 @@
 #undef private
 #undef protected
 
+#include <fcntl.h>
+#include <unistd.h>
+
 namespace {
+// The reference's Conv1DAccelBenchmark constructor printf()s (bench_conv1d_accel.cu:55); callers such
+// as bench.py must keep stdout to one JSON line, so stdout is parked on /dev/null while it runs.
+struct StdoutMute {
+    int saved = -1;
+    StdoutMute() {
+        std::fflush(stdout);
+        saved = dup(1);
+        const int devnull = open("/dev/null", O_WRONLY);
+        if (saved >= 0 && devnull >= 0) dup2(devnull, 1);
+        if (devnull >= 0) close(devnull);
+    }
+    ~StdoutMute() {
+        std::fflush(stdout);
+        if (saved >= 0) {
+            dup2(saved, 1);
+            close(saved);
+        }
+    }
+};
+
 // Never destroyed: ~BufferSet calls cudaDeviceSynchronize (bench_base.cuh:61-67) which only
 // produces a warning on a box without a GPU.  The objects own nothing.
 Conv1DBenchmark& directInstance() {
@@ -39,7 +62,10 @@ Conv1DBenchmark& directInstance() {
     return *inst;
 }
 Conv1DAccelBenchmark& accelInstance() {
-    static Conv1DAccelBenchmark* inst = new Conv1DAccelBenchmark(1, 1, 1);
+    static Conv1DAccelBenchmark* inst = [] {
+        StdoutMute mute;
+        return new Conv1DAccelBenchmark(1, 1, 1);
+    }();
     return *inst;
 }
 bool haveDevice() {
@@ -86,7 +112,11 @@ int ref_generate_ir_direct(float* h, int T, int L) {
 
 // cuda/bench_conv1d_accel.cu:152-173
 int ref_generate_ir_accel(float* h, int T, int L) {
-    auto* b = new Conv1DAccelBenchmark(L, 1, static_cast<size_t>(T));
+    Conv1DAccelBenchmark* b = nullptr;
+    {
+        StdoutMute mute;
+        b = new Conv1DAccelBenchmark(L, 1, static_cast<size_t>(T));
+    }
     b->h_ir_buf = h;
     void* dev = nullptr;
     if (haveDevice() && cudaMalloc(&dev, b->ir_buffer_bytes) == cudaSuccess) b->d_ir_buf = static_cast<float*>(dev);
