@@ -14,7 +14,8 @@
 // B*8 bytes — a whole number of 128 B lines for every supported B — and the MAC streams long
 // contiguous runs.  The real transforms are done as one complex FFT of size M = B on the
 // even/odd-packed signal (shared-memory Stockham autosort, radix 4 with one radix-2 pass when
-// log2 M is odd) plus a twiddle post-/pre-pass.  Twiddles are computed in double on the host.
+// log2 M is odd) plus a twiddle post-/pre-pass.  Twiddles are computed in-kernel (sincospif, exact
+// arguments) so the FFT phases carry no dependent table loads.
 #include "upols.cuh"
 
 #include "common.cuh"

@@ -165,6 +165,37 @@ def test_upols_partition_splits_agree(oracle, monkeypatch, split):
     assert_parity(got, want, g.ALGO_UPOLS, f"split {split}")
 
 
+def _fuzz_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(n):
+        B = int(rng.choice([32, 64, 128, 256, 512, 1024]))
+        T = int(rng.integers(1, 41))
+        L = int(rng.integers(2, 6000))
+        M = int(rng.integers(2, 7)) if B * L < 2_000_000 else 2
+        cases.append((T, B, L, M, int(rng.integers(0, 2)), int(rng.integers(0, 2))))
+    return cases
+
+
+@pytest.mark.parametrize("T,B,L,M,algo,layout", _fuzz_cases(24, seed=2026))
+def test_fuzz_random_shapes_match_streaming_oracle(oracle, T, B, L, M, algo, layout):
+    """Random track counts, buffer sizes, IR lengths (never a multiple of anything) and stream
+    lengths, both engines, both layouts, with the stereo bus, against the reference loop."""
+    xs = oracle.generate_input(M * T * B, 1000 + T + L).reshape(M, T, B)
+    h = oracle.generate_ir(T, L, "accel")
+    want = np.stack([oracle.stream(xs[:, t, :].ravel(), h[t]) for t in range(T)])
+    theta = (np.arange(T) + 0.5) / T * np.pi / 2
+    gains = np.stack([np.cos(theta), np.sin(theta)], axis=1) / np.sqrt(T)
+    bus = gains.T @ want.astype(np.float64)
+    with g.ConvEngine(T, B, L, algo, layout) as e:
+        e.load_ir(h)
+        outs = run_stream(e, xs, want_mix=True)
+    got = np.concatenate([(y.T if layout == g.OUT_SAMPLE_MAJOR else y) for y, _ in outs], axis=1)
+    got_bus = np.concatenate([m for _, m in outs], axis=1)
+    assert_parity(got, want, algo, f"fuzz T={T} B={B} L={L} M={M} layout={layout}")
+    assert snr_db(got_bus, bus) >= 90
+
+
 # ---------------------------------------------------------------------------------------------
 # Exact indexing: impulses (SURVEY App. E "Exact indexing tests")
 # ---------------------------------------------------------------------------------------------
