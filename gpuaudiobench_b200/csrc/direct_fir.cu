@@ -304,31 +304,33 @@ __global__ void __launch_bounds__(kBusWarps * 32) fir_finish_mix_kernel(FinishPa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n0 = blockIdx.x * 32, n = n0 + lane;
     const int T = p.T, B = p.B;
-    const int ngroups = (T + kMixChunk - 1) / kMixChunk;
+    const int chunk = p.chunk;  // tracks per warp step (<= kMixChunk), chosen so most warps need one step
+    const int ngroups = (T + chunk - 1) / chunk;
     float l = 0.0f, r = 0.0f;
     pdl_launch_dependents();  // e.g. the bus all-reduce kernel of a multi-GPU job
     pdl_wait_primary();       // partial rows come from the FIR kernel launched just before us
     if (n < B) {
         const uint32_t ring_idx = swz_float(static_cast<uint32_t>(p.pos + n));
         for (int gi = blockIdx.y * kBusWarps + warp; gi < ngroups; gi += kBusWarps * gridDim.y) {
-            const int t0 = gi * kMixChunk;
+            const int t0 = gi * chunk;
+            const int tend = min(T, t0 + chunk);
             float v[kMixChunk], xin[kMixChunk];
 #pragma unroll
             for (int j = 0; j < kMixChunk; ++j) v[j] = 0.0f;
             for (int s = 0; s < p.MS; ++s) {
 #pragma unroll
                 for (int j = 0; j < kMixChunk; ++j)
-                    if (t0 + j < T) v[j] += p.partial[(static_cast<size_t>(s) * T + t0 + j) * B + n];
+                    if (t0 + j < tend) v[j] += p.partial[(static_cast<size_t>(s) * T + t0 + j) * B + n];
             }
             if (p.ring) {
 #pragma unroll
                 for (int j = 0; j < kMixChunk; ++j)
-                    if (t0 + j < T) xin[j] = p.d_in[static_cast<size_t>(t0 + j) * B + n];
+                    if (t0 + j < tend) xin[j] = p.d_in[static_cast<size_t>(t0 + j) * B + n];
             }
 #pragma unroll
             for (int j = 0; j < kMixChunk; ++j) {
                 const int t = t0 + j;
-                if (t < T) {
+                if (t < tend) {
                     if (p.sample_major)
                         p.out[static_cast<size_t>(n) * p.Tg + p.toff + t] = v[j];
                     else
@@ -453,11 +455,19 @@ int fir_max_segments(int n_tiles_total, int NS, int G) {
 }
 
 // cluster height: one cluster covers all tracks of a 32-sample column tile
-static int bus_cluster_height(int T) {
-    const int ngroups = (T + kMixChunk - 1) / kMixChunk;
+static int bus_cluster_height(int T, int chunk = kMixChunk) {
+    const int ngroups = (T + chunk - 1) / chunk;
     int cy = 1;
     while (cy < 8 && cy * 2 * kBusWarps <= ngroups) cy *= 2;
     return cy;
+}
+
+// tracks per warp step of the finish kernel: the largest chunk for which the 8 x kBusWarps warps of
+// a full-height cluster still all have work, so each warp issues its loads in a single round
+static int finish_chunk(int T) {
+    int chunk = kMixChunk;
+    while (chunk > 1 && (T + chunk - 1) / chunk < 8 * kBusWarps) chunk /= 2;
+    return chunk;
 }
 
 template <typename... KArgs, typename... Args>
@@ -479,8 +489,10 @@ static cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, int cy,
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-cudaError_t launch_fir_finish_mix(const FinishParams& p, cudaStream_t st) {
-    const int cy = bus_cluster_height(p.T);
+cudaError_t launch_fir_finish_mix(const FinishParams& p0, cudaStream_t st) {
+    FinishParams p = p0;
+    p.chunk = finish_chunk(p.T);
+    const int cy = bus_cluster_height(p.T, p.chunk);
     return launch_clustered(fir_finish_mix_kernel, dim3((p.B + 31) / 32, cy), cy, st, p);
 }
 

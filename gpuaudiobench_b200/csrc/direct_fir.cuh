@@ -50,6 +50,7 @@ struct FinishParams {
     const float* d_in;     // [T][B]
     float* ring;           // [T][cap] or null (PEEK: do not append)
     int cap, pos;
+    int chunk;             // set by the launcher: tracks per warp step (<= kMixChunk)
 };
 cudaError_t launch_fir_finish_mix(const FinishParams& p, cudaStream_t st);
 // Deterministic stereo bus of an output already in memory: mix[c][n] = sum_t gains[t][c] * y_t[n].
