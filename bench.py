@@ -401,6 +401,74 @@ def run_sweep(args, rank, world, local_rank, dist):
     return rows
 
 
+def run_latency(args, rank, world, local_rank, dist):
+    """SURVEY §8(d) latency run: `--latency N` blocks of the chosen workload through the host-buffer
+    path (pinned H2D, kernels, bus all-reduce, D2H, synchronise), after >= P warm-up blocks, submitted
+    (i) back-to-back and (ii) periodically at the buffer period B/fs (spin to the deadline, like the
+    reference's Metal DAWSimulator).  Latency = submission -> results on the host, max over ranks."""
+    import torch
+
+    import gpuaudiobench_b200 as g
+    from gpuaudiobench_b200 import synth
+    from gpuaudiobench_b200.distributed import BusAllReduce
+
+    algo_name, T, B, L, layout_name, label = WORKLOADS[args.workload]
+    algo = g.ALGO_DIRECT if algo_name == "direct" else g.ALGO_UPOLS
+    Tg, t0 = T * world, T * rank
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream(dev)
+    eng = g.ConvEngine(T, B, L, algo, g.OUT_TRACK_MAJOR, device=local_rank, track_offset=t0, total_tracks=Tg)
+    eng.load_ir(synth.make_ir(Tg, L, t0, t0 + T))
+    NB = 8
+    h_in = torch.from_numpy(synth.make_input(NB * T * B, seed=42 + rank).reshape(NB, T, B)).pin_memory()
+    h_out = torch.zeros(T, B).pin_memory()
+    h_mix = torch.zeros(2, B).pin_memory()
+    d_in, d_y, d_mix = torch.zeros(T, B, device=dev), torch.zeros(T, B, device=dev), torch.zeros(2, B, device=dev)
+    bus = BusAllReduce(d_mix, force_nccl=bool(os.environ.get("B200CONV_BUS_NCCL")))
+
+    def block(k):
+        if world == 1:
+            eng.process_host_ptr(h_in[k % NB].data_ptr(), h_out.data_ptr(), h_mix.data_ptr())
+        else:
+            d_in.copy_(h_in[k % NB], non_blocking=True)
+            eng.process(d_in.data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
+            bus(stream.cuda_stream)
+            h_out.copy_(d_y, non_blocking=True)
+            h_mix.copy_(d_mix, non_blocking=True)
+            stream.synchronize()
+
+    N = args.latency
+    period = B / FS
+    out = {}
+    for mode in ("back_to_back", "periodic"):
+        for k in range(min((L + B - 1) // B + 2, 400)):
+            block(k)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        lat = np.empty(N)
+        t_next = time.perf_counter() + period
+        for k in range(N):
+            if mode == "periodic":
+                while time.perf_counter() < t_next:
+                    pass
+                t_next += period
+            a = time.perf_counter()
+            block(k)
+            lat[k] = (time.perf_counter() - a) * 1e3
+        if world > 1:
+            lt = torch.from_numpy(lat).to(dev)
+            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+            lat = lt.cpu().numpy()
+        s = np.sort(lat)
+        out[mode] = {"blocks": N, "p50_ms": pct(s, 0.50), "p95_ms": pct(s, 0.95), "p99_ms": pct(s, 0.99), "max_ms": float(s[-1]),
+                     "mean_ms": float(lat.mean()), "deadline_ms": period * 1e3, "meets_deadline": bool(pct(s, 0.99) <= period * 1e3),
+                     "missed_blocks": int((lat > period * 1e3).sum())}
+    bus.check()
+    return {"latency_run": out, "workload": f"{args.workload}: {label}", "n_gpus": world, "total_tracks": Tg, "block": B,
+            "ir_taps": L, "fs": FS, "path": "host buffers -> results on host (e2e)", "collective": bus.kind}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,6 +478,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads in the default line")
     ap.add_argument("--sweep", action="store_true", help="buffer-size sweep (BASELINE config 5): one JSON line with a table")
+    ap.add_argument("--latency", type=int, default=0, metavar="N", help="latency run: N blocks back-to-back and N periodic at B/fs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -431,6 +500,14 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.latency > 0:
+        res = run_latency(args, rank, world, local_rank, dist)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     if args.sweep:
         rows = run_sweep(args, rank, world, local_rank, dist)
         if rank == 0:
