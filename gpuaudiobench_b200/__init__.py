@@ -8,7 +8,7 @@ Layout (only what the hot path needs):
   engine.py / plugin.py   ctypes bindings used by the tests and bench.py (harness, not product)
 """
 from .engine import (ALGO_DIRECT, ALGO_UPOLS, OUT_SAMPLE_MAJOR, OUT_TRACK_MAJOR, PEEK, B200ConvError,  # noqa: F401
-                     ConvEngine, load_library, measure_fp32_peak, plan, rfft)
+                     ConvEngine, ConvGroup, load_library, measure_fp32_peak, plan, rfft)
 
-__all__ = ["ConvEngine", "B200ConvError", "load_library", "plan", "measure_fp32_peak", "ALGO_DIRECT", "ALGO_UPOLS",
+__all__ = ["ConvEngine", "ConvGroup", "B200ConvError", "load_library", "plan", "measure_fp32_peak", "ALGO_DIRECT", "ALGO_UPOLS",
            "OUT_TRACK_MAJOR", "OUT_SAMPLE_MAJOR", "PEEK"]

@@ -1,0 +1,273 @@
+// group.cu — multi-GPU convolution in ONE process: the b200conv_group_* entry points.
+//
+// Tracks are independent, so a group is simply one engine per GPU owning a contiguous track range
+// (IRs, bus gains and sample-major columns use the global track index — SURVEY.md §8e), one
+// persistent host thread per device that submits that device's work (so 8 GPUs are fed in
+// parallel, not 8 x launch latency in series), and ONE collective per block: the stereo bus
+// all-reduce, done by the engine's own P2P kernel (bus_allreduce.cu) over peer-mapped buffers
+// (cudaDeviceEnablePeerAccess; every device stores into every other device's slot over NVLink).
+// The one-process-per-GPU variant of the same thing is bench.py + gpuaudiobench_b200/distributed.py.
+#include "../../include/b200conv.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_group_error;
+
+int gfail(int code, const std::string& msg) {
+    g_group_error = msg;
+    return code;
+}
+
+struct Job {
+    const float* h_in = nullptr;
+    float* h_out = nullptr;
+    float* h_mix = nullptr;
+    uint32_t flags = 0;
+};
+
+struct Member {
+    int device = 0;
+    int t0 = 0, t1 = 0;  // global track range
+    b200conv_engine* engine = nullptr;
+    cudaStream_t stream = nullptr;
+    float* d_in = nullptr;
+    float* d_out = nullptr;
+    float* d_mix = nullptr;
+    float* bus_buf = nullptr;       // symmetric slot buffer of this device
+    uint32_t* d_err = nullptr;
+    int rc = 0;
+    std::string err;
+    std::thread worker;
+};
+
+}  // namespace
+
+struct b200conv_group {
+    b200conv_config cfg{};  // tracks = total tracks
+    int n = 0;
+    std::vector<Member> members;
+    std::vector<uint64_t> peer_ptrs;
+    uint32_t epoch = 0;
+    // worker coordination
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+    Job job;
+};
+
+namespace {
+
+int member_submit(b200conv_group* g, Member& m, const Job& job, uint32_t epoch) {
+    const int T = m.t1 - m.t0, B = static_cast<int>(g->cfg.block), Tg = static_cast<int>(g->cfg.tracks);
+    const size_t tb = static_cast<size_t>(T) * B;
+    const bool sample_major = g->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR;
+    if (cudaSetDevice(m.device) != cudaSuccess) return B200CONV_ERR_CUDA;
+    if (cudaMemcpyAsync(m.d_in, job.h_in + static_cast<size_t>(m.t0) * B, tb * sizeof(float), cudaMemcpyHostToDevice, m.stream) != cudaSuccess)
+        return B200CONV_ERR_CUDA;
+    int rc = b200conv_process(m.engine, m.d_in, m.d_out, job.h_mix ? m.d_mix : nullptr, job.flags, m.stream);
+    if (rc) return rc;
+    if (job.h_mix) {
+        rc = b200conv_bus_allreduce(m.d_mix, m.d_mix, g->peer_ptrs.data(), static_cast<int>(&m - g->members.data()), g->n, 2 * B,
+                                    epoch, m.d_err, m.stream);
+        if (rc) return rc;
+    }
+    if (job.h_out) {
+        cudaError_t e;
+        if (sample_major)  // this member's column tile of the [B][Tg] matrix
+            e = cudaMemcpy2DAsync(job.h_out + m.t0, static_cast<size_t>(Tg) * sizeof(float), m.d_out + m.t0,
+                                  static_cast<size_t>(Tg) * sizeof(float), static_cast<size_t>(T) * sizeof(float), B,
+                                  cudaMemcpyDeviceToHost, m.stream);
+        else
+            e = cudaMemcpyAsync(job.h_out + static_cast<size_t>(m.t0) * B, m.d_out, tb * sizeof(float), cudaMemcpyDeviceToHost, m.stream);
+        if (e != cudaSuccess) return B200CONV_ERR_CUDA;
+    }
+    if (job.h_mix && m.t0 == 0)  // every rank holds the identical bus; member 0 returns it
+        if (cudaMemcpyAsync(job.h_mix, m.d_mix, static_cast<size_t>(2) * B * sizeof(float), cudaMemcpyDeviceToHost, m.stream) != cudaSuccess)
+            return B200CONV_ERR_CUDA;
+    if (cudaStreamSynchronize(m.stream) != cudaSuccess) return B200CONV_ERR_CUDA;
+    return B200CONV_OK;
+}
+
+void worker_loop(b200conv_group* g, int idx) {
+    uint64_t seen = 0;
+    for (;;) {
+        Job job;
+        uint32_t epoch;
+        {
+            std::unique_lock<std::mutex> lk(g->mu);
+            g->cv_go.wait(lk, [&] { return g->stop || g->generation != seen; });
+            if (g->stop) return;
+            seen = g->generation;
+            job = g->job;
+            epoch = g->epoch;
+        }
+        Member& m = g->members[idx];
+        m.rc = member_submit(g, m, job, epoch);
+        if (m.rc) m.err = b200conv_last_error();
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            if (--g->pending == 0) g->cv_done.notify_all();
+        }
+    }
+}
+
+template <typename F> int for_each_member(b200conv_group* g, F&& fn) {
+    for (Member& m : g->members) {
+        if (cudaSetDevice(m.device) != cudaSuccess) return gfail(B200CONV_ERR_CUDA, "cudaSetDevice failed");
+        const int rc = fn(m);
+        if (rc) return gfail(rc, b200conv_last_error());
+    }
+    return B200CONV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200conv_group_last_error(void) { return g_group_error.c_str(); }
+
+int b200conv_group_create(const b200conv_config* cfg, int n_gpus, b200conv_group** out) {
+    if (!cfg || !out || n_gpus < 1) return gfail(B200CONV_ERR_INVALID, "b200conv_group_create: bad argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < n_gpus)
+        return gfail(B200CONV_ERR_NO_DEVICE, "b200conv_group_create: " + std::to_string(n_gpus) + " GPUs requested, " +
+                                                 std::to_string(ndev) + " visible (no CPU fallback)");
+    if (cfg->tracks < static_cast<uint32_t>(n_gpus)) return gfail(B200CONV_ERR_INVALID, "b200conv_group_create: fewer tracks than GPUs");
+    auto* g = new b200conv_group();
+    g->cfg = *cfg;
+    g->n = n_gpus;
+    g->members.resize(n_gpus);
+    const int Tg = static_cast<int>(cfg->tracks), B = static_cast<int>(cfg->block);
+    auto bail = [&](int code, const std::string& msg) {
+        const std::string keep = msg;
+        b200conv_group_destroy(g);
+        return gfail(code, keep);
+    };
+    for (int i = 0; i < n_gpus; ++i) {
+        Member& m = g->members[i];
+        m.device = i;
+        m.t0 = static_cast<int>(static_cast<long long>(Tg) * i / n_gpus);
+        m.t1 = static_cast<int>(static_cast<long long>(Tg) * (i + 1) / n_gpus);
+        b200conv_config c = *cfg;
+        c.device = i;
+        c.tracks = static_cast<uint32_t>(m.t1 - m.t0);
+        c.track_offset = static_cast<uint32_t>(m.t0);
+        c.total_tracks = static_cast<uint32_t>(Tg);
+        if (int rc = b200conv_create(&c, &m.engine)) return bail(rc, b200conv_last_error());
+        cudaSetDevice(i);
+        const size_t out_elems = (cfg->out_layout == B200CONV_OUT_SAMPLE_MAJOR) ? static_cast<size_t>(B) * Tg
+                                                                               : static_cast<size_t>(m.t1 - m.t0) * B;
+        const size_t bus_bytes = b200conv_bus_buffer_bytes(n_gpus, 2 * B);
+        if (cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&m.d_in, static_cast<size_t>(m.t1 - m.t0) * B * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&m.d_out, out_elems * sizeof(float)) != cudaSuccess || cudaMalloc(&m.d_mix, 2 * B * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&m.bus_buf, bus_bytes) != cudaSuccess || cudaMalloc(&m.d_err, sizeof(uint32_t)) != cudaSuccess)
+            return bail(B200CONV_ERR_CUDA, "b200conv_group_create: device allocation failed");
+        cudaMemset(m.bus_buf, 0, bus_bytes);
+        cudaMemset(m.d_err, 0, sizeof(uint32_t));
+        cudaMemset(m.d_out, 0, out_elems * sizeof(float));
+        cudaDeviceSynchronize();
+        g->peer_ptrs.push_back(reinterpret_cast<uint64_t>(m.bus_buf));
+    }
+    for (int i = 0; i < n_gpus; ++i) {  // every device may store into every other device's bus buffer
+        cudaSetDevice(i);
+        for (int j = 0; j < n_gpus; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, i, j);
+            if (!can) return bail(B200CONV_ERR_NO_DEVICE, "b200conv_group_create: no peer access between GPU " + std::to_string(i) +
+                                                              " and " + std::to_string(j));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(B200CONV_ERR_CUDA, "cudaDeviceEnablePeerAccess failed");
+            cudaGetLastError();
+        }
+    }
+    for (int i = 0; i < n_gpus; ++i) g->members[i].worker = std::thread(worker_loop, g, i);
+    *out = g;
+    return B200CONV_OK;
+}
+
+void b200conv_group_destroy(b200conv_group* g) {
+    if (!g) return;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->stop = true;
+    }
+    g->cv_go.notify_all();
+    for (Member& m : g->members) {
+        if (m.worker.joinable()) m.worker.join();
+        cudaSetDevice(m.device);
+        cudaDeviceSynchronize();
+        b200conv_destroy(m.engine);
+        if (m.stream) cudaStreamDestroy(m.stream);
+        cudaFree(m.d_in);
+        cudaFree(m.d_out);
+        cudaFree(m.d_mix);
+        cudaFree(m.bus_buf);
+        cudaFree(m.d_err);
+    }
+    delete g;
+}
+
+int b200conv_group_size(const b200conv_group* g) { return g ? g->n : 0; }
+
+int b200conv_group_load_ir(b200conv_group* g, const float* host_ir) {
+    if (!g || !host_ir) return gfail(B200CONV_ERR_INVALID, "b200conv_group_load_ir: null argument");
+    const size_t L = g->cfg.ir_len;
+    return for_each_member(g, [&](Member& m) { return b200conv_load_ir(m.engine, host_ir + static_cast<size_t>(m.t0) * L); });
+}
+
+int b200conv_group_prime_history(b200conv_group* g, const float* host_hist) {
+    if (!g) return gfail(B200CONV_ERR_INVALID, "b200conv_group_prime_history: null group");
+    const size_t H = g->cfg.ir_len - 1;
+    return for_each_member(g, [&](Member& m) {
+        return b200conv_prime_history(m.engine, host_hist ? host_hist + static_cast<size_t>(m.t0) * H : nullptr);
+    });
+}
+
+int b200conv_group_reset(b200conv_group* g) {
+    if (!g) return gfail(B200CONV_ERR_INVALID, "b200conv_group_reset: null group");
+    return for_each_member(g, [&](Member& m) { return b200conv_reset(m.engine); });
+}
+
+int b200conv_group_process_host(b200conv_group* g, const float* h_in, float* h_out, float* h_mix, uint32_t flags) {
+    if (!g || !h_in) return gfail(B200CONV_ERR_INVALID, "b200conv_group_process_host: null argument");
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->job = Job{h_in, h_out, h_mix, flags};
+        if (h_mix) g->epoch += 1;
+        g->pending = g->n;
+        g->generation += 1;
+    }
+    g->cv_go.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(g->mu);
+        g->cv_done.wait(lk, [&] { return g->pending == 0; });
+    }
+    for (Member& m : g->members)
+        if (m.rc) return gfail(m.rc, "GPU " + std::to_string(m.device) + ": " + m.err);
+    if (h_mix) {
+        for (Member& m : g->members) {
+            uint32_t err = 0;
+            cudaSetDevice(m.device);
+            cudaMemcpy(&err, m.d_err, sizeof(err), cudaMemcpyDeviceToHost);
+            if (err) return gfail(B200CONV_ERR_CUDA, "bus all-reduce: a peer did not signal within the spin bound");
+        }
+    }
+    return B200CONV_OK;
+}
+
+}  // extern "C"

@@ -72,6 +72,15 @@ def load_library():
     L.b200conv_bus_buffer_bytes.restype = C.c_size_t
     L.b200conv_bus_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
                                          C.c_uint32, C.c_void_p, C.c_void_p]
+    L.b200conv_group_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]
+    L.b200conv_group_destroy.argtypes = [C.c_void_p]
+    L.b200conv_group_destroy.restype = None
+    L.b200conv_group_size.argtypes = [C.c_void_p]
+    L.b200conv_group_load_ir.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200conv_group_prime_history.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200conv_group_reset.argtypes = [C.c_void_p]
+    L.b200conv_group_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.b200conv_group_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -110,6 +119,56 @@ def rfft(d_in, d_out, count, n, stream=0):
 
 def _host_ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class ConvGroup:
+    """b200conv_group_*: one engine per GPU in this process; host buffers in, host buffers out."""
+
+    def __init__(self, total_tracks, block, ir_len, algo, n_gpus, out_layout=OUT_TRACK_MAJOR):
+        self.lib = load_library()
+        self.Tg, self.B, self.L, self.out_layout = total_tracks, block, ir_len, out_layout
+        cfg = make_config(total_tracks, block, ir_len, algo, out_layout)
+        self.handle = C.c_void_p()
+        self._check(self.lib.b200conv_group_create(C.byref(cfg), n_gpus, C.byref(self.handle)))
+
+    def _check(self, rc):
+        if rc != OK:
+            raise B200ConvError(rc, self.lib.b200conv_group_last_error().decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.b200conv_group_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def load_ir(self, host_ir):
+        h = np.ascontiguousarray(host_ir, dtype=np.float32)
+        assert h.size == self.Tg * self.L
+        self._check(self.lib.b200conv_group_load_ir(self.handle, _host_ptr(h)))
+
+    def reset(self):
+        self._check(self.lib.b200conv_group_reset(self.handle))
+
+    def prime_history(self, hist=None):
+        if hist is None:
+            self._check(self.lib.b200conv_group_prime_history(self.handle, None))
+        else:
+            h = np.ascontiguousarray(hist, dtype=np.float32)
+            self._check(self.lib.b200conv_group_prime_history(self.handle, _host_ptr(h)))
+
+    def process_host(self, x, flags=0, want_mix=True):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        shape = (self.B, self.Tg) if self.out_layout == OUT_SAMPLE_MAJOR else (self.Tg, self.B)
+        y = np.zeros(shape, dtype=np.float32)
+        mix = np.zeros((2, self.B), dtype=np.float32) if want_mix else None
+        self._check(self.lib.b200conv_group_process_host(self.handle, _host_ptr(x), _host_ptr(y),
+                                                         _host_ptr(mix) if want_mix else None, flags))
+        return y, mix
 
 
 class ConvEngine:

@@ -29,11 +29,15 @@ void Conv1DBenchmark::generateImpulseResponses() {
 void Conv1DBenchmark::primeReferenceHistory() {
     const size_t T = getTrackCount(), B = getBufferSize();
     const size_t H = static_cast<size_t>(ir_length_) - 1;
+    auto prime = [&](const float* h) {
+        if (group_.valid()) group_.primeHistory(h); else engine_.primeHistory(h);
+    };
     if (H == 0) {
-        engine_.primeHistory(nullptr);
+        prime(nullptr);
         return;
     }
-    std::vector<float> hist(T * H, 0.0f);
+    std::vector<float>& hist = history_;
+    hist.assign(T * H, 0.0f);
     const float* x = getHostInput();
     for (size_t t = 0; t < T; ++t) {
         const long long first = static_cast<long long>(t * B) - static_cast<long long>(H);  // flat index of hist[t][0]
@@ -42,7 +46,7 @@ void Conv1DBenchmark::primeReferenceHistory() {
             if (idx >= 0) hist[t * H + i] = x[idx];
         }
     }
-    engine_.primeHistory(hist.data());
+    prime(hist.data());
 }
 
 void Conv1DBenchmark::calculateCPUReference() {
@@ -54,18 +58,27 @@ void Conv1DBenchmark::setupBenchmark() {
     allocateBuffers(getTotalElements());
     allocateConvBuffers();
     generateImpulseResponses();
-    engine_.create(B200CONV_ALGO_DIRECT, B200CONV_OUT_TRACK_MAJOR, getTrackCount(), getBufferSize(), ir_length_);
-    engine_.loadIR(h_ir_buf);
+    if (NGPUS > 1) {
+        group_.create(B200CONV_ALGO_DIRECT, B200CONV_OUT_TRACK_MAJOR, getTrackCount(), getBufferSize(), ir_length_, NGPUS);
+        group_.loadIR(h_ir_buf);
+    } else {
+        engine_.create(B200CONV_ALGO_DIRECT, B200CONV_OUT_TRACK_MAJOR, getTrackCount(), getBufferSize(), ir_length_);
+        engine_.loadIR(h_ir_buf);
+    }
     generateTestData(42);
     primeReferenceHistory();
     calculateCPUReference();
     ready_ = true;
-    std::printf("Conv1D benchmark setup complete (IR length = %d, B200 direct-form engine, %s mode)\n", ir_length_,
-                STREAM_MODE ? "streaming" : "stateless");
+    std::printf("Conv1D benchmark setup complete (IR length = %d, B200 direct-form engine, %d GPU%s, %s mode)\n", ir_length_,
+                NGPUS, NGPUS > 1 ? "s" : "", STREAM_MODE ? "streaming" : "stateless");
 }
 
 void Conv1DBenchmark::oneIteration(const char* caller) {
     if (!ready_) throw std::runtime_error(std::string("Conv1DBenchmark::") + caller + " called before setupBenchmark");
+    if (group_.valid()) {  // tracks sharded over NGPUS devices: host buffers in, host buffers out
+        group_.processHost(getHostInput(), getHostOutput(), nullptr, /*advance_state=*/STREAM_MODE);
+        return;
+    }
     transferToDevice();
     BenchmarkUtils::CudaEventTimer gpu;
     gpu.start();
@@ -82,10 +95,14 @@ void Conv1DBenchmark::validate(ValidationData& validation_data) {
     using namespace BenchmarkConstants;
     if (STREAM_MODE) {  // the timed loop advanced the stream: recreate the state the CPU reference describes
         primeReferenceHistory();
-        transferToDevice();
-        engine_.process(getDeviceInput(), getDeviceOutput(), nullptr, false, nullptr);
-        synchronizeAndCheck();
-        transferToHost();
+        if (group_.valid()) {
+            group_.processHost(getHostInput(), getHostOutput(), nullptr, false);
+        } else {
+            transferToDevice();
+            engine_.process(getDeviceInput(), getDeviceOutput(), nullptr, false, nullptr);
+            synchronizeAndCheck();
+            transferToHost();
+        }
     }
     validation_data = compareWithReference(cpu_reference, CONV1D_REFERENCE_ABS_TOL);  // the reference's check
     const ConvCommon::Accuracy acc = ConvCommon::measureAccuracy(getHostOutput(), cpu_reference, getTotalElements());

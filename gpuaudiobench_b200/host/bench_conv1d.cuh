@@ -5,6 +5,7 @@
 // The texture-memory kernel and its cudaArray (bench_conv1d.cu:7-27,123-157) are replaced by the
 // engine; the CPU reference and the abs-1e-3 check are kept, with the stated SNR tolerance added.
 #include <memory>
+#include <vector>
 
 #include "bench_base.cuh"
 #include "conv_common.cuh"
@@ -37,5 +38,7 @@ private:
     float* h_ir_buf = nullptr;       // pinned, [T][L]
     float* cpu_reference = nullptr;  // pinned, [T][B]
     ConvCommon::Engine engine_;
+    ConvCommon::Group group_;  // used instead of engine_ when NGPUS > 1
+    std::vector<float> history_;  // R1-compatible priming history [T][L-1]
     bool ready_ = false;
 };

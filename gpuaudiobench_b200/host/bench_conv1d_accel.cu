@@ -35,8 +35,14 @@ void Conv1DAccelBenchmark::setupBenchmark() {
     h_ir_buf = BenchmarkUtils::allocateHostBuffer<float>(getTrackCount() * ir_length_, "conv1d_accel host IR buffer");
     cpu_reference = BenchmarkUtils::allocateHostBuffer<float>(getTotalElements(), "conv1d_accel cpu reference");
     generateImpulseResponses();
-    engine_.create(B200CONV_ALGO_UPOLS, B200CONV_OUT_SAMPLE_MAJOR, getTrackCount(), getBufferSize(), ir_length_);
-    engine_.loadIR(h_ir_buf);  // partition spectra: what precomputeImpulseResponseFFTs did with cuFFT
+    // partition spectra: what precomputeImpulseResponseFFTs did with cuFFT
+    if (NGPUS > 1) {
+        group_.create(B200CONV_ALGO_UPOLS, B200CONV_OUT_SAMPLE_MAJOR, getTrackCount(), getBufferSize(), ir_length_, NGPUS);
+        group_.loadIR(h_ir_buf);
+    } else {
+        engine_.create(B200CONV_ALGO_UPOLS, B200CONV_OUT_SAMPLE_MAJOR, getTrackCount(), getBufferSize(), ir_length_);
+        engine_.loadIR(h_ir_buf);
+    }
     calculateCPUReference();
     ready_ = true;
     std::printf("Conv1D accelerated benchmark setup complete.\n");
@@ -46,6 +52,10 @@ void Conv1DAccelBenchmark::runKernel() { performBenchmarkIteration(); }
 
 void Conv1DAccelBenchmark::performBenchmarkIteration() {
     if (!ready_) throw std::runtime_error("Conv1DAccelBenchmark::performBenchmarkIteration called before setupBenchmark");
+    if (group_.valid()) {
+        group_.processHost(getHostInput(), getHostOutput(), nullptr, /*advance_state=*/STREAM_MODE);
+        return;
+    }
     transferToDevice();
     BenchmarkUtils::CudaEventTimer gpu;
     gpu.start();
@@ -58,11 +68,16 @@ void Conv1DAccelBenchmark::performBenchmarkIteration() {
 void Conv1DAccelBenchmark::validate(ValidationData& validation_data) {
     using namespace BenchmarkConstants;
     if (STREAM_MODE) {
-        engine_.reset();
-        transferToDevice();
-        engine_.process(getDeviceInput(), getDeviceOutput(), nullptr, false, nullptr);
-        synchronizeAndCheck();
-        transferToHost();
+        if (group_.valid()) {
+            group_.reset();
+            group_.processHost(getHostInput(), getHostOutput(), nullptr, false);
+        } else {
+            engine_.reset();
+            transferToDevice();
+            engine_.process(getDeviceInput(), getDeviceOutput(), nullptr, false, nullptr);
+            synchronizeAndCheck();
+            transferToHost();
+        }
     }
     // the reference's metric (bench_conv1d_accel.cu:312-336): |g-c|/|c|, absolute where c == 0
     const size_t n = getTotalElements();

@@ -36,5 +36,6 @@ private:
     float* h_ir_buf = nullptr;
     float* cpu_reference = nullptr;
     ConvCommon::Engine engine_;
+    ConvCommon::Group group_;  // used instead of engine_ when NGPUS > 1
     bool ready_ = false;
 };

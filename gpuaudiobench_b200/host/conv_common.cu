@@ -49,6 +49,33 @@ b200conv_info Engine::info() {
     return i;
 }
 
+void Group::check(int rc, const char* what) {
+    if (rc != B200CONV_OK)
+        throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + b200conv_group_last_error());
+}
+
+Group::~Group() { b200conv_group_destroy(handle_); }
+
+void Group::create(b200conv_algo algo, b200conv_layout layout, size_t total_tracks, size_t block, int ir_len, int n_gpus) {
+    b200conv_group_destroy(handle_);
+    handle_ = nullptr;
+    b200conv_config cfg{};
+    cfg.abi_version = B200CONV_ABI_VERSION;
+    cfg.tracks = static_cast<uint32_t>(total_tracks);
+    cfg.block = static_cast<uint32_t>(block);
+    cfg.ir_len = static_cast<uint32_t>(ir_len);
+    cfg.algo = algo;
+    cfg.out_layout = layout;
+    check(b200conv_group_create(&cfg, n_gpus, &handle_), "b200conv_group_create");
+}
+
+void Group::loadIR(const float* host_ir) { check(b200conv_group_load_ir(handle_, host_ir), "b200conv_group_load_ir"); }
+void Group::primeHistory(const float* host_hist) { check(b200conv_group_prime_history(handle_, host_hist), "b200conv_group_prime_history"); }
+void Group::reset() { check(b200conv_group_reset(handle_), "b200conv_group_reset"); }
+void Group::processHost(const float* h_in, float* h_out, float* h_mix, bool advance_state) {
+    check(b200conv_group_process_host(handle_, h_in, h_out, h_mix, advance_state ? 0u : B200CONV_PEEK), "b200conv_group_process_host");
+}
+
 void generateImpulseResponses(float* h, size_t track_count, int ir_len, IRVariant variant) {
     using namespace BenchmarkConstants;
     const float PI = 3.14159265358979323846f;

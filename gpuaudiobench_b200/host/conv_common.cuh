@@ -30,6 +30,25 @@ private:
     static void check(int rc, const char* what);
 };
 
+// The same over b200conv_group_*: one engine per GPU in this process, host buffers in and out.
+class Group {
+public:
+    Group() = default;
+    ~Group();
+    Group(const Group&) = delete;
+    Group& operator=(const Group&) = delete;
+    void create(b200conv_algo algo, b200conv_layout layout, size_t total_tracks, size_t block, int ir_len, int n_gpus);
+    void loadIR(const float* host_ir);
+    void primeHistory(const float* host_hist);
+    void reset();
+    void processHost(const float* h_in, float* h_out, float* h_mix, bool advance_state);
+    bool valid() const { return handle_ != nullptr; }
+
+private:
+    b200conv_group* handle_ = nullptr;
+    static void check(int rc, const char* what);
+};
+
 enum class IRVariant { DIRECT_FLOAT_PI, ACCEL_DOUBLE_PI };
 
 // Hamming-windowed sinc, cutoff BASE + RANGE * t / T, centre L/2, scaled 1/L.

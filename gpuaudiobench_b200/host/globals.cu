@@ -14,6 +14,7 @@ std::string OUTPUT_FILE;
 bool JSON_OUTPUT = false;
 int IR_LEN = 0;
 int WARMUP_RUNS = 3;
+int NGPUS = 1;
 bool STREAM_MODE = false;
 bool DAWSIM = false;
 bool DAWSIM_SLEEP = false;

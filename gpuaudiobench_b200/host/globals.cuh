@@ -14,6 +14,7 @@ extern bool JSON_OUTPUT;         // --json
 // Additions of this build (the reference has no CLI knob for them):
 extern int IR_LEN;               // --irLen   (0 = the plugin's default: 1024 direct, 512 accel)
 extern int WARMUP_RUNS;          // --warmup  (3, the value main.cu:130 hard-codes)
+extern int NGPUS;                // --nGpus: shard the tracks over this many GPUs (b200conv_group_*; default 1)
 extern bool STREAM_MODE;         // --mode stream: advance the convolution state every iteration
 // DAW-style periodic submission.  The reference's CUDA port only has unused compile-time stubs
 // (cuda/globals.cuh:28-30 ENABLE_DAWSIM_SLEEP / SLEEP_MS / ENABLE_DAWSIM_SPIN); the behaviour follows

@@ -37,6 +37,7 @@ static void printHelp() {
     std::printf("  --json              Output results in JSON format\n");
     std::printf("  --irLen [taps]      Impulse response length (default: 1024 Conv1D, 512 Conv1D_accel)\n");
     std::printf("  --warmup [count]    Warm-up iterations before timing (default: 3)\n");
+    std::printf("  --nGpus [count]     Shard the tracks over this many GPUs of the box (default: 1)\n");
     std::printf("  --mode [stateless|stream]  stateless re-submits one buffer (reference behaviour, default);\n");
     std::printf("                      stream advances the convolution state every iteration\n");
     std::printf("  --dawsim            Pace iterations at the buffer period bufferSize/fs (DAW-style submission)\n");
@@ -71,6 +72,7 @@ int main(int argc, char** argv) {
         {"--nRuns", "--nruns", &NRUNS, nullptr},
         {"--irLen", "--irlen", &IR_LEN, "IR length set to: %d\n"},
         {"--warmup", nullptr, &WARMUP_RUNS, nullptr},
+        {"--nGpus", "--ngpus", &NGPUS, "Number of GPUs set to: %d\n"},
     };
 
     for (int i = 1; i < argc; ++i) {

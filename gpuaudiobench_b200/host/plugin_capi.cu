@@ -44,6 +44,8 @@ void gpubench_set_globals(int fs, int nruns, int stream_mode) {
     STREAM_MODE = (stream_mode != 0);
 }
 
+void gpubench_set_ngpus(int n) { NGPUS = n > 0 ? n : 1; }
+
 void gpubench_set_dawsim(int enable, int sleep_mode, double jitter_us) {
     DAWSIM = (enable != 0);
     DAWSIM_SLEEP = (sleep_mode != 0);

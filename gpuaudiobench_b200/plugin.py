@@ -43,6 +43,8 @@ def load_library():
         getattr(L, name).restype = C.POINTER(C.c_float)
     L.gpubench_json_results.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     L.gpubench_statistics.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.gpubench_set_ngpus.argtypes = [C.c_int]
+    L.gpubench_set_ngpus.restype = None
     L.gpubench_set_dawsim.argtypes = [C.c_int, C.c_int, C.c_double]
     L.gpubench_set_dawsim.restype = None
     L.gpubench_dawsim_probe.argtypes = [C.c_double, C.c_int, C.c_double, C.c_int, C.c_void_p]
@@ -63,6 +65,10 @@ def statistics(latencies_ms):
     out = np.zeros(8, dtype=np.float32)
     load_library().gpubench_statistics(lat.ctypes.data, lat.size, out.ctypes.data)
     return dict(zip(("mean", "median", "std", "min", "max", "p95", "p99", "count"), out.tolist()))
+
+
+def set_ngpus(n):
+    load_library().gpubench_set_ngpus(int(n))
 
 
 def set_dawsim(enable, sleep_mode=False, jitter_us=0.0):

@@ -165,6 +165,22 @@ size_t b200conv_bus_buffer_bytes(int world, int n);
 int b200conv_bus_allreduce(const float* d_local, float* d_out, const uint64_t* peer_buffers, int rank, int world,
                            int n, uint32_t epoch, uint32_t* d_error_flag, void* stream);
 
+/* ---- multi-GPU in one process: one engine per GPU over contiguous track ranges -------------------
+ * cfg->tracks is the TOTAL track count Tg (cfg->device / track_offset / total_tracks are ignored);
+ * GPU g of n owns tracks [g*Tg/n, (g+1)*Tg/n).  host_ir [Tg][L], host_hist [Tg][L-1], h_in [Tg][B],
+ * h_out [Tg][B] or [B][Tg], h_mix [2][B] (the bus summed over ALL GPUs by b200conv_bus_allreduce over
+ * peer-mapped buffers).  One persistent submission thread per GPU; the call returns when every GPU is
+ * done.  No reference counterpart (the reference is single-GPU); SURVEY.md §8b/§8e. */
+typedef struct b200conv_group b200conv_group;
+int b200conv_group_create(const b200conv_config* cfg, int n_gpus, b200conv_group** out);
+void b200conv_group_destroy(b200conv_group* g);
+int b200conv_group_size(const b200conv_group* g);
+int b200conv_group_load_ir(b200conv_group* g, const float* host_ir);
+int b200conv_group_prime_history(b200conv_group* g, const float* host_hist);
+int b200conv_group_reset(b200conv_group* g);
+int b200conv_group_process_host(b200conv_group* g, const float* h_in, float* h_out, float* h_mix, uint32_t flags);
+const char* b200conv_group_last_error(void);
+
 /* Launch plan the engine would use for `cfg` on a device with `sm_count` SMs; needs no GPU.
  * plan[0..15] = direct: {A, CL, SPS, JSb, NS, G, Lc, cap, nbuf, xtile_blocks, ntiles, smem_bytes, MS, 0...}
  *               UPOLS : {P, M, logM, S, 0...}.  Used by the host-logic tests and by capacity planning. */

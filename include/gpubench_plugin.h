@@ -30,6 +30,8 @@ const char* gpubench_last_error(void);
 
 /* The CLI globals (cuda/globals.cu:4-9): --fs, --nRuns; stream != 0 is --mode stream. */
 void gpubench_set_globals(int fs, int nruns, int stream_mode);
+/* --nGpus: shard the tracks of subsequently created plugins over n GPUs (b200conv_group_*). */
+void gpubench_set_ngpus(int n);
 
 /* DAW-style pacing of runBenchmark (--dawsim, --dawsim-mode, --dawsim-jitter-us); enable = 0 turns it off. */
 void gpubench_set_dawsim(int enable, int sleep_mode, double jitter_us);

@@ -1,0 +1,56 @@
+"""b200conv_group_* (one process, one engine per GPU) on 2 real GPUs; skipped on a 1-GPU box."""
+import numpy as np
+import pytest
+import torch
+
+import gpuaudiobench_b200 as g
+from gpuaudiobench_b200 import plugin
+
+pytestmark = pytest.mark.gpu
+needs2 = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+
+
+def snr_db(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return 10 * np.log10((ref ** 2).sum() / max(((np.asarray(got, dtype=np.float64) - ref) ** 2).sum(), 1e-300))
+
+
+@needs2
+@pytest.mark.parametrize("algo", [g.ALGO_DIRECT, g.ALGO_UPOLS])
+@pytest.mark.parametrize("layout", [g.OUT_TRACK_MAJOR, g.OUT_SAMPLE_MAJOR])
+def test_two_gpu_group_matches_streaming_oracle_and_bus(oracle, algo, layout):
+    Tg, B, L, M = 21, 256, 3000, 9  # 21 tracks -> uneven shards 10 + 11
+    xs = oracle.generate_input(M * Tg * B, 13).reshape(M, Tg, B)
+    h = oracle.generate_ir(Tg, L, "accel")
+    want = np.stack([oracle.stream(xs[:, t, :].ravel(), h[t]) for t in range(Tg)])
+    theta = (np.arange(Tg) + 0.5) / Tg * np.pi / 2
+    gains = np.stack([np.cos(theta), np.sin(theta)], axis=1) / np.sqrt(Tg)
+    bus = gains.T @ want.astype(np.float64)
+    with g.ConvGroup(Tg, B, L, algo, 2, layout) as grp:
+        grp.load_ir(h)
+        outs = [grp.process_host(xs[m]) for m in range(M)]
+    got = np.concatenate([(y.T if layout == g.OUT_SAMPLE_MAJOR else y) for y, _ in outs], axis=1)
+    got_bus = np.concatenate([m for _, m in outs], axis=1)
+    min_snr = 100 if algo == g.ALGO_DIRECT else 90
+    assert snr_db(got, want) >= min_snr
+    assert snr_db(got_bus, bus) >= 90
+
+
+@needs2
+def test_plugin_on_two_gpus_validates_against_r1_and_r2():
+    plugin.set_ngpus(2)
+    try:
+        for name, L in (("Conv1D", 4096), ("Conv1D_accel", 4096)):
+            with plugin.Plugin(name, L, 512, 64) as p:
+                p.setup()
+                p.run(5, 3)
+                v = p.validate()
+                assert v["status"] == 0, (name, v)
+    finally:
+        plugin.set_ngpus(1)
+
+
+def test_group_rejects_more_gpus_than_visible():
+    with pytest.raises(g.B200ConvError) as ei:
+        g.ConvGroup(64, 512, 1024, g.ALGO_DIRECT, torch.cuda.device_count() + 1)
+    assert ei.value.code == g.engine.ERR_NO_DEVICE
