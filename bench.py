@@ -55,7 +55,7 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.004):
         self.samples, self.reasons, self.power = [], set(), []
         self.period, self._stop, self.max_mhz, self.ok = period, threading.Event(), None, False
         try:
@@ -181,6 +181,8 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
         wall = time.perf_counter() - wall0
     lat = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)], dtype=np.float64)  # ms
     launches = eng.query()["kernel_launches"] - launches_before
+    if world > 1 and bus_reduce.kind.startswith("own"):
+        launches += K  # the engine's own bus all-reduce kernel, one per step
     total_ms = float(lat.sum())
     if world > 1:
         tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)

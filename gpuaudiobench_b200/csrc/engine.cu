@@ -147,7 +147,8 @@ int plan_direct(b200conv_engine* e) {
     const size_t stage_bytes = static_cast<size_t>(d.JSb + d.xtile_blocks) * 64;
     const size_t red_bytes = static_cast<size_t>(kFirWarps) * d.A * 16 * sizeof(float);
     const int per_cta = static_cast<int>((units + d.G - 1) / d.G);
-    d.nbuf = std::min({per_cta, 4, kFirMaxStages});
+    const int depth = std::max(1, std::min(env_int("B200CONV_DIRECT_NBUF", 4), kFirMaxStages));
+    d.nbuf = std::min({per_cta, depth, kFirMaxStages});
     while (d.nbuf > 1 && 128 + d.nbuf * stage_bytes + red_bytes > kFirMaxSmem) --d.nbuf;
     d.smem = 128 + d.nbuf * stage_bytes + red_bytes;
     if (d.smem > kFirMaxSmem) return fail(B200CONV_ERR_INVALID, "direct engine: stage does not fit shared memory");
