@@ -14,7 +14,8 @@ the global track index); the only collective is the NCCL all-reduce of the stere
 The default line also carries the c3 and c4 results under "also" so one run shows both engines.
 
 Timing: W warm-up steps, then K timed steps, each bracketed by CUDA events on the launch stream,
-with an L2 flush (write of a 256 MiB buffer) between steps outside the brackets; the whole timed
+with an L2 flush (256 MiB write, then a 256 MiB read of a second buffer so that the flush's dirty
+lines are written back before the step instead of during it) between steps outside the brackets; the whole timed
 region is bracketed by barrier + torch.cuda.synchronize(); per-rank totals are max-reduced.
 `--impl reference` times the reference's own CPU implementation (oracle/_ref when built, else the
 oracle port) on the host cores for the same workload.
@@ -48,6 +49,29 @@ def measured_peaks():
             return json.load(f), "MEASURED_PEAKS.json"
     except Exception:
         return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback (B200_PROFILING.md)"
+
+
+class L2Flush:
+    """Evict the step's working set from the 126 MB L2 between timed steps.  A plain write of a large
+    buffer does that but leaves L2 full of DIRTY lines, and their write-back (~126 MB, ~20 us of HBM time)
+    is then charged to the next step's reads — an artifact of the flush, not of the workload.  So the write
+    is followed by a read pass over a second buffer: afterwards L2 holds clean foreign lines only."""
+    DESCRIPTION = ("flushed between steps outside the event brackets: 256 MiB write, then 256 MiB read of a second "
+                   "buffer (evicts the working set and leaves no dirty lines to write back inside the step)")
+
+    def __init__(self, dev, mode=None):
+        import torch
+        self.mode = mode or os.environ.get("B200CONV_BENCH_FLUSH", "write+read")
+        self.w = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        self.r = torch.zeros(64 << 20, dtype=torch.int32, device=dev) if self.mode == "write+read" else None
+        self.sink = None
+        self.description = self.DESCRIPTION if self.r is not None else \
+            "flushed between steps (256 MiB write outside the event brackets)"
+
+    def __call__(self, k):
+        self.w.fill_(k & 0xFF)
+        if self.r is not None:
+            self.sink = self.r.sum()
 
 
 class ClockSampler:
@@ -132,7 +156,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     out_shape = (B, Tg) if layout == g.OUT_SAMPLE_MAJOR else (T, B)
     d_y = torch.zeros(out_shape, device=dev)
     d_mix = torch.zeros(2, B, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush = L2Flush(dev)
     bus_reduce = BusAllReduce(d_mix, force_nccl=bool(os.environ.get("B200CONV_BUS_NCCL")))
 
     def step(k):
@@ -171,7 +195,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     with clocks:
         wall0 = time.perf_counter()
         for k in range(K):
-            flush.fill_(k & 0xFF)
+            flush(k)
             ev0[k].record(stream)
             step(k)
             ev1[k].record(stream)
@@ -201,7 +225,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     eng.set_profiling(True)
     KP = min(K, 100)
     for k in range(KP):
-        flush.fill_(k & 0xFF)
+        flush(k)
         eng.process(d_x[k % NB].data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
     torch.cuda.synchronize(dev)
     q = eng.query()
@@ -262,7 +286,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     aligned_start()
     e2e_lat = np.empty(K)
     for k in range(K):
-        flush.fill_(k & 0xFF)
+        flush(k)
         torch.cuda.synchronize(dev)
         t_a = time.perf_counter()
         e2e_step(k)
@@ -287,7 +311,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
         "dtype": "f32", "data": "synthetic (mt19937 seed 42 uniform(-1,1) input; Hamming-windowed-sinc IRs scaled 1/L, as the reference generates)",
         "config": {"workload": f"{name}: {label}", "algo": algo_name, "tracks_per_gpu": T, "total_tracks": Tg, "block": B,
                    "ir_taps": L, "fs": FS, "out_layout": layout_name, "partitions_or_splits": q["partitions"],
-                   "l2": "flushed between steps (256 MiB write outside the event brackets)",
+                   "l2": flush.description,
                    "timing": "sum of per-step CUDA-event times on the launch stream, max over ranks",
                    "collective": f"all-reduce of the stereo mix bus float[2][B]: {bus_reduce.kind}"},
         "rt_tracks": value * 1e9 / (L * FS),
