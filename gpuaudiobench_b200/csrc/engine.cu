@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "direct_fir.cuh"
+#include "strip.cuh"
 #include "upols.cuh"
 
 using namespace b200conv;
@@ -88,6 +89,15 @@ struct b200conv_engine {
     float* d_gains = nullptr;
     DirectState dir;
     UpolsState up;
+    // channel strip (b200conv_set_strip): device copies of the per-track parameters
+    uint32_t strip_ops = 0;
+    float strip_gain = 1.0f;
+    float* d_strip_gains = nullptr;  // [T] or null
+    float* d_strip_coef = nullptr;   // [T][5] or [5]
+    bool strip_shared_coef = false;
+    bool strip_use_gains = false;
+    float* d_strip_state = nullptr;  // [T][2]
+    float* d_strip_stats = nullptr;  // [T][2]
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float stage_ms[4] = {0, 0, 0, 0};
@@ -203,8 +213,32 @@ int reset_state(b200conv_engine* e) {
         CU_TRY(cudaMemset(e->up.X, 0, static_cast<size_t>(e->T) * e->up.P * e->up.M * sizeof(float2)));
         CU_TRY(cudaMemset(e->up.prev, 0, static_cast<size_t>(e->T) * e->B * sizeof(float)));
     }
+    if (e->d_strip_state) CU_TRY(cudaMemset(e->d_strip_state, 0, static_cast<size_t>(2) * e->T * sizeof(float)));
     CU_TRY(cudaDeviceSynchronize());
     e->blocks = 0;
+    return B200CONV_OK;
+}
+
+// convolution output -> strip, in place, on the launch stream (PDL: waits for the producing kernel)
+int run_strip(b200conv_engine* e, float* d_out, bool commit, cudaStream_t st) {
+    StripParams sp{};
+    sp.in = d_out;
+    sp.out = d_out;
+    sp.T = e->T;
+    sp.B = e->B;
+    sp.sample_major = (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR);
+    sp.ld = e->Tg;
+    sp.col0 = e->toff;
+    sp.ops = e->strip_ops;
+    sp.gain = e->strip_gain;
+    sp.gains = e->strip_use_gains ? e->d_strip_gains : nullptr;
+    sp.coef = e->d_strip_coef;
+    sp.shared_coef = e->strip_shared_coef ? 1 : 0;
+    sp.state = e->d_strip_state;
+    sp.stats = e->d_strip_stats;
+    sp.peek = commit ? 0 : 1;
+    CU_TRY(launch_strip(sp, st));
+    e->launches += 1;
     return B200CONV_OK;
 }
 
@@ -554,13 +588,21 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         f.Tg = e->Tg;
         f.toff = e->toff;
         f.gains = e->d_gains;
-        f.mix = d_mix;
+        f.mix = e->strip_ops ? nullptr : d_mix;  // with a strip the bus is taken after it
         f.d_in = d_in;
         f.ring = commit ? d.ring : nullptr;
         f.cap = d.cap;
         f.pos = d.pos;
         CU_TRY(launch_fir_finish_mix(f, st));
         e->launches += 2;
+        if (e->strip_ops) {
+            int rc = run_strip(e, d_out, commit, st);
+            if (rc) return rc;
+            if (d_mix) {
+                CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
+                e->launches += 1;
+            }
+        }
         tm.mark();
         marks = tm.idx;
         if (commit) d.pos = (d.pos + e->B) % d.cap;
@@ -631,6 +673,10 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             CU_TRY(launch_irfft_ols(r, st));
             e->launches += 3;
         }
+        if (e->strip_ops) {
+            int rc = run_strip(e, d_out, commit, st);
+            if (rc) return rc;
+        }
         if (d_mix) {
             CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
             e->launches += 1;
@@ -667,7 +713,7 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     // input: every engine reads d_in once or twice -> read it straight from pinned host memory
     const bool in_place = (zc & 1) && is_pinned_host(h_in);
     // results: only the direct engine produces output and bus in its last kernel without re-reading them
-    const bool out_place = (zc & 2) && direct && h_out && is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
+    const bool out_place = (zc & 2) && !e->strip_ops && direct && h_out && is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
     const float* d_in = h_in;
     if (!in_place) {
         CU_TRY(cudaMemcpyAsync(e->d_in_stage, h_in, tb * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -682,7 +728,7 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     // fused UPOLS: the kernel keeps a device copy of the output for the bus kernel and ALSO posts it
     // to the pinned host buffer itself; the bus kernel writes its 2*B floats to pinned memory too
     // (track-major only: a sample-major column tile would be scattered 4-byte PCIe writes — measured 2x slower)
-    const bool dual = (zc & 2) && !direct && e->up.fused && e->cfg.out_layout == B200CONV_OUT_TRACK_MAJOR && h_out &&
+    const bool dual = (zc & 2) && !e->strip_ops && !direct && e->up.fused && e->cfg.out_layout == B200CONV_OUT_TRACK_MAJOR && h_out &&
                       is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
     if (dual) {
         int rc = process_impl(e, d_in, e->d_out_stage, h_out, h_mix, flags, st);
@@ -703,6 +749,101 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     }
     if (h_mix) CU_TRY(cudaMemcpyAsync(h_mix, e->d_mix_stage, static_cast<size_t>(2) * e->B * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    return B200CONV_OK;
+}
+
+int b200conv_set_strip(b200conv_engine* e, const b200conv_strip* strip) {
+    if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_set_strip: null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (!strip || !(strip->ops & (B200CONV_STRIP_STATS | B200CONV_STRIP_GAIN | B200CONV_STRIP_BIQUAD))) {
+        e->strip_ops = 0;
+        return B200CONV_OK;
+    }
+    if ((strip->ops & B200CONV_STRIP_BIQUAD) && !strip->biquad)
+        return fail(B200CONV_ERR_INVALID, "b200conv_set_strip: BIQUAD needs coefficients");
+    const size_t T = static_cast<size_t>(e->T);
+    if (!e->d_strip_state) {
+        int rc = dev_alloc(e, &e->d_strip_state, 2 * T);
+        if (!rc) rc = dev_alloc(e, &e->d_strip_stats, 2 * T);
+        if (!rc) rc = dev_alloc(e, &e->d_strip_gains, T);
+        if (!rc) rc = dev_alloc(e, &e->d_strip_coef, 5 * T);
+        if (rc) return rc;
+    }
+    CU_TRY(cudaMemset(e->d_strip_state, 0, 2 * T * sizeof(float)));
+    CU_TRY(cudaMemset(e->d_strip_stats, 0, 2 * T * sizeof(float)));
+    e->strip_gain = strip->gain;
+    float* gains = nullptr;
+    if ((strip->ops & B200CONV_STRIP_GAIN) && strip->gains) {
+        CU_TRY(cudaMemcpy(e->d_strip_gains, strip->gains, T * sizeof(float), cudaMemcpyHostToDevice));
+        gains = e->d_strip_gains;
+    }
+    e->strip_shared_coef = (strip->ops & B200CONV_STRIP_SHARED_COEFFS) != 0;
+    if (strip->ops & B200CONV_STRIP_BIQUAD)
+        CU_TRY(cudaMemcpy(e->d_strip_coef, strip->biquad, (e->strip_shared_coef ? 5 : 5 * T) * sizeof(float),
+                          cudaMemcpyHostToDevice));
+    e->strip_use_gains = gains != nullptr;
+    e->strip_ops = strip->ops & (B200CONV_STRIP_STATS | B200CONV_STRIP_GAIN | B200CONV_STRIP_BIQUAD);
+    return B200CONV_OK;
+}
+
+int b200conv_strip_state(b200conv_engine* e, float* host_state, int set) {
+    if (!e || !host_state) return fail(B200CONV_ERR_INVALID, "b200conv_strip_state: null argument");
+    if (!e->d_strip_state) return fail(B200CONV_ERR_STATE, "b200conv_strip_state: no strip attached");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t bytes = static_cast<size_t>(2) * e->T * sizeof(float);
+    if (set)
+        CU_TRY(cudaMemcpy(e->d_strip_state, host_state, bytes, cudaMemcpyHostToDevice));
+    else
+        CU_TRY(cudaMemcpy(host_state, e->d_strip_state, bytes, cudaMemcpyDeviceToHost));
+    return B200CONV_OK;
+}
+
+int b200conv_strip_stats(b200conv_engine* e, float* host_stats) {
+    if (!e || !host_stats) return fail(B200CONV_ERR_INVALID, "b200conv_strip_stats: null argument");
+    if (!e->d_strip_stats) return fail(B200CONV_ERR_STATE, "b200conv_strip_stats: no strip attached");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(host_stats, e->d_strip_stats, static_cast<size_t>(2) * e->T * sizeof(float), cudaMemcpyDeviceToHost));
+    return B200CONV_OK;
+}
+
+int b200conv_strip_process(const float* d_in, float* d_out, uint32_t tracks, uint32_t block, uint32_t layout, uint32_t ld,
+                           uint32_t col0, const b200conv_strip* strip, float* d_state, float* d_stats, uint32_t flags,
+                           void* stream) {
+    if (!d_in || !d_out || !strip || tracks == 0 || block == 0)
+        return fail(B200CONV_ERR_INVALID, "b200conv_strip_process: null or empty argument");
+    const uint32_t ops = strip->ops & (B200CONV_STRIP_STATS | B200CONV_STRIP_GAIN | B200CONV_STRIP_BIQUAD);
+    if (!ops) return fail(B200CONV_ERR_INVALID, "b200conv_strip_process: no operation selected");
+    if ((ops & B200CONV_STRIP_BIQUAD) && (!strip->biquad || !d_state))
+        return fail(B200CONV_ERR_INVALID, "b200conv_strip_process: BIQUAD needs coefficients and a state buffer");
+    if (layout == B200CONV_OUT_SAMPLE_MAJOR && static_cast<uint64_t>(col0) + tracks > ld)
+        return fail(B200CONV_ERR_INVALID, "b200conv_strip_process: column tile exceeds the leading dimension");
+    if (layout != B200CONV_OUT_SAMPLE_MAJOR && layout != B200CONV_OUT_TRACK_MAJOR)
+        return fail(B200CONV_ERR_INVALID, "b200conv_strip_process: unknown layout");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(B200CONV_ERR_NO_DEVICE, "b200conv_strip_process: no CUDA device");
+    }
+    StripParams sp{};
+    sp.in = d_in;
+    sp.out = d_out;
+    sp.T = static_cast<int>(tracks);
+    sp.B = static_cast<int>(block);
+    sp.sample_major = (layout == B200CONV_OUT_SAMPLE_MAJOR);
+    sp.ld = static_cast<int>(ld);
+    sp.col0 = static_cast<int>(col0);
+    sp.ops = ops;
+    sp.gain = strip->gain;
+    sp.gains = (ops & B200CONV_STRIP_GAIN) ? strip->gains : nullptr;
+    sp.coef = strip->biquad;
+    sp.shared_coef = (strip->ops & B200CONV_STRIP_SHARED_COEFFS) ? 1 : 0;
+    sp.state = d_state;
+    sp.stats = d_stats;
+    sp.peek = (flags & B200CONV_PEEK) ? 1 : 0;
+    CU_TRY(launch_strip(sp, static_cast<cudaStream_t>(stream)));
     return B200CONV_OK;
 }
 

@@ -16,6 +16,7 @@ ABI_VERSION = 1
 ALGO_DIRECT, ALGO_UPOLS = 0, 1
 OUT_TRACK_MAJOR, OUT_SAMPLE_MAJOR = 0, 1
 PEEK = 1
+STRIP_STATS, STRIP_GAIN, STRIP_BIQUAD, STRIP_SHARED_COEFFS = 1, 2, 4, 8
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_ABI = 0, -1, -2, -3, -4, -5
 
@@ -32,6 +33,10 @@ class Info(C.Structure):
                 ("partitions", C.c_uint32), ("fft_size", C.c_uint32), ("kernels_per_block", C.c_uint32),
                 ("sm_count", C.c_uint32), ("stage_count", C.c_uint32), ("dominant_stage", C.c_uint32),
                 ("stage_ms", C.c_float * 4), ("stage_calls", C.c_uint32), ("stage_name", (C.c_char * 24) * 4)]
+
+
+class Strip(C.Structure):
+    _fields_ = [("ops", C.c_uint32), ("gain", C.c_float), ("gains", C.c_void_p), ("biquad", C.c_void_p)]
 
 
 class B200ConvError(RuntimeError):
@@ -68,6 +73,11 @@ def load_library():
     L.b200conv_plan.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_int32)]
     L.b200conv_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.b200conv_rfft.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.b200conv_set_strip.argtypes = [C.c_void_p, C.POINTER(Strip)]
+    L.b200conv_strip_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.b200conv_strip_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200conv_strip_process.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.POINTER(Strip), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.b200conv_bus_buffer_bytes.argtypes = [C.c_int, C.c_int]
     L.b200conv_bus_buffer_bytes.restype = C.c_size_t
     L.b200conv_bus_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
@@ -119,6 +129,16 @@ def rfft(d_in, d_out, count, n, stream=0):
 
 def _host_ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def strip_process(d_in, d_out, tracks, block, ops, gain=1.0, d_gains=0, d_biquad=0, shared_coeffs=True, d_state=0,
+                  d_stats=0, layout=OUT_TRACK_MAJOR, ld=0, col0=0, flags=0, stream=0):
+    """The channel strip alone on device buffers (addresses); see b200conv_strip_process."""
+    st = Strip(ops | (STRIP_SHARED_COEFFS if shared_coeffs else 0), gain, d_gains or None, d_biquad or None)
+    _check(load_library().b200conv_strip_process(C.c_void_p(d_in), C.c_void_p(d_out), tracks, block, layout, ld, col0,
+                                                 C.byref(st), C.c_void_p(d_state) if d_state else None,
+                                                 C.c_void_p(d_stats) if d_stats else None, flags,
+                                                 C.c_void_p(stream) if stream else None))
 
 
 class ConvGroup:
@@ -226,6 +246,31 @@ class ConvEngine:
         g = np.ascontiguousarray(gains, dtype=np.float32)
         assert g.size == 2 * self.T
         _check(self.lib.b200conv_set_mix_gains(self.handle, _host_ptr(g)))
+
+    def set_strip(self, ops=0, gain=1.0, gains=None, biquad=None):
+        """Attach the channel strip (host arrays: gains [T], biquad [5] shared or [T][5]); ops == 0 removes it."""
+        if not ops:
+            _check(self.lib.b200conv_set_strip(self.handle, None))
+            return
+        g = None if gains is None else np.ascontiguousarray(gains, dtype=np.float32)
+        c = None if biquad is None else np.ascontiguousarray(biquad, dtype=np.float32)
+        assert g is None or g.size == self.T
+        assert c is None or c.size in (5, 5 * self.T)
+        if c is not None and c.size == 5:
+            ops |= STRIP_SHARED_COEFFS
+        st = Strip(ops, gain, None if g is None else g.ctypes.data, None if c is None else c.ctypes.data)
+        _check(self.lib.b200conv_set_strip(self.handle, C.byref(st)))
+
+    def strip_state(self, new_state=None):
+        st = np.zeros((self.T, 2), dtype=np.float32) if new_state is None else \
+            np.ascontiguousarray(new_state, dtype=np.float32).reshape(self.T, 2)
+        _check(self.lib.b200conv_strip_state(self.handle, _host_ptr(st), 0 if new_state is None else 1))
+        return st
+
+    def strip_stats(self):
+        st = np.zeros((self.T, 2), dtype=np.float32)
+        _check(self.lib.b200conv_strip_stats(self.handle, _host_ptr(st)))
+        return st
 
     def process(self, d_in, d_out, d_mix=None, flags=0, stream=0):
         _check(self.lib.b200conv_process(self.handle, C.c_void_p(d_in), C.c_void_p(d_out),

@@ -2,7 +2,7 @@
 // Named constants of the convolution path.
 // Mirrors the conv-related entries of the reference's cuda/benchmark_constants.cuh:22-25 (which
 // the reference declares but then hard-codes as literals in bench_conv1d.cu:166-169); here the
-// plugins actually use them.  Constants of the other 15 benchmarks are out of scope.
+// plugins actually use them.  Constants of the remaining benchmarks are out of scope.
 namespace BenchmarkConstants {
 
 // Hamming window w[k] = A0 - A1 cos(2 pi k / (L-1))
@@ -24,5 +24,11 @@ constexpr double CONV1D_ACCEL_MAX_ABS_REL_TO_PEAK = 1e-4;
 // Default impulse-response lengths of the two plugins (bench_conv1d.cuh:11, bench_conv1d_accel.cuh:11)
 constexpr int CONV1D_DEFAULT_IR_LEN = 1024;
 constexpr int CONV1D_ACCEL_DEFAULT_IR_LEN = 512;
+
+// Channel-strip plugins: cuda/benchmark_constants.cuh:6-7, cuda/bench_iir.cu:162,213
+constexpr float GAIN_VALUE = 2.0f;
+constexpr float GAINSTATS_GAIN = 0.5f;
+constexpr float IIR_NORMALIZED_CUTOFF = 0.25f;  // fc / fs
+constexpr float IIR_BUTTERWORTH_Q = 0.707f;
 
 }  // namespace BenchmarkConstants

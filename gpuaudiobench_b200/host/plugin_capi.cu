@@ -10,6 +10,7 @@
 #include "bench_conv1d.cuh"
 #include "bench_conv1d_accel.cuh"
 #include "bench_fft.cuh"
+#include "bench_strip.cuh"
 #include "conv_common.cuh"
 #include "registry.cuh"
 
@@ -18,6 +19,7 @@ struct gpubench_plugin {
     Conv1DBenchmark* direct = nullptr;
     Conv1DAccelBenchmark* accel = nullptr;
     FFTBenchmark* fft = nullptr;
+    ChannelStripBenchmark* strip = nullptr;
 };
 
 namespace {
@@ -77,6 +79,7 @@ gpubench_plugin* gpubench_create(const char* name, int ir_len, int buffer_size, 
     p->direct = dynamic_cast<Conv1DBenchmark*>(bench.get());
     p->accel = dynamic_cast<Conv1DAccelBenchmark*>(bench.get());
     p->fft = dynamic_cast<FFTBenchmark*>(bench.get());
+    p->strip = dynamic_cast<ChannelStripBenchmark*>(bench.get());
     p->bench = std::move(bench);
     return p;
 }
@@ -114,7 +117,8 @@ int gpubench_validate(gpubench_plugin* p, gpubench_validation* out, char* messag
                 out->max_abs_err = v.max_error;
                 out->ref_peak = 0.0;
             } else {
-                const float* ref = p->direct ? p->direct->cpuReference() : p->accel->cpuReference();
+                const float* ref = p->strip ? p->strip->cpuReference()
+                                   : p->direct ? p->direct->cpuReference() : p->accel->cpuReference();
                 const ConvCommon::Accuracy a = ConvCommon::measureAccuracy(p->bench->hostOutput(), ref, p->bench->getTotalElements());
                 out->snr_db = a.snr_db;
                 out->max_abs_err = a.max_abs_err;
@@ -131,9 +135,27 @@ int gpubench_validate(gpubench_plugin* p, gpubench_validation* out, char* messag
 }
 
 const float* gpubench_host_input(gpubench_plugin* p) { return p->bench->hostInput(); }
-const float* gpubench_host_ir(gpubench_plugin* p) { return p->direct ? p->direct->hostIR() : p->accel->hostIR(); }
+const float* gpubench_host_ir(gpubench_plugin* p) {
+    return p->direct ? p->direct->hostIR() : p->accel ? p->accel->hostIR() : nullptr;
+}
 const float* gpubench_host_output(gpubench_plugin* p) { return p->bench->hostOutput(); }
-const float* gpubench_cpu_reference(gpubench_plugin* p) { return p->direct ? p->direct->cpuReference() : p->accel->cpuReference(); }
+const float* gpubench_cpu_reference(gpubench_plugin* p) {
+    return p->strip ? p->strip->cpuReference() : p->direct ? p->direct->cpuReference() : p->accel ? p->accel->cpuReference() : nullptr;
+}
+
+const float* gpubench_strip_stats(gpubench_plugin* p, int cpu) {
+    return !p->strip ? nullptr : cpu ? p->strip->cpuStats() : p->strip->hostStats();
+}
+const float* gpubench_strip_state(gpubench_plugin* p, int cpu) {
+    return !p->strip ? nullptr : cpu ? p->strip->cpuState() : p->strip->hostState();
+}
+int gpubench_strip_coefficients(gpubench_plugin* p, float out5[5]) {
+    if (!p->strip) return 1;
+    const IIRCoefficients& c = p->strip->coefficients();
+    out5[0] = c.b0; out5[1] = c.b1; out5[2] = c.b2; out5[3] = c.a1; out5[4] = c.a2;
+    return 0;
+}
+int gpubench_strip_bit_exact(gpubench_plugin* p) { return p->strip && p->strip->lastRunBitExact() ? 1 : 0; }
 
 const float* gpubench_fft_input(gpubench_plugin* p) { return p->fft ? p->fft->hostInputFFT() : nullptr; }
 const float* gpubench_fft_output(gpubench_plugin* p) { return p->fft ? reinterpret_cast<const float*>(p->fft->hostOutputFFT()) : nullptr; }

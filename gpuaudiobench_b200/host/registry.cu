@@ -6,6 +6,7 @@
 #include "bench_conv1d.cuh"
 #include "bench_conv1d_accel.cuh"
 #include "bench_fft.cuh"
+#include "bench_strip.cuh"
 
 namespace {
 struct Entry {
@@ -21,6 +22,10 @@ const std::vector<Entry>& registry() {
         {"Conv1D_accel",
          [] { return std::make_unique<Conv1DAccelBenchmark>(IR_LEN > 0 ? IR_LEN : Conv1DAccelBenchmark::DEFAULT_IR_LEN); }},
         {"FFT1D", [] { return std::make_unique<FFTBenchmark>(); }},  // first step beyond the conv path
+        // the channel-strip ops next to the mix bus, registry names of cuda/main.cu:85-93
+        {"gain", [] { return std::make_unique<GainBenchmark>(); }},
+        {"GainStats", [] { return std::make_unique<GainStatsBenchmark>(); }},
+        {"IIRFilter", [] { return std::make_unique<IIRBenchmark>(); }},
     };
     return entries;
 }

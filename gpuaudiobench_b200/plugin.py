@@ -41,6 +41,11 @@ def load_library():
                  "gpubench_fft_input", "gpubench_fft_output", "gpubench_fft_reference"):
         getattr(L, name).argtypes = [C.c_void_p]
         getattr(L, name).restype = C.POINTER(C.c_float)
+    for name in ("gpubench_strip_stats", "gpubench_strip_state"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_int]
+        getattr(L, name).restype = C.POINTER(C.c_float)
+    L.gpubench_strip_coefficients.argtypes = [C.c_void_p, C.c_void_p]
+    L.gpubench_strip_bit_exact.argtypes = [C.c_void_p]
     L.gpubench_json_results.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     L.gpubench_statistics.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     L.gpubench_set_ngpus.argtypes = [C.c_int]
@@ -139,7 +144,7 @@ class Plugin:
         return self._view(self.lib.gpubench_host_ir, (self.T, self.L))
 
     def _out_shape(self):
-        return (self.T, self.B) if self.name == "Conv1D" else (self.B, self.T)
+        return (self.B, self.T) if self.name == "Conv1D_accel" else (self.T, self.B)
 
     def host_output(self):
         return self._view(self.lib.gpubench_host_output, self._out_shape())
@@ -158,3 +163,20 @@ class Plugin:
     def fft_reference(self):
         v = self._view(self.lib.gpubench_fft_reference, (self.T, 513, 2))
         return v[..., 0] + 1j * v[..., 1]
+
+    # gain / GainStats / IIRFilter plugin views (channel strip)
+    def strip_stats(self, cpu=False):
+        ptr = self.lib.gpubench_strip_stats(self.handle, 1 if cpu else 0)
+        return np.ctypeslib.as_array(ptr, shape=(self.T, 2)).copy()
+
+    def strip_state(self, cpu=False):
+        ptr = self.lib.gpubench_strip_state(self.handle, 1 if cpu else 0)
+        return np.ctypeslib.as_array(ptr, shape=(self.T, 2)).copy()
+
+    def strip_coefficients(self):
+        out = np.zeros(5, dtype=np.float32)
+        self._check(self.lib.gpubench_strip_coefficients(self.handle, out.ctypes.data))
+        return out
+
+    def strip_bit_exact(self):
+        return bool(self.lib.gpubench_strip_bit_exact(self.handle))

@@ -154,6 +154,47 @@ int b200conv_set_profiling(b200conv_engine* e, int on);
  * cufftExecR2C of the reference's FFT1D benchmark (cuda/bench_fft.cu:63,105) — SURVEY.md §8(f) #3. */
 int b200conv_rfft(const float* d_in, void* d_out, int count, int n, void* stream);
 
+/* ---- channel strip on the output stage ---------------------------------------
+ * Per-track post-processing of the convolved output, applied before the stereo bus, in this order:
+ *   B200CONV_STRIP_STATS   mean and max of the strip INPUT per track, float [T][2]
+ *                          — replaces GainStatsKernel's statistics, cuda/bench_gainstats.cu:15-31
+ *   B200CONV_STRIP_GAIN    y = gain * x  — replaces GainKernel, cuda/bench_gain.cu:6-24 (and the gain of
+ *                          GainStatsKernel, cuda/bench_gainstats.cu:22)
+ *   B200CONV_STRIP_BIQUAD  Direct Form II biquad, w = x - a1 z1 - a2 z2, y = b0 w + b1 z1 + b2 z2, state
+ *                          (z1, z2) per track carried from block to block — replaces IIRFilterKernel,
+ *                          cuda/bench_iir.cu:10-44
+ * Outputs, state and statistics are bit-identical to the reference's CPU loops (cuda/bench_gain.cu:90-92,
+ * bench_gainstats.cu:121-142, bench_iir.cu:176-203) evaluated on the same input. */
+#define B200CONV_STRIP_STATS 1u
+#define B200CONV_STRIP_GAIN 2u
+#define B200CONV_STRIP_BIQUAD 4u
+#define B200CONV_STRIP_SHARED_COEFFS 8u /* `biquad` holds ONE coefficient set for all tracks (the reference's case) */
+
+typedef struct b200conv_strip {
+    uint32_t ops;        /* OR of the B200CONV_STRIP_* bits above                              */
+    float gain;          /* used when gains == NULL                                            */
+    const float* gains;  /* float [T] per-track gains, or NULL                                 */
+    const float* biquad; /* float [T][5] = b0,b1,b2,a1,a2 (a0 == 1), or [5] with SHARED_COEFFS */
+} b200conv_strip;
+
+/* Attach (strip != NULL; pointers are HOST memory, copied) or remove (NULL) the engine's channel strip.
+ * Attaching zeroes the biquad state.  With a strip attached, b200conv_process runs
+ * convolution -> strip -> bus; B200CONV_PEEK leaves the biquad state untouched as well. */
+int b200conv_set_strip(b200conv_engine* e, const b200conv_strip* strip);
+/* set == 0: copy the biquad state float [T][2] = (z1, z2) to host_state; set != 0: load it. */
+int b200conv_strip_state(b200conv_engine* e, float* host_state, int set);
+/* mean / max of the latest block, float [T][2], copied to host_stats (synchronises the engine's stream). */
+int b200conv_strip_stats(b200conv_engine* e, float* host_stats);
+
+/* The strip alone, stateless, on caller-owned DEVICE memory of the current device (what the Gain,
+ * GainStats and IIRFilter plugins call).  layout TRACK_MAJOR: d_in/d_out float [T][B]; SAMPLE_MAJOR:
+ * float [B][ld] with track t in column col0 + t.  d_out may equal d_in.  strip->gains / ->biquad are
+ * DEVICE pointers here.  d_state float [T][2] (required for BIQUAD; left unchanged under
+ * B200CONV_PEEK), d_stats float [T][2] or NULL. */
+int b200conv_strip_process(const float* d_in, float* d_out, uint32_t tracks, uint32_t block, uint32_t layout,
+                           uint32_t ld, uint32_t col0, const b200conv_strip* strip, float* d_state, float* d_stats,
+                           uint32_t flags, void* stream);
+
 /* ---- the one collective of the path: all-reduce of the stereo bus over NVLink peer memory ----
  * No reference counterpart (the reference is single-GPU).  `peer_buffers[p]` is the
  * address, valid on THIS device, of rank p's symmetric buffer of b200conv_bus_buffer_bytes(world, n)

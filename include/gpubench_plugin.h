@@ -63,6 +63,15 @@ const float* gpubench_fft_input(gpubench_plugin* p);
 const float* gpubench_fft_output(gpubench_plugin* p);
 const float* gpubench_fft_reference(gpubench_plugin* p);
 
+/* gain / GainStats / IIRFilter plugins (channel strip).  cpu == 0: what the device
+ * produced in the last iteration; cpu != 0: the plugin's CPU loop (valid after gpubench_validate).
+ * stats: float [T][2] mean, max (cuda/bench_gainstats.cu:29-30); state: float [T][2] z1, z2
+ * (cuda/bench_iir.cu:42-43).  NULL for other plugins. */
+const float* gpubench_strip_stats(gpubench_plugin* p, int cpu);
+const float* gpubench_strip_state(gpubench_plugin* p, int cpu);
+int gpubench_strip_coefficients(gpubench_plugin* p, float out5[5]); /* b0 b1 b2 a1 a2 (cuda/bench_iir.cu:205-228) */
+int gpubench_strip_bit_exact(gpubench_plugin* p);                   /* 1 if the last validate() found identical bits */
+
 /* The reference's result writers (globals.cu:69-182) for a latency vector. */
 int gpubench_json_results(const float* latencies_ms, size_t n, const char* name, int fs, int bufsize, int ntracks,
                           char* out, size_t cap);

@@ -274,6 +274,97 @@ uint64_t oracle_fnv1a64(const void* data, size_t nbytes) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Channel-strip stages: the CPU references of the Gain, GainStats and IIRFilter
+// plugins.  Track-major [T][B] in and out.
+// ---------------------------------------------------------------------------------------------
+
+// cuda/bench_gain.cu:90-92 (GainBenchmark::calculateCPUReference; GAIN_VALUE = 2.0f,
+// cuda/benchmark_constants.cuh:6).
+void oracle_gain(const float* x, float* y, size_t n, float gain) {
+    for (size_t i = 0; i < n; ++i) y[i] = gain * x[i];
+}
+
+// cuda/bench_gainstats.cu:121-142 (GAINSTATS_GAIN = 0.5f, benchmark_constants.cuh:7): output
+// gain * x; per track the running float sum / B and the maximum of the INPUT, stats [T][2].
+void oracle_gainstats(const float* x, float* y, float* stats, size_t T, size_t B, float gain) {
+    for (size_t i = 0; i < T * B; ++i) y[i] = gain * x[i];
+    for (size_t t = 0; t < T; ++t) {
+        float mean = 0.0f;
+        float maxVal = -1e9f;
+        for (size_t i = 0; i < B; ++i) {
+            float samp = x[t * B + i];
+            mean += samp;
+            if (samp > maxVal) maxVal = samp;
+        }
+        mean /= B;
+        stats[2 * t + 0] = mean;
+        stats[2 * t + 1] = maxVal;
+    }
+}
+
+// cuda/bench_iir.cu:205-228 (calculateButterworthCoefficients; the plugin passes 0.25f, :162).
+// out5 = b0, b1, b2, a1, a2 after normalisation by a0.
+void oracle_butterworth(float normalized_frequency, float* out5) {
+    const float PI = 3.14159265358979323846f;
+    float omega = 2.0f * PI * normalized_frequency;
+    float cos_omega = cosf(omega);
+    float sin_omega = sinf(omega);
+    float alpha = sin_omega / (2.0f * 0.707f);
+    float b0 = (1.0f - cos_omega) / 2.0f;
+    float b1 = 1.0f - cos_omega;
+    float b2 = (1.0f - cos_omega) / 2.0f;
+    float a0 = 1.0f + alpha;
+    float a1 = -2.0f * cos_omega;
+    float a2 = 1.0f - alpha;
+    out5[0] = b0 / a0;
+    out5[1] = b1 / a0;
+    out5[2] = b2 / a0;
+    out5[3] = a1 / a0;
+    out5[4] = a2 / a0;
+}
+
+// cuda/bench_iir.cu:176-203 (iirFilterCPUReference): Direct Form II biquad per track, state
+// [T][2] = (z1, z2) read at entry and written back.  coeffs_stride = 0: one coefficient set for all
+// tracks (the reference's case); 5: coeffs is [T][5].
+void oracle_iir(const float* x, float* y, const float* coeffs, int coeffs_stride, float* state, int T, int B) {
+    for (int track = 0; track < T; ++track) {
+        const float* c = coeffs + static_cast<size_t>(track) * coeffs_stride;
+        const float b0 = c[0], b1 = c[1], b2 = c[2], a1 = c[3], a2 = c[4];
+        float z1 = state[track * 2];
+        float z2 = state[track * 2 + 1];
+        const size_t start = static_cast<size_t>(track) * B;
+        for (int i = 0; i < B; ++i) {
+            float xin = x[start + i];
+            float w = xin - a1 * z1 - a2 * z2;
+            float out = b0 * w + b1 * z1 + b2 * z2;
+            z2 = z1;
+            z1 = w;
+            y[start + i] = out;
+        }
+        state[track * 2] = z1;
+        state[track * 2 + 1] = z2;
+    }
+}
+
+// The engine's strip = the three stages chained in the order include/b200conv.h states: statistics of
+// the input, gain, biquad.  ops bits: 1 STATS, 2 GAIN, 4 BIQUAD.  gains: [T] or null (then `gain`).
+void oracle_strip(const float* x, float* y, int T, int B, unsigned ops, float gain, const float* gains,
+                  const float* coeffs, int coeffs_stride, float* state, float* stats) {
+    std::vector<float> tmp(static_cast<size_t>(B)), sink(static_cast<size_t>(B));
+    for (int t = 0; t < T; ++t) {
+        const float* xt = x + static_cast<size_t>(t) * B;
+        float* yt = y + static_cast<size_t>(t) * B;
+        std::copy(xt, xt + B, tmp.begin());
+        if (ops & 1u) oracle_gainstats(xt, sink.data(), stats + 2 * t, 1, static_cast<size_t>(B), 1.0f);
+        if (ops & 2u) oracle_gain(xt, tmp.data(), static_cast<size_t>(B), gains ? gains[t] : gain);
+        if (ops & 4u)
+            oracle_iir(tmp.data(), yt, coeffs + static_cast<size_t>(t) * coeffs_stride, 0, state + 2 * t, 1, B);
+        else
+            std::copy(tmp.begin(), tmp.end(), yt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // CPU-baseline timing legs (bench.py cpu_baseline / --impl reference when oracle/_ref is absent).
 // The reference runs its oracle single-threaded inside setupBenchmark (bench_conv1d.cu:42-55);
 // tracks are independent, so the threaded leg splits [0, T) into contiguous ranges.  Returns

@@ -28,11 +28,30 @@
 #include "bench_conv1d.cuh"        // /root/reference/cuda/bench_conv1d.cuh
 #include "bench_conv1d_accel.cuh"  // /root/reference/cuda/bench_conv1d_accel.cuh
 #include "bench_fft.cuh"           // /root/reference/cuda/bench_fft.cuh
+#include "bench_gain.cuh"          // /root/reference/cuda/bench_gain.cuh
+#include "bench_gainstats.cuh"     // /root/reference/cuda/bench_gainstats.cuh
+#include "bench_iir.cuh"           // /root/reference/cuda/bench_iir.cuh
+#include "benchmark_constants.cuh" // /root/reference/cuda/benchmark_constants.cuh
 #undef private
 #undef protected
 
 #include <fcntl.h>
 #include <unistd.h>
+
+// Link shims, not algorithm: cuda/bench_iir.cu:135-141 calls allocateHostBuffer/allocateDeviceBuffer with
+// T = IIRCoefficients, but cuda/bench_utils.cu:173-181 instantiates those templates for float, int and
+// cufftComplex only and keeps the definitions out of the header — the reference's IIR plugin cannot link
+// as shipped.  The members that need them (allocateIIRBuffers) are never reached through this shim.
+namespace BenchmarkUtils {
+template <>
+IIRCoefficients* allocateHostBuffer<IIRCoefficients>(size_t, const std::string&) {
+    throw std::runtime_error("allocateHostBuffer<IIRCoefficients>: not instantiated by the reference");
+}
+template <>
+IIRCoefficients* allocateDeviceBuffer<IIRCoefficients>(size_t, const std::string&) {
+    throw std::runtime_error("allocateDeviceBuffer<IIRCoefficients>: not instantiated by the reference");
+}
+}  // namespace BenchmarkUtils
 
 namespace {
 // The reference's Conv1DAccelBenchmark constructor printf()s (bench_conv1d_accel.cu:55); callers such
@@ -136,6 +155,46 @@ int ref_generate_ir_accel(float* h, int T, int L) {
 void ref_fft_reference(const float* input, float* re, float* im, int size) {
     static FFTBenchmark* inst = new FFTBenchmark(1, 1);
     inst->cpuFFTReference(input, re, im, size);
+}
+
+// cuda/bench_gain.cu:82-93 (GainBenchmark::calculateCPUReference).  The member reads the plugin's own
+// host input buffer and writes its cpu_reference member; both are pointed at the caller's arrays for
+// the duration of the call.  Returns the gain constant the reference used.
+float ref_gain_reference(const float* x, float* y, size_t B, size_t T) {
+    auto* b = new GainBenchmark(B, T, true);  // leaked on purpose (see directInstance)
+    b->buffers.h_input = const_cast<float*>(x);
+    b->cpu_reference = y;
+    b->calculateCPUReference();
+    b->buffers.h_input = nullptr;
+    b->cpu_reference = nullptr;
+    return BenchmarkConstants::GAIN_VALUE;
+}
+
+// cuda/bench_gainstats.cu:116-143 (GainStatsBenchmark::calculateCPUReference): y [T][B], stats [T][2].
+float ref_gainstats_reference(const float* x, float* y, float* stats, size_t B, size_t T) {
+    auto* b = new GainStatsBenchmark(B, T);
+    b->buffers.h_input = const_cast<float*>(x);
+    b->cpu_reference = y;
+    b->cpu_stats_reference = stats;
+    b->calculateCPUReference();
+    b->buffers.h_input = nullptr;
+    b->cpu_reference = nullptr;
+    b->cpu_stats_reference = nullptr;
+    return BenchmarkConstants::GAINSTATS_GAIN;
+}
+
+// cuda/bench_iir.cu:205-228
+void ref_butterworth(float normalized_frequency, float* out5) {
+    static IIRBenchmark* inst = new IIRBenchmark(1, 1);
+    IIRCoefficients c = inst->calculateButterworthCoefficients(normalized_frequency);
+    out5[0] = c.b0; out5[1] = c.b1; out5[2] = c.b2; out5[3] = c.a1; out5[4] = c.a2;
+}
+
+// cuda/bench_iir.cu:176-203; coeffs5 = b0, b1, b2, a1, a2; state [T][2] in/out.
+void ref_iir_reference(const float* x, float* y, const float* coeffs5, float* state, int T, int B) {
+    static IIRBenchmark* inst = new IIRBenchmark(1, 1);
+    IIRCoefficients c{coeffs5[0], coeffs5[1], coeffs5[2], coeffs5[3], coeffs5[4]};
+    inst->iirFilterCPUReference(x, y, T * B, &c, state, T, B);
 }
 
 // cuda/bench_utils.cu:358-414; out8 = {mean, median, std, min, max, p95, p99, count}

@@ -42,3 +42,9 @@ def reflib():
 def golden():
     import numpy as np
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "conv_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def strip_golden():
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "strip_golden.npz"))

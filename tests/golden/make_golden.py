@@ -55,6 +55,35 @@ def main():
     path = os.path.join(HERE, "conv_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
+    strip_golden(ref)
+
+
+def strip_golden(ref):
+    """Channel-strip stages from the reference's own CPU members: cuda/bench_gain.cu:82-93,
+    bench_gainstats.cu:116-143, bench_iir.cu:176-228."""
+    out = {}
+    T, B = 6, 96
+    x = ref.generate_input(T * B, 42).reshape(T, B)
+    out["shape"] = np.array([T, B], dtype=np.int32)
+    out["x"] = x
+    y, g = ref.gain(x)
+    out["gain_value"], out["gain_y"] = np.float32(g), y
+    y, st, g = ref.gainstats(x)
+    out["gainstats_value"], out["gainstats_y"], out["gainstats_stats"] = np.float32(g), y, st
+    coef = ref.butterworth(0.25)
+    out["butterworth_025"] = coef
+    out["butterworth_010"] = ref.butterworth(0.10)
+    state = np.zeros((T, 2), dtype=np.float32)
+    out["iir_y"] = np.stack([ref.iir(x, coef, state) for _ in range(3)])  # same input, state carried (bench_iir.cu:42-43)
+    out["iir_state"] = state
+    # the reference's default size, hashes only
+    xd = ref.generate_input(128 * 512, 42).reshape(128, 512)
+    sd = np.zeros((128, 2), dtype=np.float32)
+    out["defaults_hashes"] = np.array([fnv1a64(ref.gain(xd)[0]), fnv1a64(ref.gainstats(xd)[1]), fnv1a64(ref.iir(xd, coef, sd)),
+                                       fnv1a64(sd)])
+    path = os.path.join(HERE, "strip_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

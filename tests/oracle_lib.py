@@ -55,6 +55,12 @@ class Oracle:
             getattr(L, name).argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
             getattr(L, name).restype = C.c_double
         L.oracle_hardware_threads.restype = C.c_int
+        L.oracle_gain.argtypes = [_f32p, _f32p, C.c_size_t, C.c_float]
+        L.oracle_gainstats.argtypes = [_f32p, _f32p, _f32p, C.c_size_t, C.c_size_t, C.c_float]
+        L.oracle_butterworth.argtypes = [C.c_float, _f32p]
+        L.oracle_iir.argtypes = [_f32p, _f32p, _f32p, C.c_int, _f32p, C.c_int, C.c_int]
+        L.oracle_strip.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_uint, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                   _f32p, _f32p]
 
     # -- generators --------------------------------------------------------------------------
     def generate_input(self, count, seed=42):
@@ -138,6 +144,51 @@ class Oracle:
     def hardware_threads(self):
         return self.lib.oracle_hardware_threads()
 
+    # -- channel strip: track-major [T][B] arrays ------------------------------
+    def gain(self, x, gain):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.empty_like(x)
+        self.lib.oracle_gain(x.ravel(), y.reshape(-1), x.size, gain)
+        return y
+
+    def gainstats(self, x, gain):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T, B = x.shape
+        y = np.empty_like(x)
+        stats = np.empty((T, 2), dtype=np.float32)
+        self.lib.oracle_gainstats(x.ravel(), y.reshape(-1), stats.reshape(-1), T, B, gain)
+        return y, stats
+
+    def butterworth(self, fc=0.25):
+        out = np.empty(5, dtype=np.float32)
+        self.lib.oracle_butterworth(fc, out)
+        return out
+
+    def iir(self, x, coeffs, state):
+        """coeffs [5] (shared) or [T][5]; state [T][2] is updated in place."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T, B = x.shape
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float32)
+        y = np.empty_like(x)
+        self.lib.oracle_iir(x.ravel(), y.reshape(-1), coeffs.reshape(-1), 0 if coeffs.ndim == 1 else 5,
+                            state.reshape(-1), T, B)
+        return y
+
+    def strip(self, x, ops, gain=1.0, gains=None, coeffs=None, state=None):
+        """Engine strip order: stats(input) -> gain -> biquad.  Returns (y, stats); state updated in place."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T, B = x.shape
+        y = np.empty_like(x)
+        stats = np.zeros((T, 2), dtype=np.float32)
+        if state is None:
+            state = np.zeros((T, 2), dtype=np.float32)
+        g = None if gains is None else np.ascontiguousarray(gains, dtype=np.float32)
+        c = None if coeffs is None else np.ascontiguousarray(coeffs, dtype=np.float32)
+        self.lib.oracle_strip(x.ravel(), y.reshape(-1), T, B, ops, gain,
+                              None if g is None else g.ctypes.data, None if c is None else c.ctypes.data,
+                              0 if (c is None or c.ndim == 1) else 5, state.reshape(-1), stats.reshape(-1))
+        return y, stats
+
 
 class RefLib:
     """The reference's own compiled CPU functions (oracle/_ref). `available()` is False when the
@@ -161,6 +212,41 @@ class RefLib:
             getattr(L, name).argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
             getattr(L, name).restype = C.c_double
         L.ref_hardware_threads.restype = C.c_int
+        if hasattr(L, "ref_gain_reference"):
+            L.ref_gain_reference.argtypes = [_f32p, _f32p, C.c_size_t, C.c_size_t]
+            L.ref_gain_reference.restype = C.c_float
+            L.ref_gainstats_reference.argtypes = [_f32p, _f32p, _f32p, C.c_size_t, C.c_size_t]
+            L.ref_gainstats_reference.restype = C.c_float
+            L.ref_butterworth.argtypes = [C.c_float, _f32p]
+            L.ref_iir_reference.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int]
+
+    def gain(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T, B = x.shape
+        y = np.empty_like(x)
+        g = self.lib.ref_gain_reference(x.ravel(), y.reshape(-1), B, T)
+        return y, g
+
+    def gainstats(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T, B = x.shape
+        y = np.empty_like(x)
+        stats = np.empty((T, 2), dtype=np.float32)
+        g = self.lib.ref_gainstats_reference(x.ravel(), y.reshape(-1), stats.reshape(-1), B, T)
+        return y, stats, g
+
+    def butterworth(self, fc=0.25):
+        out = np.empty(5, dtype=np.float32)
+        self.lib.ref_butterworth(fc, out)
+        return out
+
+    def iir(self, x, coeffs5, state):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T, B = x.shape
+        y = np.empty_like(x)
+        self.lib.ref_iir_reference(x.ravel(), y.reshape(-1), np.ascontiguousarray(coeffs5, dtype=np.float32),
+                                   state.reshape(-1), T, B)
+        return y
 
     def generate_input(self, count, seed=42):
         buf = np.empty(count, dtype=np.float32)

@@ -46,6 +46,20 @@ def test_no_gpu_fails_loudly():
     assert "no CPU fallback" in str(ei.value)
 
 
+def test_strip_call_without_gpu_fails_loudly_and_checks_arguments():
+    """b200conv_strip_process: argument errors first (no device needed), then NO_DEVICE — never a CPU path."""
+    with pytest.raises(g.B200ConvError) as ei:
+        g.strip_process(64, 64, 4, 32, 0)  # no operation selected
+    assert ei.value.code == g.engine.ERR_INVALID
+    with pytest.raises(g.B200ConvError) as ei:
+        g.strip_process(64, 64, 4, 32, g.STRIP_BIQUAD)  # biquad without coefficients / state
+    assert ei.value.code == g.engine.ERR_INVALID
+    if not _have_gpu():
+        with pytest.raises(g.B200ConvError) as ei:
+            g.strip_process(64, 64, 4, 32, g.STRIP_GAIN, gain=2.0)
+        assert ei.value.code == g.engine.ERR_NO_DEVICE
+
+
 def test_plan_rejects_bad_sizes():
     with pytest.raises(g.B200ConvError):
         g.plan(4, 48, 100, g.ALGO_DIRECT)  # direct: 32..256 or multiples of 512

@@ -143,3 +143,64 @@ def test_fft_oracle_equals_reference_build_and_is_coarse(oracle, reflib):
 def test_statistics_equal_reference_build(oracle, reflib):
     lat = (oracle.generate_input(257, 11) * 0.3 + 1.0).astype(np.float32)
     assert oracle.statistics(lat) == reflib.statistics(lat)
+
+
+# ---- channel-strip stages ---------------------------------------------------
+def test_strip_oracles_match_golden(oracle, strip_golden):
+    """Fixture generated from the reference's own compiled members (tests/golden/make_golden.py)."""
+    gd = strip_golden
+    x = gd["x"]
+    T, B = (int(v) for v in gd["shape"])
+    assert np.array_equal(x, oracle.generate_input(T * B).reshape(T, B))
+    assert float(gd["gain_value"]) == 2.0 and float(gd["gainstats_value"]) == 0.5  # benchmark_constants.cuh:6-7
+    assert np.array_equal(oracle.gain(x, 2.0), gd["gain_y"])
+    y, st = oracle.gainstats(x, 0.5)
+    assert np.array_equal(y, gd["gainstats_y"]) and np.array_equal(st, gd["gainstats_stats"])
+    assert np.array_equal(oracle.butterworth(0.25), gd["butterworth_025"])
+    assert np.array_equal(oracle.butterworth(0.10), gd["butterworth_010"])
+    state = np.zeros((T, 2), dtype=np.float32)
+    for blk in range(3):
+        assert np.array_equal(oracle.iir(x, gd["butterworth_025"], state), gd["iir_y"][blk]), blk
+    assert np.array_equal(state, gd["iir_state"])
+    xd = oracle.generate_input(128 * 512).reshape(128, 512)
+    sd = np.zeros((128, 2), dtype=np.float32)
+    hashes = [fnv1a64(oracle.gain(xd, 2.0)), fnv1a64(oracle.gainstats(xd, 0.5)[1]),
+              fnv1a64(oracle.iir(xd, oracle.butterworth(0.25), sd)), fnv1a64(sd)]
+    assert hashes == list(gd["defaults_hashes"])
+
+
+def test_strip_oracle_composite_is_the_chain_of_stages(oracle):
+    """oracle_strip = stats(input) -> gain -> biquad, per-track parameters, ragged sizes."""
+    T, B = 5, 37
+    x = oracle.generate_input(T * B, 9).reshape(T, B)
+    gains = np.linspace(0.5, 2.0, T).astype(np.float32)
+    coef = np.stack([oracle.butterworth(0.1 + 0.05 * t) for t in range(T)])
+    st = np.zeros((T, 2), np.float32)
+    y, stats = oracle.strip(x, 7, gains=gains, coeffs=coef, state=st)
+    st2 = np.zeros((T, 2), np.float32)
+    for t in range(T):
+        _, s_t = oracle.gainstats(x[t:t + 1], 1.0)
+        g_t = oracle.gain(x[t:t + 1], float(gains[t]))
+        y_t = oracle.iir(g_t, coef[t], st2[t:t + 1])
+        assert np.array_equal(y[t], y_t[0]) and np.array_equal(stats[t], s_t[0])
+    assert np.array_equal(st, st2)
+    # stats only: pass-through output
+    y, stats = oracle.strip(x, 1)
+    assert np.array_equal(y, x) and np.allclose(stats[:, 0], x.mean(1), atol=1e-6) and np.array_equal(stats[:, 1], x.max(1))
+
+
+@pytest.mark.parametrize("T,B", [(1, 512), (9, 33), (128, 512)])
+def test_strip_restatement_equals_reference_build(oracle, reflib, T, B):
+    x = oracle.generate_input(T * B, 21).reshape(T, B)
+    y, g = reflib.gain(x)
+    assert np.array_equal(y, oracle.gain(x, g))
+    y, st, g = reflib.gainstats(x)
+    y2, st2 = oracle.gainstats(x, g)
+    assert np.array_equal(y, y2) and np.array_equal(st, st2)
+    for fc in (0.05, 0.25, 0.45):
+        coef = reflib.butterworth(fc)
+        assert np.array_equal(coef, oracle.butterworth(fc))
+        s1, s2 = np.zeros((T, 2), np.float32), np.zeros((T, 2), np.float32)
+        for _ in range(2):
+            assert np.array_equal(reflib.iir(x, coef, s1), oracle.iir(x, coef, s2))
+        assert np.array_equal(s1, s2)

@@ -204,3 +204,64 @@ def test_cli_end_to_end_json_and_csv(tmp_path):
     assert lines[0] == "benchmark,fs,bufferSize,nTracks,nRuns,min_ms,max_ms,avg_ms,p50_ms,p95_ms,p99_ms,threshold_ms,meets_deadline"
     assert lines[1].startswith("Conv1D_accel,48000,256,64,10,") and lines[1].endswith(",true")
     assert os.path.exists("/tmp/Conv1D_accel_latencies.txt")
+
+
+# ---------------------------------------------------------------- channel-strip plugins ------
+def test_cli_lists_the_channel_strip_plugins():
+    names = run_cli("--list").stdout.split("\n")
+    for n in ("gain", "GainStats", "IIRFilter"):  # registry names of the reference, cuda/main.cu:85-93
+        assert n in names
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,B", [(128, 512), (1, 32), (37, 1000)])
+def test_gain_and_gainstats_plugin_lifecycle(oracle, T, B):
+    with plugin.Plugin("gain", 0, B, T) as p:
+        p.setup()
+        x = p.host_input()
+        assert np.array_equal(x, oracle.generate_input(T * B).reshape(T, B))  # generateTestData(42)
+        wall, gpu = p.run(5, warmup=2)
+        assert (gpu > 0).all()
+        v = p.validate()
+        assert v["status"] == 0 and v["max_error"] == 0.0, v
+        assert p.strip_bit_exact()
+        assert np.array_equal(p.host_output(), oracle.gain(x, 2.0))
+        assert np.array_equal(p.cpu_reference(), oracle.gain(x, 2.0))
+    with plugin.Plugin("GainStats", 0, B, T) as p:
+        p.setup()
+        x = p.host_input()
+        p.run(3, warmup=1)
+        v = p.validate()
+        assert v["status"] == 0 and p.strip_bit_exact(), v
+        y_ref, s_ref = oracle.gainstats(x, 0.5)
+        assert np.array_equal(p.host_output(), y_ref)
+        assert np.array_equal(p.strip_stats(), s_ref) and np.array_equal(p.strip_stats(cpu=True), s_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,B,iters", [(128, 512, 1), (128, 512, 7), (5, 96, 4)])
+def test_iir_plugin_lifecycle_state_carried_across_iterations(oracle, T, B, iters):
+    with plugin.Plugin("IIRFilter", 0, B, T) as p:
+        p.setup()
+        coef = p.strip_coefficients()
+        assert np.array_equal(coef, oracle.butterworth(0.25))
+        x = p.host_input()
+        for _ in range(iters):
+            p.iterate()
+        v = p.validate()
+        assert v["status"] == 0 and p.strip_bit_exact(), v
+        st = np.zeros((T, 2), np.float32)
+        for _ in range(iters):  # the filter state persists on the device (cuda/bench_iir.cu:42-43)
+            ref = oracle.iir(x, coef, st)
+        assert np.array_equal(p.host_output(), ref)
+        assert np.array_equal(p.strip_state(), st) and np.array_equal(p.strip_state(cpu=True), st)
+
+
+@pytest.mark.gpu
+def test_cli_runs_the_channel_strip_plugins():
+    for name in ("gain", "GainStats", "IIRFilter"):
+        r = run_cli("--benchmark", name, "--nTracks", "256", "--nRuns", "10", "--json")
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert f"Validation passed for {name}" in r.stdout and "bit-identical to the CPU loop" in r.stdout
+        js = json.loads(r.stdout[r.stdout.index("{\n"):r.stdout.rindex("}") + 1])
+        assert js["benchmark"] == name and js["deadline"]["meets_deadline"] is True
