@@ -495,6 +495,91 @@ def run_latency(args, rank, world, local_rank, dist):
             "ir_taps": L, "fs": FS, "path": "host buffers -> results on host (e2e)", "collective": bus.kind}
 
 
+def run_strip(args, local_rank):
+    """Channel-strip measurements, one GPU: (1) the three plugin configurations alone on
+    the reference's default shape 128 x 512 and on 1024 x 512, device time per call by CUDA events with the
+    L2 flushed, beside the reference's CPU loop on the host cores (one thread, as the reference runs it);
+    (2) what attaching the full strip costs per block on C2 and C3."""
+    import torch
+    import gpuaudiobench_b200 as g
+    from gpuaudiobench_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    oracle = Oracle()
+    dev = torch.device("cuda", local_rank)
+    flush = L2Flush(dev)
+    K = min(args.steps, 100)
+    rows = []
+    coef = synth.butterworth_lowpass(0.25)
+    d_coef = torch.from_numpy(coef).to(dev)
+    for T, B in ((128, 512), (1024, 512)):
+        x = synth.make_input(T * B, seed=42).reshape(T, B)
+        d_x = torch.from_numpy(x).to(dev)
+        d_y = torch.empty_like(d_x)
+        d_state = torch.zeros(T, 2, device=dev)
+        d_stats = torch.zeros(T, 2, device=dev)
+        for name, ops, gain in (("gain", g.STRIP_GAIN, 2.0), ("GainStats", g.STRIP_GAIN | g.STRIP_STATS, 0.5),
+                                ("IIRFilter", g.STRIP_BIQUAD, 1.0)):
+            def call():
+                g.strip_process(d_x.data_ptr(), d_y.data_ptr(), T, B, ops, gain=gain, d_biquad=d_coef.data_ptr(),
+                                d_state=d_state.data_ptr(), d_stats=d_stats.data_ptr())
+            for _ in range(5):
+                call()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            for k in range(K):
+                flush(k)
+                ev[k][0].record()
+                call()
+                ev[k][1].record()
+            torch.cuda.synchronize(dev)
+            ms = np.sort(np.array([a.elapsed_time(b) for a, b in ev]))
+            t0 = time.perf_counter()
+            reps = 0
+            st = np.zeros((T, 2), np.float32)
+            while time.perf_counter() - t0 < 0.3:
+                if name == "gain":
+                    oracle.gain(x, 2.0)
+                elif name == "GainStats":
+                    oracle.gainstats(x, 0.5)
+                else:
+                    oracle.iir(x, coef, st)
+                reps += 1
+            cpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+            rows.append({"plugin": name, "tracks": T, "block": B, "gpu_ms_p50": pct(ms, 0.5), "gpu_ms_p99": pct(ms, 0.99),
+                         "bytes_moved": 2 * T * B * 4, "gb_per_s": 2 * T * B * 4 / (pct(ms, 0.5) * 1e-3) / 1e9,
+                         "cpu_ms_1_thread": cpu_ms, "chain_bound_us": (B * 12 / 1.9e3) if name == "IIRFilter" else None})
+    fused = {}
+    for wl in ("c2", "c3"):
+        algo_name, T, B, L, layout_name, label = WORKLOADS[wl]
+        algo = g.ALGO_DIRECT if algo_name == "direct" else g.ALGO_UPOLS
+        layout = g.OUT_SAMPLE_MAJOR if layout_name == "sample_major" else g.OUT_TRACK_MAJOR
+        eng = g.ConvEngine(T, B, L, algo, layout, device=local_rank)
+        eng.load_ir(synth.make_ir(T, L, 0, T))
+        d_x = torch.from_numpy(synth.make_input(T * B, seed=1).reshape(T, B)).to(dev)
+        d_y = torch.zeros((B, T) if layout == g.OUT_SAMPLE_MAJOR else (T, B), device=dev)
+        d_mix = torch.zeros(2, B, device=dev)
+        res = {}
+        for tag in ("plain", "strip"):
+            if tag == "strip":
+                eng.set_strip(g.STRIP_STATS | g.STRIP_GAIN | g.STRIP_BIQUAD, gain=0.5, biquad=coef)
+            for k in range(10):
+                eng.process(d_x.data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), flags=g.PEEK)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            for k in range(K):
+                flush(k)
+                ev[k][0].record()
+                eng.process(d_x.data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), flags=g.PEEK)
+                ev[k][1].record()
+            torch.cuda.synchronize(dev)
+            res[tag + "_ms"] = float(np.median([a.elapsed_time(b) for a, b in ev]))
+        res["strip_cost_us"] = (res["strip_ms"] - res["plain_ms"]) * 1e3
+        fused[wl] = res
+        eng.close()
+        del d_x, d_y
+    return {"strip": rows, "engine_with_full_strip": fused, "l2": flush.description,
+            "note": "the strip is a dependent chain of B steps per track: ~12 cycles per sample for the biquad"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -504,6 +589,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads in the default line")
     ap.add_argument("--sweep", action="store_true", help="buffer-size sweep (BASELINE config 5): one JSON line with a table")
+    ap.add_argument("--strip", action="store_true", help="channel-strip kernels alone and attached to the engines")
     ap.add_argument("--latency", type=int, default=0, metavar="N", help="latency run: N blocks back-to-back and N periodic at B/fs")
     args = ap.parse_args()
 
@@ -526,6 +612,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.strip:
+        if rank == 0:
+            print(json.dumps(run_strip(args, local_rank)), flush=True)
+        return 0
     if args.latency > 0:
         res = run_latency(args, rank, world, local_rank, dist)
         if rank == 0:

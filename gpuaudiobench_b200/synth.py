@@ -41,3 +41,15 @@ def make_ir(total_tracks, ir_len, t_begin=0, t_end=None):
             sinc = np.where(tt == 0, np.float32(1.0), np.sin(arg, dtype=np.float32) / arg).astype(np.float32)
         out[i] = window * sinc / np.float32(ir_len)
     return out
+
+
+def butterworth_lowpass(fc):
+    """2nd-order Butterworth low-pass biquad (b0, b1, b2, a1, a2; a0 = 1) at fc cycles/sample — the RBJ
+    cookbook formula the reference's IIR plugin uses (cuda/bench_iir.cu:205-228), evaluated in float32."""
+    f = np.float32
+    omega = f(2.0) * f(np.pi) * f(fc)
+    c, s_ = f(np.cos(omega)), f(np.sin(omega))
+    alpha = s_ / (f(2.0) * f(0.707))
+    a0 = f(1.0) + alpha
+    b1 = f(1.0) - c
+    return np.array([b1 / f(2.0) / a0, b1 / a0, b1 / f(2.0) / a0, f(-2.0) * c / a0, (f(1.0) - alpha) / a0], dtype=np.float32)
