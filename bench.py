@@ -63,7 +63,7 @@ class L2Flush:
         import torch
         self.mode = mode or os.environ.get("B200CONV_BENCH_FLUSH", "write+read")
         self.w = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-        self.r = torch.zeros(64 << 20, dtype=torch.int32, device=dev) if self.mode == "write+read" else None
+        self.r = torch.zeros(64 << 20, dtype=torch.float32, device=dev) if self.mode == "write+read" else None  # 256 MiB
         self.sink = None
         self.description = self.DESCRIPTION if self.r is not None else \
             "flushed between steps (256 MiB write outside the event brackets)"

@@ -243,6 +243,28 @@ int b200conv_group_reset(b200conv_group* g) {
     return for_each_member(g, [&](Member& m) { return b200conv_reset(m.engine); });
 }
 
+// channel strip on every member: per-track arrays are sliced at the member's first track
+int b200conv_group_set_strip(b200conv_group* g, const b200conv_strip* strip) {
+    if (!g) return gfail(B200CONV_ERR_INVALID, "b200conv_group_set_strip: null group");
+    return for_each_member(g, [&](Member& m) {
+        if (!strip) return b200conv_set_strip(m.engine, nullptr);
+        b200conv_strip part = *strip;
+        if (part.gains) part.gains += m.t0;
+        if (part.biquad && !(part.ops & B200CONV_STRIP_SHARED_COEFFS)) part.biquad += static_cast<size_t>(5) * m.t0;
+        return b200conv_set_strip(m.engine, &part);
+    });
+}
+
+int b200conv_group_strip_state(b200conv_group* g, float* host_state, int set) {
+    if (!g || !host_state) return gfail(B200CONV_ERR_INVALID, "b200conv_group_strip_state: null argument");
+    return for_each_member(g, [&](Member& m) { return b200conv_strip_state(m.engine, host_state + static_cast<size_t>(2) * m.t0, set); });
+}
+
+int b200conv_group_strip_stats(b200conv_group* g, float* host_stats) {
+    if (!g || !host_stats) return gfail(B200CONV_ERR_INVALID, "b200conv_group_strip_stats: null argument");
+    return for_each_member(g, [&](Member& m) { return b200conv_strip_stats(m.engine, host_stats + static_cast<size_t>(2) * m.t0); });
+}
+
 int b200conv_group_process_host(b200conv_group* g, const float* h_in, float* h_out, float* h_mix, uint32_t flags) {
     if (!g || !h_in) return gfail(B200CONV_ERR_INVALID, "b200conv_group_process_host: null argument");
     {

@@ -90,6 +90,9 @@ def load_library():
     L.b200conv_group_prime_history.argtypes = [C.c_void_p, C.c_void_p]
     L.b200conv_group_reset.argtypes = [C.c_void_p]
     L.b200conv_group_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.b200conv_group_set_strip.argtypes = [C.c_void_p, C.POINTER(Strip)]
+    L.b200conv_group_strip_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.b200conv_group_strip_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.b200conv_group_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -180,6 +183,30 @@ class ConvGroup:
         else:
             h = np.ascontiguousarray(hist, dtype=np.float32)
             self._check(self.lib.b200conv_group_prime_history(self.handle, _host_ptr(h)))
+
+    def set_strip(self, ops=0, gain=1.0, gains=None, biquad=None):
+        """Channel strip on every member engine (gains [Tg], biquad [5] shared or [Tg][5]); ops == 0 removes it."""
+        if not ops:
+            self._check(self.lib.b200conv_group_set_strip(self.handle, None))
+            return
+        g = None if gains is None else np.ascontiguousarray(gains, dtype=np.float32)
+        c = None if biquad is None else np.ascontiguousarray(biquad, dtype=np.float32)
+        assert g is None or g.size == self.Tg
+        assert c is None or c.size in (5, 5 * self.Tg)
+        if c is not None and c.size == 5:
+            ops |= STRIP_SHARED_COEFFS
+        st = Strip(ops, gain, None if g is None else g.ctypes.data, None if c is None else c.ctypes.data)
+        self._check(self.lib.b200conv_group_set_strip(self.handle, C.byref(st)))
+
+    def strip_state(self):
+        st = np.zeros((self.Tg, 2), dtype=np.float32)
+        self._check(self.lib.b200conv_group_strip_state(self.handle, _host_ptr(st), 0))
+        return st
+
+    def strip_stats(self):
+        st = np.zeros((self.Tg, 2), dtype=np.float32)
+        self._check(self.lib.b200conv_group_strip_stats(self.handle, _host_ptr(st)))
+        return st
 
     def process_host(self, x, flags=0, want_mix=True):
         x = np.ascontiguousarray(x, dtype=np.float32)

@@ -220,6 +220,11 @@ int b200conv_group_load_ir(b200conv_group* g, const float* host_ir);
 int b200conv_group_prime_history(b200conv_group* g, const float* host_hist);
 int b200conv_group_reset(b200conv_group* g);
 int b200conv_group_process_host(b200conv_group* g, const float* h_in, float* h_out, float* h_mix, uint32_t flags);
+/* channel strip on every GPU's engine: strip->gains float [Tg], strip->biquad float [Tg][5] (or [5] shared);
+ * host_state / host_stats float [Tg][2] (see b200conv_set_strip / _strip_state / _strip_stats) */
+int b200conv_group_set_strip(b200conv_group* g, const b200conv_strip* strip);
+int b200conv_group_strip_state(b200conv_group* g, float* host_state, int set);
+int b200conv_group_strip_stats(b200conv_group* g, float* host_stats);
 const char* b200conv_group_last_error(void);
 
 /* Launch plan the engine would use for `cfg` on a device with `sm_count` SMs; needs no GPU.

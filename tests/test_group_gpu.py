@@ -50,6 +50,32 @@ def test_plugin_on_two_gpus_validates_against_r1_and_r2():
         plugin.set_ngpus(1)
 
 
+@pytest.mark.parametrize("n_gpus", [1, 2])
+@pytest.mark.parametrize("algo,layout", [(g.ALGO_DIRECT, g.OUT_TRACK_MAJOR), (g.ALGO_UPOLS, g.OUT_SAMPLE_MAJOR)])
+def test_group_channel_strip_is_sliced_per_member(oracle, n_gpus, algo, layout):
+    """b200conv_group_set_strip: per-track gains / biquads reach the right member; outputs, statistics and
+    filter state are bit-identical to the oracle's strip of the plain group's output (1 GPU runs everywhere)."""
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    Tg, B, L, M = 13, 128, 500, 3
+    xs = oracle.generate_input(M * Tg * B, 17).reshape(M, Tg, B)
+    h = oracle.generate_ir(Tg, L, "accel")
+    coef = np.stack([oracle.butterworth(0.05 + 0.03 * t) for t in range(Tg)])
+    gains = np.linspace(0.5, 1.5, Tg).astype(np.float32)
+    with g.ConvGroup(Tg, B, L, algo, n_gpus, layout) as plain, g.ConvGroup(Tg, B, L, algo, n_gpus, layout) as strip:
+        plain.load_ir(h)
+        strip.load_ir(h)
+        strip.set_strip(g.STRIP_STATS | g.STRIP_GAIN | g.STRIP_BIQUAD, gains=gains, biquad=coef)
+        state = np.zeros((Tg, 2), np.float32)
+        for m in range(M):
+            y0, _ = plain.process_host(xs[m])
+            y1, _ = strip.process_host(xs[m])
+            tm = np.ascontiguousarray(y0.T if layout == g.OUT_SAMPLE_MAJOR else y0)
+            ref, stats_ref = oracle.strip(tm, 7, gains=gains, coeffs=coef, state=state)
+            assert np.array_equal(y1.T if layout == g.OUT_SAMPLE_MAJOR else y1, ref), f"block {m}"
+            assert np.array_equal(strip.strip_stats(), stats_ref) and np.array_equal(strip.strip_state(), state)
+
+
 def test_group_rejects_more_gpus_than_visible():
     with pytest.raises(g.B200ConvError) as ei:
         g.ConvGroup(64, 512, 1024, g.ALGO_DIRECT, torch.cuda.device_count() + 1)
