@@ -18,6 +18,8 @@
 // arguments) so the FFT phases carry no dependent table loads.
 #include "upols.cuh"
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200conv {
@@ -310,16 +312,20 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 // Each CTA leaves its partial spectrum in Ypart and takes a ticket on the track's counter; the
 // last one adds the S partials in split order, runs the inverse transform and writes the output.
 // ---------------------------------------------------------------------------------------------
-#ifndef B200CONV_FUSED_UNROLL
-#define B200CONV_FUSED_UNROLL 2
-#endif
-constexpr int kFusedUnroll = B200CONV_FUSED_UNROLL;
+// Occupancy variants <UNROLL, MINCTAS> with UNROLL * MINCTAS = 16, i.e. the same bytes in flight per SM at
+// full residency (256 threads x UNROLL x 2 loads x 16 B x MINCTAS = 131 KB).  Measured (C3: 1024 CTAs,
+// C4 shard: 512 CTAs; profiles/experiments/upols_variant_bench.py): a grid that needs ~1.7 waves beats one
+// that is exactly resident, because every CTA starts and ends with a transform phase that moves no HBM
+// bytes and in a single wave those phases line up across the whole GPU — C3 <2,8> 171.1 us (1 wave)
+// vs <4,4> 161.9 us (1.73 waves); C4 <2,8> 127.9 us vs <8,2> 125.1 us.  launch_upols_fused picks the
+// variant from the grid size.
 #ifndef B200CONV_FUSED_PREFETCH
 #define B200CONV_FUSED_PREFETCH 8
 #endif
 constexpr int kPrefetchParts = B200CONV_FUSED_PREFETCH;  // partitions pulled into L2 under the forward FFT  // partitions in flight per thread (x2 loads); 32-register budget
 
-__global__ void __launch_bounds__(256, 8) upols_fused_kernel(FusedParams p) {
+template <int kFusedUnroll, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(FusedParams p) {
     extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
     __shared__ int s_last;
     const int M = p.M, half = M >> 1, U = M >> 1, G = 256 / U;
@@ -539,10 +545,32 @@ cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// CTAs per SM (8, 4 or 2) of the fused kernel for a grid of `ctas`: the largest occupancy that still
+// leaves the grid at >= 1.5 waves (see the note above upols_fused_kernel)
+int upols_fused_occupancy(int ctas, int sm_count) {
+    static const int forced = [] {
+        const char* v = std::getenv("B200CONV_UPOLS_OCC");
+        return v ? std::atoi(v) : 0;
+    }();
+    if (forced == 8 || forced == 4 || forced == 2) return forced;
+    int c = 8;
+    while (c > 2 && 2 * ctas < 3 * sm_count * c) c >>= 1;
+    return c;
+}
+
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st) {
     dim3 grid(p.S, p.T);
     const size_t smem = static_cast<size_t>(2) * p.M * sizeof(float2) + 256 * 8 * sizeof(float);
-    upols_fused_kernel<<<grid, 256, smem, st>>>(p);
+    static const int sm_count = [] {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    switch (upols_fused_occupancy(p.S * p.T, sm_count)) {
+        case 8: upols_fused_kernel<2, 8><<<grid, 256, smem, st>>>(p); break;
+        case 4: upols_fused_kernel<4, 4><<<grid, 256, smem, st>>>(p); break;
+        default: upols_fused_kernel<8, 2><<<grid, 256, smem, st>>>(p); break;
+    }
     return cudaGetLastError();
 }
 

@@ -12,10 +12,11 @@ e.load_ir(synth.make_ir(T, L))
 x = torch.from_numpy(synth.make_input(8 * T * B).reshape(8, T, B)).cuda()
 y = torch.zeros(T, B, device="cuda"); mix = torch.zeros(2, B, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+flush_r = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")  # read pass: no dirty lines left for the step
 for k in range(40): e.process(x[k % 8].data_ptr(), y.data_ptr(), mix.data_ptr())
 torch.cuda.synchronize(); e.set_profiling(True)
 for k in range(100):
-    flush.fill_(k & 255); e.process(x[k % 8].data_ptr(), y.data_ptr(), mix.data_ptr())
+    flush.fill_(k & 255); _ = flush_r.sum(); e.process(x[k % 8].data_ptr(), y.data_ptr(), mix.data_ptr())
 torch.cuda.synchronize(); q = e.query()
 n = q["stage_count"]; ms = [m / q["stage_calls"] for m in q["stage_ms"][:n]]
 d = q["dominant_stage"]
