@@ -177,16 +177,25 @@ int plan_upols(b200conv_engine* e) {
     u.logM = ilog2(B);
     u.P = (e->L + B - 1) / B;
     const int KT = std::max(1, (B / 2) / 256);
-    int S = env_int("B200CONV_UPOLS_SPLIT", 0);
-    if (S <= 0) {
-        // splitting the partition range costs a partial-spectrum round trip and a last-CTA pass, so
-        // split only when the tracks alone cannot put ~2 CTAs on every SM (measured: C4 shard, 512
-        // tracks, S=1 138 us vs S=2 149 us)
-        const long long base = static_cast<long long>(e->T) * KT;
-        S = static_cast<int>((2LL * e->sm_count + base - 1) / base);
-    }
-    u.S = std::max(1, std::min({S, u.P, 32}));
     u.fused = (u.M <= kFusedMaxM) && env_int("B200CONV_UPOLS_FUSED", 1) != 0;
+    int S = env_int("B200CONV_UPOLS_SPLIT", 0);
+    int min_parts = 1;
+    if (S <= 0) {
+        const long long base = static_cast<long long>(e->T) * KT;
+        if (u.fused) {
+            // The fused kernel runs 4 CTAs per SM (upols.cu) and is fastest when the grid needs about two
+            // waves: every CTA starts and ends with a transform phase that moves no HBM bytes, and in a
+            // single resident wave those phases line up across the whole GPU.  Measured on the C4 shard
+            // (512 tracks): S = 1 128.3 us, S = 2 124.0 us, S = 3 122.5 us; C3 (1024 tracks): S = 1 160.9 us,
+            // S = 2 161.7 us.  A split costs a partial-spectrum round trip, so keep >= 16 partitions each.
+            S = static_cast<int>((6LL * e->sm_count + base - 1) / base);
+            min_parts = 16;
+        } else {
+            // three-kernel path (M > 512): split only when the tracks alone cannot put ~2 CTAs on every SM
+            S = static_cast<int>((2LL * e->sm_count + base - 1) / base);
+        }
+    }
+    u.S = std::max(1, std::min({S, std::max(1, u.P / min_parts), 32}));
     return B200CONV_OK;
 }
 

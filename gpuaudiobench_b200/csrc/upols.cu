@@ -317,8 +317,9 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 // C4 shard: 512 CTAs; profiles/experiments/upols_variant_bench.py): a grid that needs ~1.7 waves beats one
 // that is exactly resident, because every CTA starts and ends with a transform phase that moves no HBM
 // bytes and in a single wave those phases line up across the whole GPU — C3 <2,8> 171.1 us (1 wave)
-// vs <4,4> 161.9 us (1.73 waves); C4 <2,8> 127.9 us vs <8,2> 125.1 us.  launch_upols_fused picks the
-// variant from the grid size.
+// vs <4,4> 161.9 us (1.73 waves); C4 <2,8> 127.9 us vs <8,2> 125.1 us vs <4,4> with the partition range
+// split in 2 / 3 (1024 / 1536 CTAs) 124.0 / 122.5 us.  The product uses <4,4> and the planner
+// (engine.cu plan_upols) sizes the split for about two waves.
 #ifndef B200CONV_FUSED_PREFETCH
 #define B200CONV_FUSED_PREFETCH 8
 #endif
@@ -545,28 +546,20 @@ cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// CTAs per SM (8, 4 or 2) of the fused kernel for a grid of `ctas`: the largest occupancy that still
-// leaves the grid at >= 1.5 waves (see the note above upols_fused_kernel)
-int upols_fused_occupancy(int ctas, int sm_count) {
+// CTAs per SM of the fused kernel: <4,4> measured best at every grid size tried (C3 with 1024 and 2048
+// CTAs, C4 shard with 512, 1024 and 1536); the other two instantiations stay selectable for experiments.
+int upols_fused_occupancy() {
     static const int forced = [] {
         const char* v = std::getenv("B200CONV_UPOLS_OCC");
         return v ? std::atoi(v) : 0;
     }();
-    if (forced == 8 || forced == 4 || forced == 2) return forced;
-    int c = 8;
-    while (c > 2 && 2 * ctas < 3 * sm_count * c) c >>= 1;
-    return c;
+    return (forced == 8 || forced == 2) ? forced : 4;
 }
 
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st) {
     dim3 grid(p.S, p.T);
     const size_t smem = static_cast<size_t>(2) * p.M * sizeof(float2) + 256 * 8 * sizeof(float);
-    static const int sm_count = [] {
-        int dev = 0, n = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n;
-    }();
-    switch (upols_fused_occupancy(p.S * p.T, sm_count)) {
+    switch (upols_fused_occupancy()) {
         case 8: upols_fused_kernel<2, 8><<<grid, 256, smem, st>>>(p); break;
         case 4: upols_fused_kernel<4, 4><<<grid, 256, smem, st>>>(p); break;
         default: upols_fused_kernel<8, 2><<<grid, 256, smem, st>>>(p); break;
