@@ -67,6 +67,8 @@ class L2Flush:
         self.sink = None
         self.description = self.DESCRIPTION if self.r is not None else \
             "flushed between steps (256 MiB write outside the event brackets)"
+        if self.mode == "none":
+            self.description = "NOT flushed (diagnostic run, B200CONV_BENCH_FLUSH=none): not a valid bench line"
 
         # first use loads the reduction kernel (milliseconds, and not at the same moment on every rank): do it
         # here, not inside the first timed step, where the other ranks would wait for it in the bus all-reduce
@@ -75,6 +77,8 @@ class L2Flush:
         torch.cuda.synchronize(dev)
 
     def __call__(self, k):
+        if self.mode == "none":  # diagnostic only: warm L2 and instruction caches, not a valid bench setting
+            return
         self.w.fill_(k & 0xFF)
         if self.r is not None:
             self.sink = self.r.sum()

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 #ifndef B200CONV_FUSED_PREFETCH
 #define B200CONV_FUSED_PREFETCH 8
 #endif
-constexpr int kPrefetchParts = B200CONV_FUSED_PREFETCH;  // partitions pulled into L2 under the forward FFT  // partitions in flight per thread (x2 loads); 32-register budget
+constexpr int kPrefetchParts = B200CONV_FUSED_PREFETCH;  // partitions pulled into L2 under the forward FFT
 
 template <int kFusedUnroll, int kMinCtas>
 __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(FusedParams p) {
