@@ -379,7 +379,13 @@ def cpu_baseline(name, budget_s, threads=None):
     h = synth.make_ir(T, L, 0, Ts)
     secs = cpu_time_block(lib, algo_name, x, h, L, B, Ts, cores)
     gmacs = Ts * iters_per_track / secs / 1e9
+    # the reference itself runs this loop on ONE thread (bench_conv1d.cu:42-55 calls it from setupBenchmark):
+    # time that too, on a subset sized for about a second (SURVEY §8d asks for both figures)
+    T1 = int(max(1, min(Ts, 1.0 * 0.5e9 / iters_per_track)))
+    secs1 = cpu_time_block(lib, algo_name, x[:T1 * B], h[:T1], L, B, T1, 1)
+    gmacs1 = T1 * iters_per_track / secs1 / 1e9
     return {"value": gmacs, "unit": "GMAC/s", "cores": cores, "kind": kind,
+            "value_1_thread": gmacs1, "sample_1_thread": f"{T1} tracks on one thread, {secs1:.2f} s",
             "sample": f"{'R1 bench_conv1d.cu:188-208' if algo_name == 'direct' else 'R2 bench_conv1d_accel.cu:234-252'} "
                       f"on {Ts} of {T} tracks at full B={B}, L={L}, {cores} threads over contiguous track ranges, "
                       f"{secs:.2f} s; GMAC/s counts T*B*L loop iterations (time-domain equivalent)",
