@@ -229,7 +229,16 @@ int reset_state(b200conv_engine* e) {
 }
 
 // convolution output -> strip, in place, on the launch stream (PDL: waits for the producing kernel)
+StripParams strip_params(b200conv_engine* e, float* d_out, bool commit);
+
 int run_strip(b200conv_engine* e, float* d_out, bool commit, cudaStream_t st) {
+    const StripParams sp = strip_params(e, d_out, commit);
+    CU_TRY(launch_strip(sp, st));
+    e->launches += 1;
+    return B200CONV_OK;
+}
+
+StripParams strip_params(b200conv_engine* e, float* d_out, bool commit) {
     StripParams sp{};
     sp.in = d_out;
     sp.out = d_out;
@@ -246,9 +255,7 @@ int run_strip(b200conv_engine* e, float* d_out, bool commit, cudaStream_t st) {
     sp.state = e->d_strip_state;
     sp.stats = e->d_strip_stats;
     sp.peek = commit ? 0 : 1;
-    CU_TRY(launch_strip(sp, st));
-    e->launches += 1;
-    return B200CONV_OK;
+    return sp;
 }
 
 struct StageTimer {
@@ -639,6 +646,7 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             fp.sample_major = sample_major;
             fp.Tg = e->Tg;
             fp.toff = e->toff;
+            if (e->strip_ops) fp.strip = strip_params(e, d_out, commit);  // strip runs inside the kernel's epilogue
             CU_TRY(launch_upols_fused(fp, st));
             e->launches += 1;
             tm.mark();
@@ -682,7 +690,7 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             CU_TRY(launch_irfft_ols(r, st));
             e->launches += 3;
         }
-        if (e->strip_ops) {
+        if (e->strip_ops && !u.fused) {
             int rc = run_strip(e, d_out, commit, st);
             if (rc) return rc;
         }

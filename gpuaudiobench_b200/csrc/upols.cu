@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 #endif
 constexpr int kPrefetchParts = B200CONV_FUSED_PREFETCH;  // partitions pulled into L2 under the forward FFT
 
-template <int kFusedUnroll, int kMinCtas>
+template <int kFusedUnroll, int kMinCtas, bool kStrip>
 __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(FusedParams p) {
     extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
     __shared__ int s_last;
@@ -489,6 +489,13 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(FusedParams 
     }
     __syncthreads();
     const float2* z = fft_stockham<true>(a, b, M, p.logM, tid, 256, true);
+    if (kStrip) {
+        // channel strip on the track's B output samples while they are still in shared memory: one
+        // thread walks the dependent chain (~12 cycles per sample) while the SM's other CTAs keep streaming
+        __syncthreads();
+        if (tid == 0) strip_track_in_smem(p.strip, t, const_cast<float*>(reinterpret_cast<const float*>(z + half)), M);
+        __syncthreads();
+    }
     for (int copy = 0; copy < 2; ++copy) {
         float* dst = copy ? p.out2 : p.out;
         if (!dst) continue;
@@ -559,10 +566,14 @@ int upols_fused_occupancy() {
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st) {
     dim3 grid(p.S, p.T);
     const size_t smem = static_cast<size_t>(2) * p.M * sizeof(float2) + 256 * 8 * sizeof(float);
+    if (p.strip.ops) {  // strip in the epilogue: one more instantiation of the product configuration
+        upols_fused_kernel<4, 4, true><<<grid, 256, smem, st>>>(p);
+        return cudaGetLastError();
+    }
     switch (upols_fused_occupancy()) {
-        case 8: upols_fused_kernel<2, 8><<<grid, 256, smem, st>>>(p); break;
-        case 4: upols_fused_kernel<4, 4><<<grid, 256, smem, st>>>(p); break;
-        default: upols_fused_kernel<8, 2><<<grid, 256, smem, st>>>(p); break;
+        case 8: upols_fused_kernel<2, 8, false><<<grid, 256, smem, st>>>(p); break;
+        case 4: upols_fused_kernel<4, 4, false><<<grid, 256, smem, st>>>(p); break;
+        default: upols_fused_kernel<8, 2, false><<<grid, 256, smem, st>>>(p); break;
     }
     return cudaGetLastError();
 }

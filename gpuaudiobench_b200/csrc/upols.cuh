@@ -2,6 +2,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+
+#include "strip.cuh"
 #include <stddef.h>
 
 namespace b200conv {
@@ -57,6 +59,8 @@ struct FusedParams {
                           // last CTA of each track posts its PCIe writes while other CTAs still stream)
     int T, P, M, logM, S, slot0, commit;
     int sample_major, Tg, toff;
+    StripParams strip;    // strip.ops != 0: the last CTA of a track runs the channel strip on its B output samples
+                          // in shared memory before writing them (in/out/T/B/layout fields unused here)
 };
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st);
 constexpr int kFusedMaxM = 512;
