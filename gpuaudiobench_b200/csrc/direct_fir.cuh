@@ -9,7 +9,10 @@ namespace b200conv {
 #ifndef B200CONV_FIR_CTAS_PER_SM
 #define B200CONV_FIR_CTAS_PER_SM 2
 #endif
-constexpr int kFirWarps = 8;                              // consumer warps per CTA
+#ifndef B200CONV_FIR_WARPS
+#define B200CONV_FIR_WARPS 8
+#endif
+constexpr int kFirWarps = B200CONV_FIR_WARPS;             // consumer warps per CTA
 constexpr int kFirThreads = (kFirWarps + 1) * 32;         // + one TMA producer warp
 constexpr int kFirMaxStages = 8;                          // mbarrier slots reserved in shared memory
 constexpr int kFirCtasPerSm = B200CONV_FIR_CTAS_PER_SM;   // persistent grid = kFirCtasPerSm * SM count
