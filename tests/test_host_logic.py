@@ -86,6 +86,14 @@ def test_upols_plan_c3_c4():
     assert g.plan(1024, 256, 65536, g.ALGO_UPOLS)["P"] == 256
     p = g.plan(512, 512, 96000, g.ALGO_UPOLS)
     assert p["P"] == 188 and p["M"] == 512 and p["logM"] == 9
+    # fused kernel (B <= 512) at 4 CTAs/SM: the partition split is sized for about two waves (6 x 148 CTAs),
+    # never below 16 partitions per split; C3 has enough tracks on its own
+    assert p["S"] == 2 and g.plan(1024, 256, 65536, g.ALGO_UPOLS)["S"] == 1
+    for T, B, L in [(1, 512, 1024), (4, 256, 1000), (128, 512, 16384), (64, 32, 96000), (8, 64, 700)]:
+        q = g.plan(T, B, L, g.ALGO_UPOLS)
+        assert 1 <= q["S"] <= 32 and (q["S"] == 1 or q["P"] // q["S"] >= 16), (T, B, L, q)
+    # three-kernel path (B >= 1024): split only to put ~2 CTAs on every SM
+    assert g.plan(512, 1024, 96000, g.ALGO_UPOLS)["S"] == 1 and g.plan(16, 2048, 96000, g.ALGO_UPOLS)["S"] >= 2
 
 
 def test_swizzle_is_a_permutation_inside_128_byte_lines():
