@@ -6,8 +6,11 @@ Outputs:  gpuaudiobench_b200/lib/libb200conv.so   (kernels + C ABI, include/b200
           (the reference-shaped plugin host code under gpuaudiobench_b200/host/, when present)
 """
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
@@ -37,6 +40,20 @@ def _run(cmd, verbose):
     subprocess.run(cmd, check=True)
 
 
+def _compile_and_link(srcs, out, extra, link, verbose, shared=True):
+    """One nvcc process per translation unit, in parallel, objects in a scratch directory (nothing but the
+    final .so / binary stays in the tree, so nothing extra travels to the GPU box)."""
+    tmp = tempfile.mkdtemp(prefix="b200conv_build_")
+    try:
+        objs = [os.path.join(tmp, os.path.basename(src) + ".o") for src in srcs]
+        jobs = [[NVCC] + ARCH + COMMON + extra + ["-c", src, "-o", obj] for src, obj in zip(srcs, objs)]
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            list(pool.map(lambda cmd: _run(cmd, verbose), jobs))
+        _run([NVCC] + ARCH + (["-shared"] if shared else []) + ["-o", out] + objs + link, verbose)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def build_engine(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libb200conv.so")
@@ -44,7 +61,7 @@ def build_engine(force=False, verbose=False):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
         os.path.join(ROOT, "include", "b200conv.h")]
     if force or _newer(out, deps):
-        _run([NVCC] + ARCH + COMMON + ["-shared", "-o", out] + srcs, verbose)
+        _compile_and_link(srcs, out, [], [], verbose)
     return out
 
 
@@ -61,7 +78,7 @@ def build_host(force=False, verbose=False):
     inc = ["-I", os.path.join(ROOT, "include"), "-I", HOST]
     link = ["-L", LIBDIR, "-lb200conv", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
     if force or _newer(lib, deps):
-        _run([NVCC] + ARCH + COMMON + inc + ["-shared", "-o", lib] + srcs + link, verbose)
+        _compile_and_link(srcs, lib, inc, link, verbose)
     link_exe = ["-L", LIBDIR, "-lgpubench_b200", "-lb200conv", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib"]
     if force or _newer(exe, deps + [lib, os.path.join(HOST, "main.cu")]):
         _run([NVCC] + ARCH + COMMON + inc + ["-o", exe, os.path.join(HOST, "main.cu")] + link_exe, verbose)
