@@ -13,6 +13,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A hung kernel (e.g. a barrier that never completes) must fail the test, not stall the whole run."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(900))
+
+
 def _build_native():
     """Build whatever is missing (the driver normally calls __graft_entry__.build() first)."""
     import __graft_entry__ as ge
