@@ -162,6 +162,29 @@ def test_engine_strip_equals_strip_of_engine_output(oracle, algo, layout):
         assert np.array_equal(y0, y1)
 
 
+@pytest.mark.parametrize("layout", [g.OUT_TRACK_MAJOR, g.OUT_SAMPLE_MAJOR])
+def test_engine_strip_on_the_three_kernel_upols_path(oracle, layout):
+    """B >= 1024 runs rfft / FDL-MAC / irfft as separate kernels and the strip as its own launch before the
+    bus (the fused kernel's in-epilogue strip covers B <= 512): same bit-exact contract."""
+    T, B, L, M = 6, 1024, 3000, 3
+    ops = g.STRIP_STATS | g.STRIP_GAIN | g.STRIP_BIQUAD
+    xs = oracle.generate_input(M * T * B, seed=23).reshape(M, T, B)
+    h = oracle.generate_ir(T, L, "accel")
+    coef = per_track_biquads(oracle, T)
+    with g.ConvEngine(T, B, L, g.ALGO_UPOLS, layout) as plain, g.ConvEngine(T, B, L, g.ALGO_UPOLS, layout) as strip:
+        plain.load_ir(h)
+        strip.load_ir(h)
+        strip.set_strip(ops, gain=0.25, biquad=coef)
+        st = np.zeros((T, 2), np.float32)
+        for m in range(M):
+            y0, _ = plain.process_host(xs[m])
+            y1, _ = strip.process_host(xs[m])
+            tm = np.ascontiguousarray(y0.T if layout == g.OUT_SAMPLE_MAJOR else y0)
+            ref, stats_ref = oracle.strip(tm, ops, gain=0.25, coeffs=coef, state=st)
+            assert np.array_equal(y1.T if layout == g.OUT_SAMPLE_MAJOR else y1, ref), f"block {m}"
+            assert np.array_equal(strip.strip_stats(), stats_ref) and np.array_equal(strip.strip_state(), st)
+
+
 def test_strip_error_codes():
     d = torch.zeros(4, 32, device="cuda")
     with pytest.raises(g.B200ConvError) as ei:
