@@ -10,8 +10,14 @@ copies inside the timed region (`e2e`).  Workloads (BASELINE.json configs):
     c3          : UPOLS,     1024 tracks x 256-sample blocks  x 65536-tap IR per GPU  [configs[2]]
     c4          : UPOLS,      512 tracks x 512-sample buffers x 96000-tap IR per GPU  [configs[3] / 8]
 Tracks shard across ranks (weak scaling: the per-GPU track count is fixed, IRs and mix gains use
-the global track index); the only collective is the NCCL all-reduce of the stereo mix bus [2][B].
+the global track index); the only collective is the all-reduce of the stereo mix bus [2][B], which the
+engine performs inside its last convolution kernel over NVLink peer memory (NCCL is the fallback).
 The default line also carries the c3 and c4 results under "also" so one run shows both engines.
+Every run — any N — ends with a PARITY leg outside the timed region: the engine is reset, a fresh
+ceil(L/B)+2-block stream is pushed through the very call that was timed, two tracks per rank are
+compared with the reference's own streaming loop (oracle/, checker only), the all-reduced bus with the
+fp64 sum of the all-gathered per-rank partials, and the bus must be bit-identical on all ranks; a
+failure makes the run exit non-zero.
 
 Timing: W warm-up steps, then K timed steps, each bracketed by CUDA events on the launch stream,
 with an L2 flush (256 MiB write, then a 256 MiB read of a second buffer so that the flush's dirty
@@ -130,7 +136,8 @@ class ClockSampler:
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None,
+                "window": "warm-up + timed region (the timed region alone is ~1-10 ms of GPU work: too short to sample)"}
 
 
 def pct(sorted_vals, q):
@@ -140,12 +147,98 @@ def pct(sorted_vals, q):
 # =================================================================================================
 # our arm
 # =================================================================================================
-def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
+def workload_config(name, world):
+    """`config` of the JSON line — the SAME dict in both arms (ours and --impl reference)."""
+    algo_name, T, B, L, layout_name, label = WORKLOADS[name]
+    return {"workload": f"{name}: {label}", "algo": algo_name, "tracks_per_gpu": T, "total_tracks": T * world, "block": B,
+            "ir_taps": L, "fs": FS, "out_layout": layout_name,
+            "l2": "GPU arm: " + L2Flush.DESCRIPTION,
+            "timing": "GPU arm: sum of per-step CUDA-event times on the launch stream, max over ranks; "
+                      "reference arm: steady_clock around the CPU loop"}
+
+
+def snr_db(got, ref):
+    ref64 = np.asarray(ref, dtype=np.float64)
+    err = float(np.sum((np.asarray(got, dtype=np.float64) - ref64) ** 2))
+    return float(10 * np.log10(max(float(np.sum(ref64 ** 2)), 1e-300) / max(err, 1e-300)))
+
+
+def parity_leg(name, eng, bus, step_fn, d_y, d_mix, rank, world, dev, dist, with_oracle=True):
+    """Outside the timed region, in EVERY run: reset, stream ceil(L/B)+2 fresh blocks through the call that
+    was timed, and compare (i) two tracks of this rank with the reference's streaming loop (SURVEY App. A.2;
+    oracle/ used as the checker only), (ii) the all-reduced bus of the last block with the fp64 sum of the
+    all-gathered per-rank partials, (iii) the bus of all ranks bit for bit."""
     import torch
 
     import gpuaudiobench_b200 as g
     from gpuaudiobench_b200 import synth
-    from gpuaudiobench_b200.distributed import BusAllReduce
+    from gpuaudiobench_b200.distributed import default_mix_gains
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    from concurrent.futures import ThreadPoolExecutor
+
+    algo_name, T, B, L, layout_name, _ = WORKLOADS[name]
+    Tg, t0 = T * world, T * rank
+    M = (L + B - 1) // B + 2
+    if not with_oracle:  # sweep points: bus + rank identity only (their oracle parity is tests/test_bench_shapes_gpu.py)
+        M = min(M, 6)
+    gen = torch.Generator(device=dev).manual_seed(9000 + rank)
+    d_x = torch.rand(M, T, B, generator=gen, device=dev) * 2 - 1
+    keep = sorted({0, T - 1})
+    idx = torch.tensor(keep, device=dev)
+    kept = torch.zeros(len(keep), M * B, device=dev)
+    eng.reset()
+    for m in range(M):
+        step_fn(d_x[m].data_ptr())
+        if layout_name == "sample_major":
+            kept[:, m * B:(m + 1) * B] = d_y[:, t0 + idx].T
+        else:
+            kept[:, m * B:(m + 1) * B] = d_y[idx]
+    torch.cuda.synchronize(dev)
+    bus.check()
+    y_last = (d_y[:, t0:t0 + T].T if layout_name == "sample_major" else d_y).double()  # [T][B]
+    snrs, rel = [float("inf")], 0.0
+    if with_oracle:
+        got = kept.cpu().numpy()
+        x_keep = d_x[:, idx, :].cpu().numpy()
+        oracle = Oracle()
+        h_rows = [synth.make_ir(Tg, L, t0 + t, t0 + t + 1)[0] for t in keep]
+        with ThreadPoolExecutor(max_workers=len(keep)) as pool:  # the C loop releases the GIL
+            want = list(pool.map(lambda i: oracle.stream(x_keep[:, i, :].ravel(), h_rows[i]), range(len(keep))))
+        snrs = [snr_db(got[i], want[i]) for i in range(len(keep))]
+        snrs += [snr_db(got[i][-B:], want[i][-B:]) for i in range(len(keep))]  # the last block alone
+        rel = max(float(np.abs(got[i].astype(np.float64) - want[i]).max() / np.abs(want[i]).max()) for i in range(len(keep)))
+    # bus: fp64 partial of this rank from its own last-block outputs, summed over ranks
+    gains = default_mix_gains(Tg, t0, t0 + T).to(dev).double()  # [T][2]
+    partial = gains.T @ y_last                                   # [2][B] fp64
+    bus_got = d_mix.clone()
+    identical = True
+    if world > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM)
+        allbus = [torch.empty_like(bus_got) for _ in range(world)]
+        dist.all_gather(allbus, bus_got)
+        identical = all(bool(torch.equal(allbus[0], b)) for b in allbus)
+    bus_snr = snr_db(bus_got.cpu().numpy(), partial.cpu().numpy())
+    stats = torch.tensor([min(snrs), -rel, bus_snr], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MIN)
+    snr_min, rel_max, bus_snr = float(stats[0]), -float(stats[1]), float(stats[2])
+    min_snr, max_rel = (100.0, 1e-5) if algo_name == "direct" else (90.0, 1e-4)
+    ok = bool(snr_min >= min_snr and rel_max <= max_rel and bus_snr >= 100.0 and identical)
+    del d_x, kept
+    return {"ok": ok, "snr_db_min": snr_min if with_oracle else None, "max_abs_err_rel": rel_max if with_oracle else None, "bus_snr_db": bus_snr, "ranks_bit_identical": identical,
+            "blocks": M, "tracks_checked_per_rank": keep, "ranks": world,
+            "tolerance": f"SNR >= {min_snr:.0f} dB and max|err| <= {max_rel:g} max|y_ref| vs the reference's streaming loop "
+                         "(fp32, bench_conv1d_accel.cu:234-252 on the whole stream); bus >= 100 dB vs the fp64 sum of the "
+                         "all-gathered per-rank partials; bus bit-identical on all ranks"}
+
+
+def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, sweep=False):
+    import torch
+
+    import gpuaudiobench_b200 as g
+    from gpuaudiobench_b200 import synth
+    from gpuaudiobench_b200.distributed import EngineBusGroup
 
     algo_name, T, B, L, layout_name, label = WORKLOADS[name]
     algo = g.ALGO_DIRECT if algo_name == "direct" else g.ALGO_UPOLS
@@ -167,14 +260,19 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     d_y = torch.zeros(out_shape, device=dev)
     d_mix = torch.zeros(2, B, device=dev)
     flush = L2Flush(dev)
-    bus_reduce = BusAllReduce(d_mix, force_nccl=bool(os.environ.get("B200CONV_BUS_NCCL")))
+    # the one collective: with symmetric memory the engine's own kernel does it (no further launch)
+    bus = EngineBusGroup(eng, d_mix, force_nccl=bool(os.environ.get("B200CONV_BUS_NCCL")))
+
+    def step_ptr(ptr):
+        eng.process(ptr, d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
+        bus.reduce()  # no-op when the exchange ran inside the kernel
 
     def step(k):
-        eng.process(d_x[k % NB].data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
-        if world > 1:
-            bus_reduce(stream.cuda_stream)
+        step_ptr(d_x[k % NB].data_ptr())
 
-    # warm-up: also fills the history / delay line with signal
+    clocks = ClockSampler(local_rank)  # nvmlInit takes milliseconds: do it before the ranks line up
+    clocks.__enter__()                 # sampled across warm-up + timed region (the timed region alone is ~ms)
+    # warm-up: at least W steps, and enough to fill the history / delay line with signal
     fill = max(W, min((L + B - 1) // B + 2, 400))
     for k in range(fill):
         step(k)
@@ -200,23 +298,20 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
         else:
             torch.cuda.synchronize(dev)
 
-    clocks = ClockSampler(local_rank)  # nvmlInit takes milliseconds: do it before the ranks line up
     aligned_start()
-    with clocks:
-        wall0 = time.perf_counter()
-        for k in range(K):
-            flush(k)
-            ev0[k].record(stream)
-            step(k)
-            ev1[k].record(stream)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        wall = time.perf_counter() - wall0
+    wall0 = time.perf_counter()
+    for k in range(K):
+        flush(k)
+        ev0[k].record(stream)
+        step(k)
+        ev1[k].record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    clocks.__exit__()
     lat = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)], dtype=np.float64)  # ms
     launches = eng.query()["kernel_launches"] - launches_before
-    if world > 1 and bus_reduce.kind.startswith("own"):
-        launches += K  # the engine's own bus all-reduce kernel, one per step
     total_ms = float(lat.sum())
     if world > 1:
         tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -231,12 +326,37 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     s = np.sort(lat)
     deadline_ms = 1000.0 * B / FS
 
+    # --- sustained: the same step back to back for ~1 s (no flush), clocks sampled — what the step does at the
+    # clocks a long run settles at (the timed region above is a few ms of GPU work at boost clocks) -------------
+    n_sus = int(max(50, min(20000, (50.0 if sweep else 1000.0) / ms_per_step)))
+    sus_clocks = ClockSampler(local_rank, period=0.02)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    aligned_start()
+    with sus_clocks:
+        e0.record(stream)
+        for k in range(n_sus):
+            step(k)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+    sus_ms = e0.elapsed_time(e1) / n_sus
+    if world > 1:
+        tmax = torch.tensor([sus_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        sus_ms = float(tmax.item())
+    sc = sus_clocks.summary()
+    sustained = {"ms_per_step": sus_ms, "value": macs_per_step / (sus_ms * 1e-3) / 1e9, "unit": "GMAC/s", "steps": n_sus,
+                 "sm_mhz": sc.get("sm_mhz"), "power_w_max": sc.get("power_w_max"), "reasons": sc.get("reasons"),
+                 "note": "back-to-back steps, L2 NOT flushed (inputs cycle through 8 buffers; IR tables / delay lines are "
+                         "the working set): context for the flushed, boost-clock number above, not the bench value"}
+
     # --- roofline of the dominant kernel: per-kernel CUDA events on the launch stream ----------
+    if world > 1:
+        dist.barrier()
     eng.set_profiling(True)
     KP = min(K, 100)
     for k in range(KP):
         flush(k)
-        eng.process(d_x[k % NB].data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
+        step(k)
     torch.cuda.synchronize(dev)
     q = eng.query()
     eng.set_profiling(False)
@@ -252,6 +372,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
                     "peak_source": "FFMA microbenchmark measured in this run (b200conv_measure_fp32_peak); "
                                    "MEASURED_PEAKS.json has no CUDA-core figure; nominal 74.4 TFLOP/s at 1965 MHz",
                     "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
+                    "step_frac_of_nominal": q["flops_per_block"] / (ms_per_step * 1e-3) / 1e12 / NOMINAL_FP32_TFLOPS,
                     "algorithmic_flops_per_launch": q["flops_per_block"]}
     else:
         achieved = q["alg_bytes_per_block"] / (dom_ms * 1e-3) / 1e9
@@ -261,32 +382,36 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
                     "peak_source": f"hbm_gbs of {peak_src} (measured COPY bandwidth, reads + writes; this kernel only "
                                    "reads, and a read-only stream can exceed it: ncu measured 6.84 TB/s for the FDL-MAC)",
                     "frac_of_spec_8tbs": achieved / 8000.0,
+                    "step_frac": q["alg_bytes_per_block"] / (ms_per_step * 1e-3) / 1e9 / peak,
                     "algorithmic_bytes_per_launch": q["alg_bytes_per_block"]}
-    try:  # per-launch DRAM traffic of the dominant kernel, from the committed ncu capture (null if none for this workload)
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tr = json.load(f).get(name)
-        if tr and tr["kernel"] == q["stage_name"][dom]:
-            roofline["traffic"] = tr["bytes"]
-            roofline["traffic_source"] = "profiles/r01_traffic.json (ncu --set full, one launch)"
-    except Exception:
-        pass
+    for fn in ("r02_traffic.json", "r01_traffic.json"):  # per-launch DRAM traffic of the dominant kernel (committed ncu capture)
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                tr = json.load(f).get(name)
+            if tr and tr["kernel"] == q["stage_name"][dom]:
+                roofline["traffic"] = tr["bytes"]
+                roofline["traffic_source"] = f"profiles/{fn} (ncu --set full, one launch)"
+                break
+        except Exception:
+            pass
     roofline["kernel_ms"] = dom_ms
     roofline["stage_ms"] = dict(zip(q["stage_name"][:q["stage_count"]], stage_ms))
     roofline["kernel_share_of_step"] = dom_ms / sum(stage_ms)
 
     # --- e2e: the same steps through the C ABI with HOST buffers (pinned), copies timed ---------
+    # b200conv_process_host at every N: with the bus exchange inside the kernel the multi-GPU host call IS the
+    # single-GPU host call (pinned buffers are read / written in place over PCIe by the kernels)
     h_in = torch.from_numpy(x_host).pin_memory()
     h_out = torch.zeros(out_shape).pin_memory()
     h_mix = torch.zeros(2, B).pin_memory()
     d_in2 = torch.zeros(T, B, device=dev)
 
     def e2e_step(k):
-        if world == 1:
+        if world == 1 or bus.in_kernel:
             eng.process_host_ptr(h_in[k % NB].data_ptr(), h_out.data_ptr(), h_mix.data_ptr())
-        else:  # identical sequence, with the NCCL bus reduce between the kernels and the read-back
+        else:  # fallback only (no symmetric memory): staged copies around the NCCL all-reduce
             d_in2.copy_(h_in[k % NB], non_blocking=True)
-            eng.process(d_in2.data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
-            bus_reduce(stream.cuda_stream)
+            step_ptr(d_in2.data_ptr())
             if layout == g.OUT_SAMPLE_MAJOR:  # only this rank's column tile of [B][Tg]
                 h_out[:, t0:t0 + T].copy_(d_y[:, t0:t0 + T], non_blocking=True)
             else:
@@ -312,32 +437,38 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline):
     e2e_ms = e2e_total / K
     es = np.sort(e2e_lat)
     out_bytes = int(np.prod(out_shape)) * 4 if layout == g.OUT_TRACK_MAJOR else T * B * 4
+    tail = "p99" if K >= 100 else "max"  # with fewer than 100 steps the nearest-rank p99 IS the maximum
     e2e = {"value": macs_per_step / (e2e_ms * 1e-3) / 1e9, "unit": "GMAC/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": world * T * B * 4, "d2h_bytes_per_step": world * (out_bytes + 2 * B * 4),
-           "p50_ms": pct(es, 0.50), "p99_ms": pct(es, 0.99), "meets_deadline": bool(pct(es, 0.99) <= deadline_ms),
-           "api": "b200conv_process_host (C ABI, pinned host buffers)" if world == 1 else
-                  "pinned H2D + b200conv_process + mix-bus all-reduce + D2H"}
+           "p50_ms": pct(es, 0.50), "p99_ms": pct(es, 0.99), "tail_is": tail, "meets_deadline": bool(pct(es, 0.99) <= deadline_ms),
+           "api": "b200conv_process_host (C ABI, pinned host buffers; bus exchange inside the kernel)" if (world == 1 or bus.in_kernel)
+                  else "pinned H2D + b200conv_process + NCCL mix-bus all-reduce + D2H (fallback)"}
 
+    # --- parity, outside every timed region, in every run ---------------------------------------
+    parity = parity_leg(name, eng, bus, step_ptr, d_y, d_mix, rank, world, dev, dist, with_oracle=not sweep)
+
+    cfg = workload_config(name, world)
     result = {
         "metric": "conv_tracks_x_ir_taps_gmac_per_s", "value": value, "unit": "GMAC/s", "n_gpus": world, "steps": K,
-        "warmup": fill, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (mt19937 seed 42 uniform(-1,1) input; Hamming-windowed-sinc IRs scaled 1/L, as the reference generates)",
-        "config": {"workload": f"{name}: {label}", "algo": algo_name, "tracks_per_gpu": T, "total_tracks": Tg, "block": B,
-                   "ir_taps": L, "fs": FS, "out_layout": layout_name, "partitions_or_splits": q["partitions"],
-                   "l2": flush.description,
-                   "timing": "sum of per-step CUDA-event times on the launch stream, max over ranks",
-                   "collective": f"all-reduce of the stereo mix bus float[2][B]: {bus_reduce.kind}"},
+        "config": cfg,
+        "run": {"warmup_steps_run": fill,
+                "warmup_note": "max(requested warm-up, ceil(L/B)+2 blocks) so that the whole history / delay line carries signal",
+                "partitions_or_splits": q["partitions"],
+                "collective": f"all-reduce of the stereo mix bus float[2][B]: {bus.kind}"},
         "rt_tracks": value * 1e9 / (L * FS),
-        "latency_ms": {"p50": pct(s, 0.50), "p95": pct(s, 0.95), "p99": pct(s, 0.99), "max": float(s[-1]),
+        "latency_ms": {"p50": pct(s, 0.50), "p95": pct(s, 0.95), "p99": pct(s, 0.99), "max": float(s[-1]), "tail_is": tail,
                        "slowest_step": int(np.argmax(lat)), "deadline": deadline_ms,
                        "meets_deadline": bool(pct(s, 0.99) <= deadline_ms)},
         "wall_ms_per_step_incl_flush": wall * 1e3 / K,
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "sustained": sustained, "parity": parity,
         "engine_device_bytes": q["device_bytes"],
     }
-    bus_reduce.check()
     if want_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline(name, budget_s=12.0)
+        result["cpu_baseline"] = cpu_baseline(name, budget_s=1.5, reps=3) if sweep else cpu_baseline(name, budget_s=12.0)
+    bus.close()
     eng.close()
     del d_x, d_y, flush
     torch.cuda.empty_cache()
@@ -363,9 +494,11 @@ def cpu_time_block(lib, algo_name, x, h, L, B, T, threads):
     return fn(x, h, L, B, T, threads)
 
 
-def cpu_baseline(name, budget_s, threads=None):
+def cpu_baseline(name, budget_s, threads=None, reps=5):
     """The reference's CPU path (R1 for Conv1D, R2 for Conv1D_accel) on the host cores, bounded
-    sample: full B and L, a track subset sized to the time budget, scaled linearly in T."""
+    sample: full B and L, a track subset sized to the time budget, scaled linearly in T.  One untimed
+    warm-up pass (page faults, thread start-up, clocks), then `reps` timed passes: the MEDIAN is the
+    value, min/max are reported as the spread."""
     from gpuaudiobench_b200 import synth
     algo_name, T, B, L, _, _ = WORKLOADS[name]
     lib, kind = _cpu_lib()
@@ -373,22 +506,26 @@ def cpu_baseline(name, budget_s, threads=None):
     # R2 skips the iterations its bounds test rejects, so its loop count is what matters for time
     iters_per_track = float(B) * L
     rate_guess = 0.5e9 * cores
-    Ts = int(max(cores, min(T, budget_s * rate_guess / iters_per_track)))
+    Ts = int(max(cores, min(T, budget_s / (reps + 1) * rate_guess / iters_per_track)))
     Ts = max(1, min(T, Ts))
     x = synth.make_input(Ts * B)
     h = synth.make_ir(T, L, 0, Ts)
-    secs = cpu_time_block(lib, algo_name, x, h, L, B, Ts, cores)
+    cpu_time_block(lib, algo_name, x, h, L, B, Ts, cores)  # warm-up
+    runs = sorted(cpu_time_block(lib, algo_name, x, h, L, B, Ts, cores) for _ in range(reps))
+    secs = runs[len(runs) // 2]
     gmacs = Ts * iters_per_track / secs / 1e9
     # the reference itself runs this loop on ONE thread (bench_conv1d.cu:42-55 calls it from setupBenchmark):
-    # time that too, on a subset sized for about a second (SURVEY §8d asks for both figures)
-    T1 = int(max(1, min(Ts, 1.0 * 0.5e9 / iters_per_track)))
-    secs1 = cpu_time_block(lib, algo_name, x[:T1 * B], h[:T1], L, B, T1, 1)
+    # time that too, on a subset sized for about half a second (SURVEY §8d asks for both figures)
+    T1 = int(max(1, min(Ts, 0.5 * 0.5e9 / iters_per_track)))
+    cpu_time_block(lib, algo_name, x[:T1 * B], h[:T1], L, B, T1, 1)
+    secs1 = sorted(cpu_time_block(lib, algo_name, x[:T1 * B], h[:T1], L, B, T1, 1) for _ in range(3))[1]
     gmacs1 = T1 * iters_per_track / secs1 / 1e9
     return {"value": gmacs, "unit": "GMAC/s", "cores": cores, "kind": kind,
-            "value_1_thread": gmacs1, "sample_1_thread": f"{T1} tracks on one thread, {secs1:.2f} s",
+            "spread": {"reps": reps, "min": Ts * iters_per_track / runs[-1] / 1e9, "max": Ts * iters_per_track / runs[0] / 1e9},
+            "value_1_thread": gmacs1, "sample_1_thread": f"{T1} tracks on one thread, median of 3, {secs1:.2f} s",
             "sample": f"{'R1 bench_conv1d.cu:188-208' if algo_name == 'direct' else 'R2 bench_conv1d_accel.cu:234-252'} "
-                      f"on {Ts} of {T} tracks at full B={B}, L={L}, {cores} threads over contiguous track ranges, "
-                      f"{secs:.2f} s; GMAC/s counts T*B*L loop iterations (time-domain equivalent)",
+                      f"on {Ts} of {T} tracks at full B={B}, L={L}, {cores} threads over contiguous track ranges; one warm-up "
+                      f"pass, median of {reps} ({secs:.2f} s each); GMAC/s counts T*B*L loop iterations (time-domain equivalent)",
             "seconds": secs, "ms_per_block_scaled_to_T": secs * 1e3 * T / Ts,
             "rt_tracks": gmacs * 1e9 / (L * FS)}
 
@@ -401,7 +538,7 @@ def run_reference(args, rank, world):
     algo_name, T, B, L, _, label = WORKLOADS[name]
     lib, kind = _cpu_lib()
     cores = lib.hardware_threads()
-    K, W = args.steps, max(1, min(args.warmup, 2))
+    K, W = args.steps, args.warmup
     # bounded sample: whole run (K + W steps) within ~150 s
     iters_per_track = float(B) * L
     per_step_budget = 150.0 / (K + W)
@@ -419,8 +556,7 @@ def run_reference(args, rank, world):
     return {"impl": "reference", "metric": "conv_tracks_x_ir_taps_gmac_per_s", "value": value, "unit": "GMAC/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_full, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generators as our arm)",
-            "config": {"workload": f"{name}: {label}", "algo": algo_name, "tracks_per_gpu": T, "total_tracks": T * world,
-                       "block": B, "ir_taps": L, "fs": FS},
+            "config": workload_config(name, world),
             "cpu_baseline": {"value": value, "unit": "GMAC/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "GMAC/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "rt_tracks": value * 1e9 / (L * FS), "gpu_launches": 0}
@@ -428,21 +564,29 @@ def run_reference(args, rank, world):
 
 def run_sweep(args, rank, world, local_rank, dist):
     """BASELINE config 5: buffer-size sweep 32..4096 at C4's per-GPU tracks and IR length (UPOLS) and
-    at C2's (direct): throughput vs p50/p99 per-buffer latency vs the B/fs deadline."""
+    at C2's (direct): throughput vs p50/p99 per-buffer latency vs the B/fs deadline
+    (meets_deadline = p99 <= 1000*B/fs, cuda/globals.cu:86-89,155-156), with the reference's CPU loop on
+    the host cores beside every point (rank 0, bounded sample)."""
     rows = []
     for algo_name, T, L, sizes in (("upols", 512, 96000, (32, 64, 128, 256, 512, 1024, 2048, 4096)),
                                    ("direct", 128, 16384, (32, 64, 128, 256, 512, 1024, 2048, 4096))):
         for B in sizes:
             key = f"sweep_{algo_name}_{B}"
             WORKLOADS[key] = (algo_name, T, B, L, "track_major", f"sweep: {algo_name} {T} tracks/GPU x {B}-sample buffers x {L}-tap IR")
-            sub = argparse.Namespace(**vars(args))
-            sub.steps = min(args.steps, 100)
-            r = run_workload(key, sub, rank, world, local_rank, dist, want_cpu_baseline=False)
-            rows.append({"algo": algo_name, "block": B, "tracks_per_gpu": T, "ir_taps": L, "n_gpus": world,
+            r = run_workload(key, args, rank, world, local_rank, dist, want_cpu_baseline=(rank == 0), sweep=True)
+            cpu = r.get("cpu_baseline") or {}
+            rows.append({"algo": algo_name, "block": B, "tracks_per_gpu": T, "ir_taps": L, "n_gpus": world, "steps": args.steps,
                          "ms_per_step": r["ms_per_step"], "gmac_per_s": r["value"], "rt_tracks": r["rt_tracks"],
-                         "p50_ms": r["latency_ms"]["p50"], "p99_ms": r["latency_ms"]["p99"], "deadline_ms": r["latency_ms"]["deadline"],
-                         "meets_deadline": r["latency_ms"]["meets_deadline"], "e2e_ms": r["e2e"]["ms_per_step"],
-                         "roofline_frac": r["roofline"]["frac"], "roofline_bound": r["roofline"]["bound"]})
+                         "p50_ms": r["latency_ms"]["p50"], "p99_ms": r["latency_ms"]["p99"], "max_ms": r["latency_ms"]["max"],
+                         "deadline_ms": r["latency_ms"]["deadline"], "meets_deadline": r["latency_ms"]["meets_deadline"],
+                         "e2e_ms": r["e2e"]["ms_per_step"], "e2e_p99_ms": r["e2e"]["p99_ms"],
+                         "e2e_meets_deadline": r["e2e"]["meets_deadline"],
+                         "roofline_frac": r["roofline"]["frac"], "roofline_bound": r["roofline"]["bound"],
+                         "step_frac": r["roofline"].get("step_frac", r["roofline"].get("step_frac_of_nominal")),
+                         "gpu_launches_per_step": r["gpu_launches"] / args.steps,
+                         "bus_parity_ok": r["parity"]["ok"], "ranks_bit_identical": r["parity"]["ranks_bit_identical"],
+                         "cpu_gmac_per_s": cpu.get("value"), "cpu_cores": cpu.get("cores"), "cpu_kind": cpu.get("kind"),
+                         "cpu_rt_tracks": cpu.get("rt_tracks")})
     return rows
 
 
@@ -455,7 +599,7 @@ def run_latency(args, rank, world, local_rank, dist):
 
     import gpuaudiobench_b200 as g
     from gpuaudiobench_b200 import synth
-    from gpuaudiobench_b200.distributed import BusAllReduce
+    from gpuaudiobench_b200.distributed import EngineBusGroup
 
     algo_name, T, B, L, layout_name, label = WORKLOADS[args.workload]
     algo = g.ALGO_DIRECT if algo_name == "direct" else g.ALGO_UPOLS
@@ -469,15 +613,15 @@ def run_latency(args, rank, world, local_rank, dist):
     h_out = torch.zeros(T, B).pin_memory()
     h_mix = torch.zeros(2, B).pin_memory()
     d_in, d_y, d_mix = torch.zeros(T, B, device=dev), torch.zeros(T, B, device=dev), torch.zeros(2, B, device=dev)
-    bus = BusAllReduce(d_mix, force_nccl=bool(os.environ.get("B200CONV_BUS_NCCL")))
+    bus = EngineBusGroup(eng, d_mix, force_nccl=bool(os.environ.get("B200CONV_BUS_NCCL")))
 
     def block(k):
-        if world == 1:
+        if world == 1 or bus.in_kernel:  # the multi-GPU host call is the single-GPU host call
             eng.process_host_ptr(h_in[k % NB].data_ptr(), h_out.data_ptr(), h_mix.data_ptr())
         else:
             d_in.copy_(h_in[k % NB], non_blocking=True)
             eng.process(d_in.data_ptr(), d_y.data_ptr(), d_mix.data_ptr(), stream=stream.cuda_stream)
-            bus(stream.cuda_stream)
+            bus.reduce()
             h_out.copy_(d_y, non_blocking=True)
             h_mix.copy_(d_mix, non_blocking=True)
             stream.synchronize()
@@ -510,6 +654,7 @@ def run_latency(args, rank, world, local_rank, dist):
                      "mean_ms": float(lat.mean()), "deadline_ms": period * 1e3, "meets_deadline": bool(pct(s, 0.99) <= period * 1e3),
                      "missed_blocks": int((lat > period * 1e3).sum())}
     bus.check()
+    bus.close()
     return {"latency_run": out, "workload": f"{args.workload}: {label}", "n_gpus": world, "total_tracks": Tg, "block": B,
             "ir_taps": L, "fs": FS, "path": "host buffers -> results on host (e2e)", "collective": bus.kind}
 
@@ -646,12 +791,14 @@ def main():
     if args.sweep:
         rows = run_sweep(args, rank, world, local_rank, dist)
         if rank == 0:
-            print(json.dumps({"sweep": rows, "n_gpus": world, "fs": FS}), flush=True)
+            print(json.dumps({"sweep": rows, "n_gpus": world, "fs": FS, "steps_per_point": args.steps,
+                              "deadline_rule": "meets_deadline = p99 <= 1000*B/fs (cuda/globals.cu:86-89,155-156)"}), flush=True)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        return 0
+        return 0 if all(r["bus_parity_ok"] for r in rows) else 3
     result = run_workload(args.workload, args, rank, world, local_rank, dist, want_cpu_baseline=(rank == 0 and world == 1))
+    ok = result["parity"]["ok"]
     if not args.no_also and args.workload == "c2":
         also = {}
         for other in ("c3", "c4"):
@@ -659,13 +806,17 @@ def main():
             sub.steps = min(args.steps, 100)
             r = run_workload(other, sub, rank, world, local_rank, dist, want_cpu_baseline=False)
             also[other] = {k: r[k] for k in ("value", "unit", "ms_per_step", "rt_tracks", "latency_ms", "roofline", "e2e",
-                                             "gpu_launches", "config")}
+                                             "gpu_launches", "config", "run", "sustained", "parity")}
+            ok = ok and r["parity"]["ok"]
         result["also"] = also
     if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        print("bench.py: PARITY FAILED (see the \"parity\" objects of the line above)", file=sys.stderr, flush=True)
+        return 3
     return 0
 
 

@@ -13,16 +13,22 @@
 // Two slots (epoch parity) are enough: a rank cannot finish epoch e+1 before every peer has
 // signalled e+1, which a peer only does after its epoch-e kernel has completed.
 // `out` may alias `local` (element i is read in step 1 and written in step 4 by the same thread).
-// Buffer layout per rank (floats unless noted): data[2][world][n] | flags uint32 [2][world] (+pad).
+// Buffer layout per rank (floats unless noted): data[2][world][n] | flags uint32 [2][world][kBusMaxChunks]
+// (+pad) — shared with the in-kernel exchange of bus_tree.cuh, which signals per column chunk; this
+// stand-alone kernel (used by the paths whose last kernel cannot carry the bus tree, and by callers
+// that reduce a bus of their own) uses chunk 0's flag.
 #include "../../include/b200conv.h"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bus_tree.cuh"
+
 namespace {
 
-constexpr int kMaxWorld = 16;
-constexpr unsigned kSpinLimit = 1u << 26;  // ~seconds; then give up instead of hanging the GPU
+using b200conv::kBusMaxChunks;
+constexpr int kMaxWorld = b200conv::kBusMaxWorld;
+constexpr unsigned kSpinLimit = b200conv::kBusSpinLimit;  // ~seconds; then give up instead of hanging the GPU
 
 struct PeerTable {
     float* buf[kMaxWorld];
@@ -53,12 +59,12 @@ __global__ void __launch_bounds__(1024) bus_allreduce_kernel(PeerTable peers, co
     // 2. signal, 3. wait
     if (threadIdx.x < world) {
         uint32_t* peer_flags = reinterpret_cast<uint32_t*>(peers.buf[threadIdx.x] + data_floats);
-        st_release_sys(peer_flags + slot * world + rank, epoch);
+        st_release_sys(peer_flags + (slot * world + rank) * kBusMaxChunks, epoch);
         const uint32_t* my_flags = reinterpret_cast<const uint32_t*>(peers.buf[rank] + data_floats);
         unsigned spins = 0;
-        while (ld_acquire_sys(my_flags + slot * world + threadIdx.x) != epoch) {
+        while (ld_acquire_sys(my_flags + (slot * world + threadIdx.x) * kBusMaxChunks) != epoch) {
             if (++spins > kSpinLimit) {
-                atomicExch(error_flag, 1u);
+                *reinterpret_cast<volatile uint32_t*>(error_flag) = 1u;  // may be mapped host memory: a plain store
                 break;
             }
         }
@@ -77,7 +83,7 @@ __global__ void __launch_bounds__(1024) bus_allreduce_kernel(PeerTable peers, co
 
 extern "C" size_t b200conv_bus_buffer_bytes(int world, int n) {
     const size_t data = static_cast<size_t>(2) * world * n * sizeof(float);
-    const size_t flags = static_cast<size_t>(2) * world * sizeof(uint32_t);
+    const size_t flags = static_cast<size_t>(2) * world * kBusMaxChunks * sizeof(uint32_t);
     return (data + flags + 255) / 256 * 256;
 }
 

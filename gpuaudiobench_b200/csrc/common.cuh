@@ -4,9 +4,52 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace b200conv {
 
 constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------------------------
+// Host: opt a kernel into more than 48 KB of dynamic shared memory.  The attribute belongs to the
+// (function, DEVICE) pair, and one process may drive several devices from concurrent threads
+// (group.cu), so the "already done" cache is keyed by both and guarded by a mutex — a process-wide
+// flag would leave every device but the first without the opt-in.
+// ---------------------------------------------------------------------------------------------
+inline cudaError_t ensure_dyn_smem(const void* fn, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = done[{fn, dev}];
+    if (have >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
+// Make `device` current for the lifetime of the guard and restore the caller's device afterwards:
+// every ABI entry point that takes an engine runs on the engine's device without side effects on
+// the calling thread's current device.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        status = cudaGetDevice(&prev);
+        if (status == cudaSuccess && prev != device) status = cudaSetDevice(device);
+        else if (status == cudaSuccess) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // ---------------------------------------------------------------------------------------------
 // 16-byte-chunk swizzle used by the direct FIR for BOTH the tap table and the input-history ring.

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "bus_tree.cuh"
 #include "common.cuh"
 #include "direct_fir.cuh"
 #include "strip.cuh"
@@ -41,6 +42,14 @@ int fail(int code, const std::string& msg) {
             return fail(B200CONV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));  \
     } while (0)
 
+// Run the rest of the entry point on the engine's device and give the caller's device back on return
+// (b200conv.h: "every call that takes an engine runs on cfg.device and leaves the calling thread's
+// current device as it found it").
+#define ENGINE_DEVICE(dev)                                                                              \
+    DeviceGuard _device_guard(dev);                                                                     \
+    if (_device_guard.status != cudaSuccess)                                                            \
+        return fail(B200CONV_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_device_guard.status))
+
 bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 int ilog2(uint32_t v) {
     int l = 0;
@@ -59,6 +68,7 @@ struct DirectState {
     float* h = nullptr;
     float* ring = nullptr;
     float* partial = nullptr;
+    unsigned* tcount = nullptr;  // [T*ntiles] last-arriver tickets of shared track-tiles
     int pos = 0;
 };
 
@@ -87,6 +97,18 @@ struct b200conv_engine {
     float* d_out_stage = nullptr;
     float* d_mix_stage = nullptr;
     float* d_gains = nullptr;
+    // stereo-bus tree (bus_tree.cuh): scratch rows, group partials, tickets
+    float* d_ybus = nullptr;      // [T][B]
+    float* d_gpart = nullptr;     // [NG][2][B]
+    unsigned* d_gcount = nullptr; // [NG][NC]
+    unsigned* d_ccount = nullptr; // [NC]
+    int bus_G1 = 1, bus_NG = 1, bus_CH = 0, bus_NC = 1;
+    // multi-GPU bus group (b200conv_attach_bus): world == 1 means a stand-alone engine
+    int bus_world = 1, bus_rank = 0;
+    uint64_t bus_peers[kBusMaxWorld] = {};
+    uint32_t bus_epoch = 0;
+    uint32_t* d_bus_err = nullptr;  // pinned, mapped host word (UVA): kernels store 1 on a spin timeout, the host
+                                    // reads it after its stream synchronise without a copy
     DirectState dir;
     UpolsState up;
     // channel strip (b200conv_set_strip): device copies of the per-track parameters
@@ -258,6 +280,42 @@ StripParams strip_params(b200conv_engine* e, float* d_out, bool commit) {
     return sp;
 }
 
+// The bus tree of this block (bus_tree.cuh).  d_mix == null disables it.  On a multi-GPU job the epoch was
+// advanced by the caller (once per block with a bus, in lockstep on every rank).
+BusTreeParams bus_params(const b200conv_engine* e, float* d_mix) {
+    BusTreeParams b{};
+    b.mix = d_mix;
+    if (!d_mix) return b;
+    b.gains = e->d_gains;
+    b.ybus = e->d_ybus;
+    b.gpart = e->d_gpart;
+    b.gcount = e->d_gcount;
+    b.ccount = e->d_ccount;
+    b.T = e->T;
+    b.B = e->B;
+    b.G1 = e->bus_G1;
+    b.NG = e->bus_NG;
+    b.CH = e->bus_CH;
+    b.NC = e->bus_NC;
+    b.rank = e->bus_rank;
+    b.world = e->bus_world;
+    for (int i = 0; i < e->bus_world; ++i) b.peers[i] = reinterpret_cast<float*>(e->bus_peers[i]);
+    b.epoch = e->bus_epoch;
+    b.err = e->d_bus_err;
+    return b;
+}
+
+// Stand-alone all-reduce of a local bus already in d_mix: only the paths whose last kernel cannot carry the
+// bus tree (direct engine with a channel strip, three-kernel UPOLS) need it on a multi-GPU job.
+int allreduce_local_bus(b200conv_engine* e, float* d_mix, cudaStream_t st) {
+    if (e->bus_world <= 1 || !d_mix) return B200CONV_OK;
+    const int rc = b200conv_bus_allreduce(d_mix, d_mix, e->bus_peers, e->bus_rank, e->bus_world, 2 * e->B, e->bus_epoch,
+                                          e->d_bus_err, st);
+    if (rc) return fail(rc, "b200conv_bus_allreduce launch failed");
+    e->launches += 1;
+    return B200CONV_OK;
+}
+
 struct StageTimer {
     b200conv_engine* e;
     cudaStream_t st;
@@ -343,7 +401,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
     if (prop.major != 10)
         return fail(B200CONV_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
                                                 std::to_string(prop.minor) + "; kernels are built for sm_100a only");
-    CU_TRY(cudaSetDevice(cfg->device));
+    ENGINE_DEVICE(cfg->device);
 
     auto* e = new b200conv_engine();
     e->cfg = *cfg;
@@ -368,12 +426,34 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
     if ((rc = dev_alloc(e, &e->d_mix_stage, static_cast<size_t>(2) * e->B))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_gains, static_cast<size_t>(2) * e->T))) return bail(rc);
     if ((rc = set_default_gains(e))) return bail(rc);
+    {   // bus tree geometry: groups of ~sqrt(T) tracks; column chunks = the kernels' output tiles
+        int g1 = 1;
+        while (g1 < 64 && g1 * g1 < e->T) g1 *= 2;
+        e->bus_G1 = g1;
+        e->bus_NG = (e->T + g1 - 1) / g1;
+        if (cfg->algo == B200CONV_ALGO_DIRECT) {
+            e->bus_CH = e->dir.A * 16;
+            e->bus_NC = e->dir.ntiles;
+        } else {
+            e->bus_CH = e->B;
+            e->bus_NC = 1;
+        }
+        if (e->bus_NC > kBusMaxChunks) return bail(fail(B200CONV_ERR_INVALID, "b200conv_create: block too large for the bus tree"));
+        if ((rc = dev_alloc(e, &e->d_ybus, tb))) return bail(rc);
+        if ((rc = dev_alloc(e, &e->d_gpart, static_cast<size_t>(e->bus_NG) * 2 * e->B))) return bail(rc);
+        if ((rc = dev_alloc(e, &e->d_gcount, static_cast<size_t>(e->bus_NG) * e->bus_NC))) return bail(rc);
+        if ((rc = dev_alloc(e, &e->d_ccount, static_cast<size_t>(e->bus_NC)))) return bail(rc);
+        err = cudaHostAlloc(reinterpret_cast<void**>(&e->d_bus_err), sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable);
+        if (err != cudaSuccess) return bail(fail(B200CONV_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(err)));
+        *e->d_bus_err = 0;
+    }
 
     if (cfg->algo == B200CONV_ALGO_DIRECT) {
         DirectState& d = e->dir;
         if ((rc = dev_alloc(e, &d.h, static_cast<size_t>(e->T) * d.Lc * 16))) return bail(rc);
         if ((rc = dev_alloc(e, &d.ring, static_cast<size_t>(e->T) * d.cap))) return bail(rc);
         if ((rc = dev_alloc(e, &d.partial, static_cast<size_t>(d.MS) * tb))) return bail(rc);
+        if ((rc = dev_alloc(e, &d.tcount, static_cast<size_t>(e->T) * d.ntiles))) return bail(rc);
     } else {
         UpolsState& u = e->up;
         const size_t spec = static_cast<size_t>(e->T) * u.P * u.M;
@@ -395,18 +475,19 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
 
 void b200conv_destroy(b200conv_engine* e) {
     if (!e) return;
-    cudaSetDevice(e->cfg.device);
+    DeviceGuard guard(e->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
     for (auto& ev : e->ev)
         if (ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->d_bus_err) cudaFreeHost(e->d_bus_err);
     delete e;
 }
 
 int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
     if (!e || !host_ir) return fail(B200CONV_ERR_INVALID, "b200conv_load_ir: null argument");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    ENGINE_DEVICE(e->cfg.device);
     const int T = e->T, L = e->L, B = e->B;
     if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
         DirectState& d = e->dir;
@@ -474,14 +555,14 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
 
 int b200conv_reset(b200conv_engine* e) {
     if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_reset: null engine");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    ENGINE_DEVICE(e->cfg.device);
     CU_TRY(cudaDeviceSynchronize());
     return reset_state(e);
 }
 
 int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
     if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_prime_history: null engine");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    ENGINE_DEVICE(e->cfg.device);
     CU_TRY(cudaDeviceSynchronize());
     int rc = reset_state(e);
     if (rc || !host_hist || e->L < 2) return rc;
@@ -542,24 +623,16 @@ int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
 
 int b200conv_set_mix_gains(b200conv_engine* e, const float* host_gains) {
     if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_set_mix_gains: null engine");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    ENGINE_DEVICE(e->cfg.device);
     if (!host_gains) return set_default_gains(e);
     CU_TRY(cudaMemcpy(e->d_gains, host_gains, static_cast<size_t>(2) * e->T * sizeof(float), cudaMemcpyHostToDevice));
     return B200CONV_OK;
 }
 
-static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, float* d_out2, float* d_mix, uint32_t flags,
-                        void* stream);
-
 int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float* d_mix, uint32_t flags, void* stream) {
-    return process_impl(e, d_in, d_out, nullptr, d_mix, flags, stream);
-}
-
-// d_out2: optional second copy of the output (fused UPOLS kernel only; null otherwise)
-static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, float* d_out2, float* d_mix, uint32_t flags,
-                        void* stream) {
     if (!e || !d_in || !d_out) return fail(B200CONV_ERR_INVALID, "b200conv_process: null argument");
     if (!e->ir_loaded) return fail(B200CONV_ERR_STATE, "b200conv_process: call b200conv_load_ir first");
+    ENGINE_DEVICE(e->cfg.device);  // launches, smem opt-ins and the null stream are those of the engine's device
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the engine's state lives on whatever stream the previous block ran on: switching streams is
     // allowed, but the new stream must see the old one's work (cheap: only when the stream changes)
@@ -570,6 +643,7 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
     const int sample_major = (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR);
     StageTimer tm{e, st};
     int marks = 0;
+    if (d_mix && e->bus_world > 1) e->bus_epoch += 1;  // one exchange per block with a bus, in lockstep on every rank
 
     if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
         DirectState& d = e->dir;
@@ -592,34 +666,29 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         p.ntiles = d.ntiles;
         p.U = e->T * d.ntiles * d.NS;
         p.G = d.G;
+        // tile epilogue inside the same launch: output, ring append, bus tree (+ NVLink all-reduce)
+        p.tcount = d.tcount;
+        p.out = d_out;
+        p.sample_major = sample_major;
+        p.Tg = e->Tg;
+        p.toff = e->toff;
+        p.ring_w = commit ? d.ring : nullptr;
+        p.cap = d.cap;
+        p.pos = d.pos;
+        p.bus = bus_params(e, e->strip_ops ? nullptr : d_mix);  // with a strip the bus is taken after it
         CU_TRY(launch_fir(p, d.A, d.smem, st));
+        e->launches += 1;
         tm.mark();
-        FinishParams f{};
-        f.partial = d.partial;
-        f.out = d_out;
-        f.MS = d.MS;
-        f.T = e->T;
-        f.B = e->B;
-        f.sample_major = sample_major;
-        f.Tg = e->Tg;
-        f.toff = e->toff;
-        f.gains = e->d_gains;
-        f.mix = e->strip_ops ? nullptr : d_mix;  // with a strip the bus is taken after it
-        f.d_in = d_in;
-        f.ring = commit ? d.ring : nullptr;
-        f.cap = d.cap;
-        f.pos = d.pos;
-        CU_TRY(launch_fir_finish_mix(f, st));
-        e->launches += 2;
         if (e->strip_ops) {
             int rc = run_strip(e, d_out, commit, st);
             if (rc) return rc;
             if (d_mix) {
                 CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
                 e->launches += 1;
+                if ((rc = allreduce_local_bus(e, d_mix, st))) return rc;
             }
+            tm.mark();
         }
-        tm.mark();
         marks = tm.idx;
         if (commit) d.pos = (d.pos + e->B) % d.cap;
     } else {
@@ -635,7 +704,7 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             fp.Ypart = u.Ypart;
             fp.counters = u.counters;
             fp.out = d_out;
-            fp.out2 = d_out2;
+            fp.out2 = nullptr;
             fp.T = e->T;
             fp.P = u.P;
             fp.M = u.M;
@@ -647,6 +716,7 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             fp.Tg = e->Tg;
             fp.toff = e->toff;
             if (e->strip_ops) fp.strip = strip_params(e, d_out, commit);  // strip runs inside the kernel's epilogue
+            fp.bus = bus_params(e, d_mix);                                // ... and so do the bus and its all-reduce
             CU_TRY(launch_upols_fused(fp, st));
             e->launches += 1;
             tm.mark();
@@ -694,11 +764,12 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             int rc = run_strip(e, d_out, commit, st);
             if (rc) return rc;
         }
-        if (d_mix) {
+        if (d_mix && !u.fused) {
             CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
             e->launches += 1;
+            if (int rc = allreduce_local_bus(e, d_mix, st)) return rc;
         }
-        tm.mark();
+        if (!u.fused) tm.mark();
         marks = tm.idx;
     }
     if (commit) e->blocks += 1;
@@ -722,38 +793,41 @@ bool is_pinned_host(const void* p) {
 
 int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix, uint32_t flags) {
     if (!e || !h_in) return fail(B200CONV_ERR_INVALID, "b200conv_process_host: null argument");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    ENGINE_DEVICE(e->cfg.device);
     cudaStream_t st = e->own_stream;
     const size_t tb = static_cast<size_t>(e->T) * e->B;
     const int zc = env_int("B200CONV_ZEROCOPY", 3);  // bit 0: read the input in place; bit 1: write results in place
     const bool direct = (e->cfg.algo == B200CONV_ALGO_DIRECT);
     // input: every engine reads d_in once or twice -> read it straight from pinned host memory
     const bool in_place = (zc & 1) && is_pinned_host(h_in);
-    // results: only the direct engine produces output and bus in its last kernel without re-reading them
-    const bool out_place = (zc & 2) && !e->strip_ops && direct && h_out && is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
+    // results: the kernels that finish a track in their own epilogue (direct FIR, fused UPOLS) can post the
+    // output rows and the bus straight to pinned host memory — the bus tree sums from a device-side copy of
+    // the rows, so nothing is read back over PCIe.  Not for: a strip kernel after the direct FIR (it works in
+    // place on the output), the three-kernel UPOLS path, and sample-major UPOLS (a column tile written track
+    // by track is scattered 4-byte PCIe writes: measured 2x slower than the staged copy).
+    const bool fused_ok = !direct && e->up.fused && e->cfg.out_layout == B200CONV_OUT_TRACK_MAJOR;
+    const bool out_place = (zc & 2) && ((direct && !e->strip_ops) || fused_ok) && h_out && is_pinned_host(h_out) &&
+                           (!h_mix || is_pinned_host(h_mix));
     const float* d_in = h_in;
     if (!in_place) {
         CU_TRY(cudaMemcpyAsync(e->d_in_stage, h_in, tb * sizeof(float), cudaMemcpyHostToDevice, st));
         d_in = e->d_in_stage;
     }
+    auto bus_ok = [&]() -> int {  // after the synchronise: did a peer engine miss the bus exchange of this block?
+        if (e->bus_world > 1 && h_mix && *static_cast<volatile uint32_t*>(e->d_bus_err)) {
+            *e->d_bus_err = 0;
+            return fail(B200CONV_ERR_CUDA, "bus all-reduce: a peer engine did not signal within the spin bound");
+        }
+        return B200CONV_OK;
+    };
     if (out_place) {
         int rc = b200conv_process(e, d_in, h_out, h_mix, flags, st);
         if (rc) return rc;
         CU_TRY(cudaStreamSynchronize(st));
-        return B200CONV_OK;
+        return bus_ok();
     }
-    // fused UPOLS: the kernel keeps a device copy of the output for the bus kernel and ALSO posts it
-    // to the pinned host buffer itself; the bus kernel writes its 2*B floats to pinned memory too
-    // (track-major only: a sample-major column tile would be scattered 4-byte PCIe writes — measured 2x slower)
-    const bool dual = (zc & 2) && !e->strip_ops && !direct && e->up.fused && e->cfg.out_layout == B200CONV_OUT_TRACK_MAJOR && h_out &&
-                      is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
-    if (dual) {
-        int rc = process_impl(e, d_in, e->d_out_stage, h_out, h_mix, flags, st);
-        if (rc) return rc;
-        CU_TRY(cudaStreamSynchronize(st));
-        return B200CONV_OK;
-    }
-    int rc = b200conv_process(e, d_in, e->d_out_stage, h_mix ? e->d_mix_stage : nullptr, flags, st);
+    const bool mix_place = (zc & 2) && h_mix && is_pinned_host(h_mix);  // 2*B floats: written in place whatever the output path
+    int rc = b200conv_process(e, d_in, e->d_out_stage, h_mix ? (mix_place ? h_mix : e->d_mix_stage) : nullptr, flags, st);
     if (rc) return rc;
     if (h_out) {
         if (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR && e->Tg != e->T) {
@@ -764,14 +838,15 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
             CU_TRY(cudaMemcpyAsync(h_out, e->d_out_stage, tb * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
     }
-    if (h_mix) CU_TRY(cudaMemcpyAsync(h_mix, e->d_mix_stage, static_cast<size_t>(2) * e->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_mix && !mix_place)
+        CU_TRY(cudaMemcpyAsync(h_mix, e->d_mix_stage, static_cast<size_t>(2) * e->B * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    return B200CONV_OK;
+    return bus_ok();
 }
 
 int b200conv_set_strip(b200conv_engine* e, const b200conv_strip* strip) {
     if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_set_strip: null engine");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    ENGINE_DEVICE(e->cfg.device);
     CU_TRY(cudaDeviceSynchronize());
     if (!strip || !(strip->ops & (B200CONV_STRIP_STATS | B200CONV_STRIP_GAIN | B200CONV_STRIP_BIQUAD))) {
         e->strip_ops = 0;
@@ -780,12 +855,18 @@ int b200conv_set_strip(b200conv_engine* e, const b200conv_strip* strip) {
     if ((strip->ops & B200CONV_STRIP_BIQUAD) && !strip->biquad)
         return fail(B200CONV_ERR_INVALID, "b200conv_set_strip: BIQUAD needs coefficients");
     const size_t T = static_cast<size_t>(e->T);
-    if (!e->d_strip_state) {
-        int rc = dev_alloc(e, &e->d_strip_state, 2 * T);
-        if (!rc) rc = dev_alloc(e, &e->d_strip_stats, 2 * T);
-        if (!rc) rc = dev_alloc(e, &e->d_strip_gains, T);
-        if (!rc) rc = dev_alloc(e, &e->d_strip_coef, 5 * T);
-        if (rc) return rc;
+    if (!e->d_strip_state || !e->d_strip_stats || !e->d_strip_gains || !e->d_strip_coef) {
+        // all or nothing: a partial failure must not leave some buffers set and others null
+        float *st = nullptr, *ss = nullptr, *sg = nullptr, *sc = nullptr;
+        int rc = dev_alloc(e, &st, 2 * T);
+        if (!rc) rc = dev_alloc(e, &ss, 2 * T);
+        if (!rc) rc = dev_alloc(e, &sg, T);
+        if (!rc) rc = dev_alloc(e, &sc, 5 * T);
+        if (rc) return rc;  // whatever was allocated stays in e->allocs and is freed by destroy
+        e->d_strip_state = st;
+        e->d_strip_stats = ss;
+        e->d_strip_gains = sg;
+        e->d_strip_coef = sc;
     }
     CU_TRY(cudaMemset(e->d_strip_state, 0, 2 * T * sizeof(float)));
     CU_TRY(cudaMemset(e->d_strip_stats, 0, 2 * T * sizeof(float)));
@@ -807,7 +888,7 @@ int b200conv_set_strip(b200conv_engine* e, const b200conv_strip* strip) {
 int b200conv_strip_state(b200conv_engine* e, float* host_state, int set) {
     if (!e || !host_state) return fail(B200CONV_ERR_INVALID, "b200conv_strip_state: null argument");
     if (!e->d_strip_state) return fail(B200CONV_ERR_STATE, "b200conv_strip_state: no strip attached");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    ENGINE_DEVICE(e->cfg.device);
     CU_TRY(cudaDeviceSynchronize());
     const size_t bytes = static_cast<size_t>(2) * e->T * sizeof(float);
     if (set)
@@ -820,7 +901,7 @@ int b200conv_strip_state(b200conv_engine* e, float* host_state, int set) {
 int b200conv_strip_stats(b200conv_engine* e, float* host_stats) {
     if (!e || !host_stats) return fail(B200CONV_ERR_INVALID, "b200conv_strip_stats: null argument");
     if (!e->d_strip_stats) return fail(B200CONV_ERR_STATE, "b200conv_strip_stats: no strip attached");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    ENGINE_DEVICE(e->cfg.device);
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(host_stats, e->d_strip_stats, static_cast<size_t>(2) * e->T * sizeof(float), cudaMemcpyDeviceToHost));
     return B200CONV_OK;
@@ -864,6 +945,40 @@ int b200conv_strip_process(const float* d_in, float* d_out, uint32_t tracks, uin
     return B200CONV_OK;
 }
 
+int b200conv_attach_bus(b200conv_engine* e, const uint64_t* peer_buffers, int rank, int world) {
+    if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_attach_bus: null engine");
+    ENGINE_DEVICE(e->cfg.device);
+    CU_TRY(cudaDeviceSynchronize());
+    if (!peer_buffers || world <= 1) {  // detach: a stand-alone engine again
+        e->bus_world = 1;
+        e->bus_rank = 0;
+        e->bus_epoch = 0;
+        return B200CONV_OK;
+    }
+    if (world > kBusMaxWorld || rank < 0 || rank >= world)
+        return fail(B200CONV_ERR_INVALID, "b200conv_attach_bus: bad rank / world (at most 16 engines)");
+    for (int i = 0; i < world; ++i)
+        if (!peer_buffers[i]) return fail(B200CONV_ERR_INVALID, "b200conv_attach_bus: null peer buffer");
+    e->bus_world = world;
+    e->bus_rank = rank;
+    e->bus_epoch = 0;
+    for (int i = 0; i < world; ++i) e->bus_peers[i] = peer_buffers[i];
+    *e->d_bus_err = 0;
+    return B200CONV_OK;
+}
+
+int b200conv_bus_status(b200conv_engine* e) {
+    if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_bus_status: null engine");
+    ENGINE_DEVICE(e->cfg.device);
+    if (e->has_last_stream) CU_TRY(cudaStreamSynchronize(e->last_stream));
+    if (*static_cast<volatile uint32_t*>(e->d_bus_err)) {
+        *e->d_bus_err = 0;  // reported once; later blocks start clean
+        return fail(B200CONV_ERR_CUDA, "bus all-reduce: a peer engine did not signal within the spin bound "
+                                       "(the bus of that block is incomplete)");
+    }
+    return B200CONV_OK;
+}
+
 int b200conv_query(b200conv_engine* e, b200conv_info* info) {
     if (!e || !info) return fail(B200CONV_ERR_INVALID, "b200conv_query: null argument");
     std::memset(info, 0, sizeof(*info));
@@ -882,11 +997,11 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
         info->alg_bytes_per_block = 0;
         info->partitions = e->dir.MS;
         info->fft_size = 0;
-        info->kernels_per_block = 2;
-        info->stage_count = 2;
+        info->kernels_per_block = e->strip_ops ? 3 : 1;
+        info->stage_count = e->strip_ops ? 2 : 1;
         info->dominant_stage = 0;
         std::snprintf(info->stage_name[0], 24, "fir_direct");
-        std::snprintf(info->stage_name[1], 24, "finish+mix+append");
+        std::snprintf(info->stage_name[1], 24, "strip+mix");
     } else {
         const uint64_t P = e->up.P;
         info->flops_per_block = 8 * T * P * (B + 1);
@@ -895,10 +1010,9 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
         info->fft_size = 2 * e->B;
         if (e->up.fused) {
             info->kernels_per_block = 1;
-            info->stage_count = 2;
+            info->stage_count = 1;
             info->dominant_stage = 0;
             std::snprintf(info->stage_name[0], 24, "upols_fused");
-            std::snprintf(info->stage_name[1], 24, "mix");
         } else {
             info->kernels_per_block = 3;
             std::snprintf(info->stage_name[0], 24, "rfft_fwd");

@@ -4,8 +4,11 @@
 // (IRs, bus gains and sample-major columns use the global track index — SURVEY.md §8e), one
 // persistent host thread per device that submits that device's work (so 8 GPUs are fed in
 // parallel, not 8 x launch latency in series), and ONE collective per block: the stereo bus
-// all-reduce, done by the engine's own P2P kernel (bus_allreduce.cu) over peer-mapped buffers
-// (cudaDeviceEnablePeerAccess; every device stores into every other device's slot over NVLink).
+// all-reduce, which every member engine performs INSIDE its last convolution kernel (bus_tree.cuh)
+// over peer-mapped buffers (cudaDeviceEnablePeerAccess + b200conv_attach_bus; every device stores
+// into every other device's slot over NVLink).  A member's block is exactly the single-GPU host call,
+// b200conv_process_host, on the member's slice of the caller's buffers: pinned buffers are read and
+// written in place over PCIe by the kernels, pageable ones take the staged copies.
 // The one-process-per-GPU variant of the same thing is bench.py + gpuaudiobench_b200/distributed.py.
 #include "../../include/b200conv.h"
 
@@ -39,12 +42,9 @@ struct Member {
     int device = 0;
     int t0 = 0, t1 = 0;  // global track range
     b200conv_engine* engine = nullptr;
-    cudaStream_t stream = nullptr;
-    float* d_in = nullptr;
-    float* d_out = nullptr;
-    float* d_mix = nullptr;
     float* bus_buf = nullptr;       // symmetric slot buffer of this device
-    uint32_t* d_err = nullptr;
+    float* h_mix = nullptr;         // pinned [2][B]: every member takes part in the exchange and needs a place for
+                                    // the (identical) result; member 0 writes the caller's buffer instead
     int rc = 0;
     std::string err;
     std::thread worker;
@@ -57,7 +57,6 @@ struct b200conv_group {
     int n = 0;
     std::vector<Member> members;
     std::vector<uint64_t> peer_ptrs;
-    uint32_t epoch = 0;
     // worker coordination
     std::mutex mu;
     std::condition_variable cv_go, cv_done;
@@ -69,52 +68,31 @@ struct b200conv_group {
 
 namespace {
 
-int member_submit(b200conv_group* g, Member& m, const Job& job, uint32_t epoch) {
-    const int T = m.t1 - m.t0, B = static_cast<int>(g->cfg.block), Tg = static_cast<int>(g->cfg.tracks);
-    const size_t tb = static_cast<size_t>(T) * B;
+int member_submit(b200conv_group* g, Member& m, const Job& job) {
+    const int B = static_cast<int>(g->cfg.block);
     const bool sample_major = g->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR;
     if (cudaSetDevice(m.device) != cudaSuccess) return B200CONV_ERR_CUDA;
-    if (cudaMemcpyAsync(m.d_in, job.h_in + static_cast<size_t>(m.t0) * B, tb * sizeof(float), cudaMemcpyHostToDevice, m.stream) != cudaSuccess)
-        return B200CONV_ERR_CUDA;
-    int rc = b200conv_process(m.engine, m.d_in, m.d_out, job.h_mix ? m.d_mix : nullptr, job.flags, m.stream);
-    if (rc) return rc;
-    if (job.h_mix) {
-        rc = b200conv_bus_allreduce(m.d_mix, m.d_mix, g->peer_ptrs.data(), static_cast<int>(&m - g->members.data()), g->n, 2 * B,
-                                    epoch, m.d_err, m.stream);
-        if (rc) return rc;
-    }
-    if (job.h_out) {
-        cudaError_t e;
-        if (sample_major)  // this member's column tile of the [B][Tg] matrix
-            e = cudaMemcpy2DAsync(job.h_out + m.t0, static_cast<size_t>(Tg) * sizeof(float), m.d_out + m.t0,
-                                  static_cast<size_t>(Tg) * sizeof(float), static_cast<size_t>(T) * sizeof(float), B,
-                                  cudaMemcpyDeviceToHost, m.stream);
-        else
-            e = cudaMemcpyAsync(job.h_out + static_cast<size_t>(m.t0) * B, m.d_out, tb * sizeof(float), cudaMemcpyDeviceToHost, m.stream);
-        if (e != cudaSuccess) return B200CONV_ERR_CUDA;
-    }
-    if (job.h_mix && m.t0 == 0)  // every rank holds the identical bus; member 0 returns it
-        if (cudaMemcpyAsync(job.h_mix, m.d_mix, static_cast<size_t>(2) * B * sizeof(float), cudaMemcpyDeviceToHost, m.stream) != cudaSuccess)
-            return B200CONV_ERR_CUDA;
-    if (cudaStreamSynchronize(m.stream) != cudaSuccess) return B200CONV_ERR_CUDA;
-    return B200CONV_OK;
+    float* out = nullptr;
+    if (job.h_out)  // sample-major: the engine writes its column tile of the full [B][Tg] matrix
+        out = sample_major ? job.h_out : job.h_out + static_cast<size_t>(m.t0) * B;
+    float* mix = nullptr;
+    if (job.h_mix) mix = (m.t0 == 0) ? job.h_mix : m.h_mix;  // every rank holds the identical bus; member 0 returns it
+    return b200conv_process_host(m.engine, job.h_in + static_cast<size_t>(m.t0) * B, out, mix, job.flags);
 }
 
 void worker_loop(b200conv_group* g, int idx) {
     uint64_t seen = 0;
     for (;;) {
         Job job;
-        uint32_t epoch;
         {
             std::unique_lock<std::mutex> lk(g->mu);
             g->cv_go.wait(lk, [&] { return g->stop || g->generation != seen; });
             if (g->stop) return;
             seen = g->generation;
             job = g->job;
-            epoch = g->epoch;
         }
         Member& m = g->members[idx];
-        m.rc = member_submit(g, m, job, epoch);
+        m.rc = member_submit(g, m, job);
         if (m.rc) m.err = b200conv_last_error();
         {
             std::lock_guard<std::mutex> lk(g->mu);
@@ -168,17 +146,11 @@ int b200conv_group_create(const b200conv_config* cfg, int n_gpus, b200conv_group
         c.total_tracks = static_cast<uint32_t>(Tg);
         if (int rc = b200conv_create(&c, &m.engine)) return bail(rc, b200conv_last_error());
         cudaSetDevice(i);
-        const size_t out_elems = (cfg->out_layout == B200CONV_OUT_SAMPLE_MAJOR) ? static_cast<size_t>(B) * Tg
-                                                                               : static_cast<size_t>(m.t1 - m.t0) * B;
         const size_t bus_bytes = b200conv_bus_buffer_bytes(n_gpus, 2 * B);
-        if (cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc(&m.d_in, static_cast<size_t>(m.t1 - m.t0) * B * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&m.d_out, out_elems * sizeof(float)) != cudaSuccess || cudaMalloc(&m.d_mix, 2 * B * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&m.bus_buf, bus_bytes) != cudaSuccess || cudaMalloc(&m.d_err, sizeof(uint32_t)) != cudaSuccess)
-            return bail(B200CONV_ERR_CUDA, "b200conv_group_create: device allocation failed");
+        if (cudaMalloc(&m.bus_buf, bus_bytes) != cudaSuccess ||
+            cudaMallocHost(&m.h_mix, static_cast<size_t>(2) * B * sizeof(float)) != cudaSuccess)
+            return bail(B200CONV_ERR_CUDA, "b200conv_group_create: allocation failed");
         cudaMemset(m.bus_buf, 0, bus_bytes);
-        cudaMemset(m.d_err, 0, sizeof(uint32_t));
-        cudaMemset(m.d_out, 0, out_elems * sizeof(float));
         cudaDeviceSynchronize();
         g->peer_ptrs.push_back(reinterpret_cast<uint64_t>(m.bus_buf));
     }
@@ -195,6 +167,9 @@ int b200conv_group_create(const b200conv_config* cfg, int n_gpus, b200conv_group
             cudaGetLastError();
         }
     }
+    if (n_gpus > 1)
+        for (int i = 0; i < n_gpus; ++i)
+            if (int rc = b200conv_attach_bus(g->members[i].engine, g->peer_ptrs.data(), i, n_gpus)) return bail(rc, b200conv_last_error());
     for (int i = 0; i < n_gpus; ++i) g->members[i].worker = std::thread(worker_loop, g, i);
     *out = g;
     return B200CONV_OK;
@@ -212,12 +187,8 @@ void b200conv_group_destroy(b200conv_group* g) {
         cudaSetDevice(m.device);
         cudaDeviceSynchronize();
         b200conv_destroy(m.engine);
-        if (m.stream) cudaStreamDestroy(m.stream);
-        cudaFree(m.d_in);
-        cudaFree(m.d_out);
-        cudaFree(m.d_mix);
         cudaFree(m.bus_buf);
-        cudaFree(m.d_err);
+        if (m.h_mix) cudaFreeHost(m.h_mix);
     }
     delete g;
 }
@@ -270,7 +241,6 @@ int b200conv_group_process_host(b200conv_group* g, const float* h_in, float* h_o
     {
         std::lock_guard<std::mutex> lk(g->mu);
         g->job = Job{h_in, h_out, h_mix, flags};
-        if (h_mix) g->epoch += 1;
         g->pending = g->n;
         g->generation += 1;
     }
@@ -281,14 +251,6 @@ int b200conv_group_process_host(b200conv_group* g, const float* h_in, float* h_o
     }
     for (Member& m : g->members)
         if (m.rc) return gfail(m.rc, "GPU " + std::to_string(m.device) + ": " + m.err);
-    if (h_mix) {
-        for (Member& m : g->members) {
-            uint32_t err = 0;
-            cudaSetDevice(m.device);
-            cudaMemcpy(&err, m.d_err, sizeof(err), cudaMemcpyDeviceToHost);
-            if (err) return gfail(B200CONV_ERR_CUDA, "bus all-reduce: a peer did not signal within the spin bound");
-        }
-    }
     return B200CONV_OK;
 }
 

@@ -123,19 +123,24 @@ __global__ void __launch_bounds__(256) rfft_fwd_kernel(RfftParams p, int TX, int
     if (active) {
         const float2* f2 = p.first ? reinterpret_cast<const float2*>(p.first + static_cast<size_t>(w) * p.first_stride) : nullptr;
         const float2* s2 = p.second ? reinterpret_cast<const float2*>(p.second + static_cast<size_t>(w) * p.second_stride) : nullptr;
-        float2* prev2 = p.prev_out ? reinterpret_cast<float2*>(p.prev_out + static_cast<size_t>(w) * M) : nullptr;
         for (int n = tx; n < M; n += TX) {
             float2 v = make_float2(0.0f, 0.0f);
             if (n < half) {
                 if (f2) v = f2[n];
             } else {
                 if (s2) v = s2[n - half];
-                if (prev2) prev2[n - half] = v;
             }
             a[n] = v;
         }
     }
     __syncthreads();
+    // prev_out may alias `first` (the engine's previous-buffer row): write it only after every lane of the
+    // window has read its half — for M < 64 the reader of f2[k] and the writer of prev2[k] are different
+    // lanes of one warp on divergent sides of the branch above.  The first FFT pass only reads a.
+    if (active && p.prev_out) {
+        float2* prev2 = reinterpret_cast<float2*>(p.prev_out + static_cast<size_t>(w) * M);
+        for (int n = tx; n < half; n += TX) prev2[n] = a[n + half];
+    }
     const float2* z = fft_stockham<false>(a, b, M, p.logM, tx, TX, active);
     if (!active) return;
 
@@ -511,15 +516,19 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(FusedParams 
             }
         }
     }
+    if (p.bus.mix) {
+        // stereo bus: this track's row goes to the tree's scratch; the last track of a group / the last
+        // group sums, and on a multi-GPU job exchanges the bus over NVLink (bus_tree.cuh) — no further launch
+        float2* yb = reinterpret_cast<float2*>(p.bus.ybus + static_cast<size_t>(t) * M);
+        for (int n = tid; n < half; n += 256) yb[n] = z[half + n];
+        bus_tree_arrive(p.bus, t, 0, tid, 256, 0, &s_last);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------
-static cudaError_t ensure_fft_smem(const void* fn, size_t smem) {
-    if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-}
+static cudaError_t ensure_fft_smem(const void* fn, size_t smem) { return ensure_dyn_smem(fn, smem); }
 
 cudaError_t launch_rfft_fwd(const RfftParams& p, cudaStream_t st) {
     const int TX = fft_threads_per_window(p.M);

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include "bus_tree.cuh"
 #include "strip.cuh"
 #include <stddef.h>
 
@@ -61,6 +62,7 @@ struct FusedParams {
     int sample_major, Tg, toff;
     StripParams strip;    // strip.ops != 0: the last CTA of a track runs the channel strip on its B output samples
                           // in shared memory before writing them (in/out/T/B/layout fields unused here)
+    BusTreeParams bus;    // bus.mix != null: the stereo bus (and its multi-GPU sum) as an epilogue of this launch
 };
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st);
 constexpr int kFusedMaxM = 512;

@@ -46,9 +46,63 @@ def stitch_sample_major(column_tiles, total_tracks):
     return out
 
 
+class EngineBusGroup:
+    """One engine per rank, each owning a contiguous track range of the same job: after construction the
+    mix bus every engine's process call delivers is already the sum over ALL ranks — the exchange runs
+    inside the engine's last convolution kernel over NVLink peer memory (b200conv_attach_bus,
+    csrc/bus_tree.cuh).  torch.distributed._symmetric_memory supplies the peer mappings.  If symmetric
+    memory cannot be set up (gloo in the CPU tests, no P2P) the engine stays stand-alone and `reduce()`
+    falls back to the NCCL / gloo all-reduce of the local bus; `.kind` says which."""
+
+    def __init__(self, engine, bus, group=None, force_nccl=False):
+        self.engine, self.bus, self.group = engine, bus, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.kind = "none (1 rank)" if self.world == 1 else "NCCL all-reduce after the engine's launch"
+        self.in_kernel = False
+        if self.world == 1 or force_nccl or not bus.is_cuda:
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            from . import engine as eng_mod
+            nbytes = eng_mod.bus_buffer_bytes(self.world, bus.numel())
+            self.buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=bus.device)
+            self.buf.zero_()
+            grp = group if group is not None else dist.group.WORLD
+            self.hdl = symm_mem.rendezvous(self.buf, grp.group_name if hasattr(grp, "group_name") else grp)
+            torch.cuda.synchronize(bus.device)
+            dist.barrier(group)  # every rank's buffer is zeroed before the first push
+            engine.attach_bus([int(p) for p in self.hdl.buffer_ptrs], self.rank, self.world)
+            self.in_kernel = True
+            self.kind = ("in-kernel: the engine's last convolution kernel pushes the bus over NVLink symmetric memory "
+                         "and sums in rank order (b200conv_attach_bus)")
+        except Exception as exc:  # pragma: no cover - depends on the box
+            self.kind = f"NCCL all-reduce after the engine's launch (symmetric memory unavailable: {type(exc).__name__}: {exc})"
+
+    def reduce(self):
+        """Call after engine.process on the same stream: a no-op when the exchange ran inside the kernel."""
+        if self.world > 1 and not self.in_kernel:
+            dist.all_reduce(self.bus, op=dist.ReduceOp.SUM, group=self.group)
+        return self.bus
+
+    def check(self):
+        if self.in_kernel:
+            self.engine.bus_status()
+
+    def close(self):
+        if self.in_kernel:
+            torch.cuda.synchronize(self.bus.device)
+            dist.barrier(self.group)  # nobody unmaps a buffer a peer may still push into
+            self.engine.attach_bus(None, 0, 1)
+            self.in_kernel = False
+
+
 class BusAllReduce:
     """All-reduce of the stereo bus [2][B] across the ranks of `group`.
 
+    (The engines do this inside their last kernel — see EngineBusGroup; this class reduces a bus the
+    caller owns, and is what the stand-alone kernel's tests drive.)
     Preferred path: the engine's own one-shot kernel (csrc/bus_allreduce.cu) over a symmetric
     peer-mapped buffer obtained from torch.distributed._symmetric_memory — P2P stores + flags over
     NVLink, one launch, fixed summation order.  If symmetric memory cannot be set up (e.g. gloo in

@@ -82,6 +82,8 @@ def load_library():
     L.b200conv_bus_buffer_bytes.restype = C.c_size_t
     L.b200conv_bus_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
                                          C.c_uint32, C.c_void_p, C.c_void_p]
+    L.b200conv_attach_bus.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+    L.b200conv_bus_status.argtypes = [C.c_void_p]
     L.b200conv_group_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]
     L.b200conv_group_destroy.argtypes = [C.c_void_p]
     L.b200conv_group_destroy.restype = None
@@ -128,6 +130,10 @@ def measure_fp32_peak(device=0):
 def rfft(d_in, d_out, count, n, stream=0):
     """Batched R2C FFT on device buffers (addresses): d_out float2 [count][n/2+1]."""
     _check(load_library().b200conv_rfft(C.c_void_p(d_in), C.c_void_p(d_out), count, n, C.c_void_p(stream) if stream else None))
+
+
+def bus_buffer_bytes(world, n):
+    return load_library().b200conv_bus_buffer_bytes(world, n)
 
 
 def _host_ptr(a):
@@ -329,6 +335,18 @@ class ConvEngine:
         d["stage_ms"] = list(info.stage_ms)
         d["stage_name"] = [bytes(info.stage_name[i]).split(b"\0")[0].decode() for i in range(4)]
         return d
+
+    def attach_bus(self, peer_ptrs, rank, world):
+        """Join a bus group (b200conv_attach_bus): peer_ptrs[p] = address on this device of rank p's symmetric
+        buffer of bus_buffer_bytes(world, 2*B) bytes.  peer_ptrs None / world <= 1 detaches."""
+        if not peer_ptrs or world <= 1:
+            _check(self.lib.b200conv_attach_bus(self.handle, None, 0, 1))
+            return
+        arr = (C.c_uint64 * world)(*[int(p) for p in peer_ptrs])
+        _check(self.lib.b200conv_attach_bus(self.handle, arr, rank, world))
+
+    def bus_status(self):
+        _check(self.lib.b200conv_bus_status(self.handle))
 
     def set_profiling(self, on):
         _check(self.lib.b200conv_set_profiling(self.handle, 1 if on else 0))

@@ -12,8 +12,12 @@
  * (thread-local).  One engine per device, not thread-safe per handle.  The caller owns the I/O
  * buffers; the engine owns IR tables, input history / frequency-domain delay line and workspace.
  * All device work of b200conv_process is enqueued on the caller's cudaStream_t (passed as void*
- * so the header needs no CUDA include).  There is no CPU fallback: without a CUDA device
- * b200conv_create fails with B200CONV_ERR_NO_DEVICE.
+ * so the header needs no CUDA include).  Devices: every call that takes an engine runs on the engine's
+ * cfg.device (it selects it for the duration of the call) and leaves the calling thread's current device
+ * as it found it, so engines on different devices can be driven from one thread; the stream passed to
+ * b200conv_process must belong to the engine's device (NULL = that device's default stream).  The
+ * stateless calls (b200conv_rfft, b200conv_strip_process) run on the caller's current device.
+ * There is no CPU fallback: without a CUDA device b200conv_create fails with B200CONV_ERR_NO_DEVICE.
  *
  * Data layouts:
  *   input   float [T][B]  track-major                       (cuda/bench_base.cu:30-35 upload)
@@ -205,6 +209,22 @@ int b200conv_strip_process(const float* d_in, float* d_out, uint32_t tracks, uin
 size_t b200conv_bus_buffer_bytes(int world, int n);
 int b200conv_bus_allreduce(const float* d_local, float* d_out, const uint64_t* peer_buffers, int rank, int world,
                            int n, uint32_t epoch, uint32_t* d_error_flag, void* stream);
+
+/* Make engine `rank` of `world` engines (one per GPU, each owning a contiguous track range of the same
+ * job: cfg.track_offset / total_tracks) a member of a bus group.  From then on the mix bus that
+ * b200conv_process / b200conv_process_host deliver is the sum over ALL engines: the kernel that finishes
+ * the last track of a block pushes the local bus into every peer's buffer over NVLink, waits for the
+ * peers' flags and adds the `world` partials in rank order — inside the convolution launch, no further
+ * kernel, bit-identical on every rank.  Every engine of the group must then process the same sequence of
+ * blocks with a bus (d_mix / h_mix != NULL), PEEK blocks included.  peer_buffers[p]: address, valid on
+ * THIS engine's device, of rank p's zero-initialised buffer of b200conv_bus_buffer_bytes(world, 2*B)
+ * bytes (as for b200conv_bus_allreduce).  peer_buffers == NULL or world <= 1 detaches.
+ * No reference counterpart (the reference is single-GPU). */
+int b200conv_attach_bus(b200conv_engine* e, const uint64_t* peer_buffers, int rank, int world);
+/* Synchronises the engine's stream; B200CONV_ERR_CUDA if a peer missed a bus exchange since the last
+ * call (bounded spin, a few seconds: the kernel gives up instead of hanging the GPU), else B200CONV_OK.
+ * b200conv_process_host checks this itself on every block. */
+int b200conv_bus_status(b200conv_engine* e);
 
 /* ---- multi-GPU in one process: one engine per GPU over contiguous track ranges -------------------
  * cfg->tracks is the TOTAL track count Tg (cfg->device / track_offset / total_tracks are ignored);
