@@ -10,7 +10,9 @@
 //            ybus[t][..] (device scratch, track-major) and calls bus_tree_arrive();
 //   level 1  tracks are grouped G1 at a time; the LAST arriver of a (group, chunk) sums the group's
 //            rows in track order -> gpart[group][c][n];
-//   level 2  the LAST group of a chunk sums the group partials in group order -> the local bus chunk;
+//   level 2  tree (direct FIR, whose tracks all finish at the end): the LAST group of a chunk sums the group
+//            partials in group order;  chain (UPOLS, whose tracks finish progressively): every group is folded,
+//            in group order, into a running bus as it completes -> the local bus chunk;
 //   level 3  (world > 1) that CTA pushes the chunk into its slot of EVERY peer's symmetric buffer over
 //            NVLink (plain P2P stores), fences, raises its flag on every peer, acquire-polls the
 //            world flags of its own buffer and adds the world slots in rank order.
@@ -38,13 +40,18 @@ constexpr unsigned kBusSpinLimit = 1u << 22;  // bounded wait for a peer (system
 struct BusTreeParams {
     const float* gains;  // [T][2]
     float* ybus;         // [T][B] rows the bus is summed from (track-major, device memory)
-    float* gpart;        // [NG][2][B]
+    float4* gpart;       // [NG][B/2] group partials, one float4 {l0, r0, l1, r1} per column pair
     unsigned* gcount;    // [NG][NC] arrival tickets, zero between launches
-    unsigned* ccount;    // [NC]
+    unsigned* ccount;    // [NC] tree: group tickets;  chain: number of groups already folded into `running`
+    float4* running;     // [B/2] chain: the bus of groups 0 .. seq-1
     float* mix;          // [2][B] destination (device, or pinned host); null: no bus wanted, tree disabled
     int T, B;
     int G1, NG;          // tracks per group, groups
     int CH, NC;          // columns per chunk, chunks
+    int chain;           // 0: the last group to arrive adds the NG partials (kernels whose tracks all finish at the
+                         //    end: direct FIR).  1: groups are folded in group order into a running bus as they finish
+                         //    (kernels whose tracks finish progressively: UPOLS) — after the last track only its own
+                         //    group's sum and one add remain on the critical path
     // multi-GPU exchange (world == 1: none)
     float* peers[kBusMaxWorld];
     int rank, world;
@@ -61,32 +68,45 @@ __device__ __forceinline__ uint32_t bus_ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t bus_ld_acquire_gpu(const unsigned* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void bus_bar(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// All-reduce of the local bus chunk held in registers by threads tid < ... (columns col = tid + i*nthr):
-// called by every thread of the arriving group.  `l`/`r` callbacks are avoided: the local chunk is first
-// written to this rank's own slot like everybody else's, then summed in rank order.
-__device__ __forceinline__ void bus_exchange_chunk(const BusTreeParams& bt, int chunk, int tid, int nthr, uint32_t bar_id) {
+// Every level is "data, barrier, ONE thread fences and takes the ticket, barrier" — the barrier orders the other
+// threads' stores before thread 0's fence (cumulativity; the pattern of cooperative-groups grid sync), which
+// keeps 255 redundant membars off the critical path.  Loads of a level are issued in batches (all in flight,
+// then added in the fixed order): the tail after the last track is a chain of L2 round trips, not of bytes.
+
+// The chunk's final local bus {l0, r0, l1, r1} of this thread's column pair -> mix, or over NVLink first.
+__device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int chunk, int pair, bool active, float4 v,
+                                                 int tid, int nthr, uint32_t bar_id) {
+    const int col = chunk * bt.CH + 2 * pair;
+    if (bt.world == 1) {
+        if (active) {
+            *reinterpret_cast<float2*>(bt.mix + col) = make_float2(v.x, v.z);
+            *reinterpret_cast<float2*>(bt.mix + bt.B + col) = make_float2(v.y, v.w);
+        }
+        return;
+    }
     const int n = 2 * bt.B;
     const int slot = bt.epoch & 1u;
     const size_t data_floats = static_cast<size_t>(2) * bt.world * n;
-    const int c0 = chunk * bt.CH;
-    // push: my chunk sits in my own slot already (written by the caller); copy it to every peer
-    const float* mine = bt.peers[bt.rank] + (static_cast<size_t>(slot) * bt.world + bt.rank) * n;
-    for (int col = tid; col < bt.CH; col += nthr) {
-        const float l = mine[c0 + col], r = mine[bt.B + c0 + col];
+    const size_t my_off = (static_cast<size_t>(slot) * bt.world + bt.rank) * n;
+    if (active) {  // push: my chunk into my slot of EVERY rank's buffer (mine included), straight from registers
         for (int p = 0; p < bt.world; ++p) {
-            if (p == bt.rank) continue;
-            float* dst = bt.peers[p] + (static_cast<size_t>(slot) * bt.world + bt.rank) * n;
-            dst[c0 + col] = l;
-            dst[bt.B + c0 + col] = r;
+            float* dst = bt.peers[p] + my_off;
+            *reinterpret_cast<float2*>(dst + col) = make_float2(v.x, v.z);
+            *reinterpret_cast<float2*>(dst + bt.B + col) = make_float2(v.y, v.w);
         }
     }
-    __threadfence_system();
     bus_bar(bar_id, nthr);
-    if (tid < bt.world) {
+    if (tid < bt.world) {  // signal rank `tid`, then wait for rank `tid`'s signal
+        __threadfence_system();
         uint32_t* peer_flags = reinterpret_cast<uint32_t*>(bt.peers[tid] + data_floats);
         bus_st_release_sys(peer_flags + (slot * bt.world + bt.rank) * kBusMaxChunks + chunk, bt.epoch);
         const uint32_t* my_flags = reinterpret_cast<const uint32_t*>(bt.peers[bt.rank] + data_floats);
@@ -99,111 +119,142 @@ __device__ __forceinline__ void bus_exchange_chunk(const BusTreeParams& bt, int 
         }
     }
     bus_bar(bar_id, nthr);
-    const float* base = bt.peers[bt.rank] + static_cast<size_t>(slot) * bt.world * n;
-    for (int col = tid; col < bt.CH; col += nthr) {
-        float l = 0.0f, r = 0.0f;
-        for (int q = 0; q < bt.world; ++q) {
-            l += __ldcg(base + static_cast<size_t>(q) * n + c0 + col);
-            r += __ldcg(base + static_cast<size_t>(q) * n + bt.B + c0 + col);
+    if (active) {  // fixed rank order: every rank computes the bit-identical sum
+        const float* base = bt.peers[bt.rank] + static_cast<size_t>(slot) * bt.world * n;
+        float2 l = make_float2(0.0f, 0.0f), r = make_float2(0.0f, 0.0f);
+        for (int q0 = 0; q0 < bt.world; q0 += 8) {
+            float2 vl[8], vr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool ok = q0 + j < bt.world;
+                vl[j] = ok ? __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(q0 + j) * n + col)) : make_float2(0.0f, 0.0f);
+                vr[j] = ok ? __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(q0 + j) * n + bt.B + col)) : make_float2(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (q0 + j < bt.world) {
+                    l.x += vl[j].x; l.y += vl[j].y;
+                    r.x += vr[j].x; r.y += vr[j].y;
+                }
+            }
         }
-        bt.mix[c0 + col] = l;
-        bt.mix[bt.B + c0 + col] = r;
+        *reinterpret_cast<float2*>(bt.mix + col) = l;
+        *reinterpret_cast<float2*>(bt.mix + bt.B + col) = r;
     }
 }
 
 // Called by all `nthr` threads of the arriving group (tid = 0 .. nthr-1; they synchronise on hardware
 // barrier `bar_id`) after they have written ybus[t][chunk*CH .. +CH).  `flag` is one int of shared memory.
+// Thread `tid` owns the column pair (2 tid, 2 tid + 1) of the chunk; nthr >= CH/2 is required.
 __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, int chunk, int tid, int nthr,
                                                 uint32_t bar_id, int* flag) {
     const int g = t / bt.G1;
     const int gsize = min(bt.G1, bt.T - g * bt.G1);
     const int c0 = chunk * bt.CH;
+    const int pair = tid;
+    const bool active = (2 * pair < bt.CH);
     // ---- level 1: last arriver of (group, chunk) ----
-    __threadfence();
     bus_bar(bar_id, nthr);
     if (tid == 0) {
-        unsigned* cnt = bt.gcount + g * bt.NC + chunk;
-        const unsigned ticket = (gsize > 1) ? atomicAdd(cnt, 1u) : 0u;
-        const int last = (ticket == static_cast<unsigned>(gsize) - 1u);
-        if (last && gsize > 1) *cnt = 0;  // re-armed for the next launch
+        int last = 1;
+        if (gsize > 1) {
+            __threadfence();
+            unsigned* cnt = bt.gcount + g * bt.NC + chunk;
+            last = (atomicAdd(cnt, 1u) == static_cast<unsigned>(gsize) - 1u);
+            if (last) {
+                *cnt = 0;  // re-armed for the next launch
+                __threadfence();
+            }
+        }
         *flag = last;
     }
     bus_bar(bar_id, nthr);
     if (!*flag) return;
-    __threadfence();
-    const bool single_group = (bt.NG == 1);
-    float* my_slot = nullptr;
-    if (bt.world > 1)
-        my_slot = bt.peers[bt.rank] + (static_cast<size_t>(bt.epoch & 1u) * bt.world + bt.rank) * (2 * bt.B);
-    for (int col = tid; col < bt.CH; col += nthr) {
-        float l = 0.0f, r = 0.0f;
-        const float* row = bt.ybus + static_cast<size_t>(g) * bt.G1 * bt.B + c0 + col;
+    float4 part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // {l0, r0, l1, r1}
+    if (active) {
+        const float* row = bt.ybus + static_cast<size_t>(g) * bt.G1 * bt.B + c0 + 2 * pair;
         const float2* gn = reinterpret_cast<const float2*>(bt.gains) + g * bt.G1;
-        int tt = 0;
-        for (; tt + 4 <= gsize; tt += 4) {  // loads of four rows in flight, adds in track order
-            const float v0 = __ldcg(row + static_cast<size_t>(tt) * bt.B);
-            const float v1 = __ldcg(row + static_cast<size_t>(tt + 1) * bt.B);
-            const float v2 = __ldcg(row + static_cast<size_t>(tt + 2) * bt.B);
-            const float v3 = __ldcg(row + static_cast<size_t>(tt + 3) * bt.B);
-            const float2 g0 = gn[tt], g1 = gn[tt + 1], g2 = gn[tt + 2], g3 = gn[tt + 3];
-            l = fmaf(g0.x, v0, l); r = fmaf(g0.y, v0, r);
-            l = fmaf(g1.x, v1, l); r = fmaf(g1.y, v1, r);
-            l = fmaf(g2.x, v2, l); r = fmaf(g2.y, v2, r);
-            l = fmaf(g3.x, v3, l); r = fmaf(g3.y, v3, r);
+        for (int t0 = 0; t0 < gsize; t0 += 16) {  // 16 rows in flight, then the adds in track order
+            float2 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                v[j] = (t0 + j < gsize) ? __ldcg(reinterpret_cast<const float2*>(row + static_cast<size_t>(t0 + j) * bt.B))
+                                        : make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (t0 + j < gsize) {
+                    const float2 gg = gn[t0 + j];
+                    part.x = fmaf(gg.x, v[j].x, part.x);
+                    part.y = fmaf(gg.y, v[j].x, part.y);
+                    part.z = fmaf(gg.x, v[j].y, part.z);
+                    part.w = fmaf(gg.y, v[j].y, part.w);
+                }
+            }
         }
-        for (; tt < gsize; ++tt) {
-            const float v = __ldcg(row + static_cast<size_t>(tt) * bt.B);
-            const float2 gg = gn[tt];
-            l = fmaf(gg.x, v, l);
-            r = fmaf(gg.y, v, r);
-        }
-        if (single_group) {
-            if (bt.world == 1) {
-                bt.mix[c0 + col] = l;
-                bt.mix[bt.B + c0 + col] = r;
-            } else {
-                my_slot[c0 + col] = l;
-                my_slot[bt.B + c0 + col] = r;
+    }
+    if (bt.NG > 1) {
+        const size_t hp = static_cast<size_t>(bt.B) >> 1;  // column pairs per bus row
+        if (!bt.chain) {
+            // ---- level 2, tree: the last group of the chunk adds the NG partials in group order ----
+            if (active) bt.gpart[static_cast<size_t>(g) * hp + (c0 >> 1) + pair] = part;
+            bus_bar(bar_id, nthr);
+            if (tid == 0) {
+                __threadfence();
+                const int last = (atomicAdd(bt.ccount + chunk, 1u) == static_cast<unsigned>(bt.NG) - 1u);
+                if (last) {
+                    bt.ccount[chunk] = 0;
+                    __threadfence();
+                }
+                *flag = last;
+            }
+            bus_bar(bar_id, nthr);
+            if (!*flag) return;
+            part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (active) {
+                const float4* gp = bt.gpart + (c0 >> 1) + pair;
+                for (int g0 = 0; g0 < bt.NG; g0 += 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        v[j] = (g0 + j < bt.NG) ? __ldcg(gp + static_cast<size_t>(g0 + j) * hp) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (g0 + j < bt.NG) {
+                            part.x += v[j].x; part.y += v[j].y; part.z += v[j].z; part.w += v[j].w;
+                        }
+                    }
+                }
             }
         } else {
-            bt.gpart[(static_cast<size_t>(g) * 2) * bt.B + c0 + col] = l;
-            bt.gpart[(static_cast<size_t>(g) * 2 + 1) * bt.B + c0 + col] = r;
-        }
-    }
-    if (!single_group) {
-        // ---- level 2: last group of the chunk ----
-        __threadfence();
-        bus_bar(bar_id, nthr);
-        if (tid == 0) {
-            const unsigned ticket = atomicAdd(bt.ccount + chunk, 1u);
-            const int last = (ticket == static_cast<unsigned>(bt.NG) - 1u);
-            if (last) bt.ccount[chunk] = 0;
-            *flag = last;
-        }
-        bus_bar(bar_id, nthr);
-        if (!*flag) return;
-        __threadfence();
-        for (int col = tid; col < bt.CH; col += nthr) {
-            float l = 0.0f, r = 0.0f;
-            for (int gg = 0; gg < bt.NG; ++gg) {
-                l += __ldcg(bt.gpart + (static_cast<size_t>(gg) * 2) * bt.B + c0 + col);
-                r += __ldcg(bt.gpart + (static_cast<size_t>(gg) * 2 + 1) * bt.B + c0 + col);
+            // ---- level 2, chain: fold this group into the running bus when groups 0 .. g-1 are in ----
+            if (tid == 0) {
+                unsigned spins = 0;
+                while (bus_ld_acquire_gpu(bt.ccount + chunk) != static_cast<unsigned>(g)) {
+                    if (++spins > kBusSpinLimit) {
+                        *reinterpret_cast<volatile uint32_t*>(bt.err) = 2u;
+                        break;
+                    }
+                }
+                __threadfence();
             }
-            if (bt.world == 1) {
-                bt.mix[c0 + col] = l;
-                bt.mix[bt.B + c0 + col] = r;
-            } else {
-                my_slot[c0 + col] = l;
-                my_slot[bt.B + c0 + col] = r;
+            bus_bar(bar_id, nthr);
+            if (active && g > 0) {
+                const float4 run = __ldcg(bt.running + (c0 >> 1) + pair);
+                part.x += run.x; part.y += run.y; part.z += run.z; part.w += run.w;
             }
+            if (g < bt.NG - 1) {
+                if (active) bt.running[(c0 >> 1) + pair] = part;
+                bus_bar(bar_id, nthr);
+                if (tid == 0) {
+                    __threadfence();
+                    atomicExch(bt.ccount + chunk, static_cast<unsigned>(g) + 1u);
+                }
+                return;
+            }
+            if (tid == 0) bt.ccount[chunk] = 0;  // last group: re-armed for the next launch
         }
     }
-    if (bt.world > 1) {
-        // ---- level 3: NVLink exchange of this chunk ----
-        __threadfence();
-        bus_bar(bar_id, nthr);
-        bus_exchange_chunk(bt, chunk, tid, nthr, bar_id);
-    }
+    bus_finish_chunk(bt, chunk, pair, active, part, tid, nthr, bar_id);
 }
 #endif  // __CUDACC__
 

@@ -96,7 +96,7 @@ __host__ __device__ __forceinline__ long long fir_cta_of_unit(long long u, long 
 }
 
 template <int A>
-__global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(FirParams p) {
+__global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(const __grid_constant__ FirParams p) {
     constexpr int CL = 32 / A;  // tap groups per warp
     constexpr int OT = A * 16;  // outputs per tile
     constexpr bool kSwzTaps = (CL > 1);
@@ -261,27 +261,35 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
 #pragma unroll
                     for (int i = 0; i < VPT; ++i)
                         if (tid + i * NC < OT) dstrow[tid + i * NC] = v[i];
-                    __threadfence();
-                    named_bar_sync(1, NC);
+                    named_bar_sync(1, NC);  // orders every thread's row stores before thread 0's fence (cumulativity)
                     if (tid == 0) {
+                        __threadfence();
                         unsigned* cnt = p.tcount + t * p.ntiles + ot;
-                        const unsigned ticket = atomicAdd(cnt, 1u);
-                        const int last = (ticket == static_cast<unsigned>(nseg) - 1u);
-                        if (last) *cnt = 0;  // re-armed for the next launch
+                        const int last = (atomicAdd(cnt, 1u) == static_cast<unsigned>(nseg) - 1u);
+                        if (last) {
+                            *cnt = 0;  // re-armed for the next launch
+                            __threadfence();
+                        }
                         s_flag = last;
                     }
                     named_bar_sync(1, NC);
                     finish = (s_flag != 0);
                     if (finish) {
-                        __threadfence();
-                        // every row (the own one too) is read back in segment order: the sum does not
-                        // depend on which CTA happened to arrive last
+                        // every row (the own one too) is read back in segment order, all loads in flight before
+                        // the first add: the sum does not depend on which CTA happened to arrive last
 #pragma unroll
                         for (int i = 0; i < VPT; ++i) {
                             const int o = tid + i * NC;
                             if (o < OT) {
-                                float sum = __ldcg(p.partial + tile_off + o);
-                                for (int sgm = 1; sgm < nseg; ++sgm)
+                                float rows[kFirMaxSegRows];
+#pragma unroll
+                                for (int sgm = 0; sgm < kFirMaxSegRows; ++sgm)
+                                    rows[sgm] = (sgm < nseg) ? __ldcg(p.partial + static_cast<size_t>(sgm) * p.T * p.B + tile_off + o) : 0.0f;
+                                float sum = rows[0];
+#pragma unroll
+                                for (int sgm = 1; sgm < kFirMaxSegRows; ++sgm)
+                                    if (sgm < nseg) sum += rows[sgm];
+                                for (int sgm = kFirMaxSegRows; sgm < nseg; ++sgm)  // (not reached by the planner's schedules)
                                     sum += __ldcg(p.partial + static_cast<size_t>(sgm) * p.T * p.B + tile_off + o);
                                 v[i] = sum;
                             }
@@ -289,17 +297,23 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
                     }
                 }
                 if (finish) {
-                    // ---- tile epilogue: output, ring append, bus ----
+                    // ---- tile epilogue.  The bus first: its tickets and L2 round trips are the critical path after
+                    // the last tile, so nothing slow (cold d_in reads, PCIe stores of a host-resident output) may sit
+                    // in front of its fence; output and ring append follow ----
+                    if (p.bus.mix) {
+#pragma unroll
+                        for (int i = 0; i < VPT; ++i)
+                            if (tid + i * NC < OT) p.bus.ybus[tile_off + tid + i * NC] = v[i];
+                        bus_tree_arrive(p.bus, t, ot, tid, NC, 1, &s_flag);
+                    }
 #pragma unroll
                     for (int i = 0; i < VPT; ++i) {
                         const int o = tid + i * NC;
                         if (o < OT) {
-                            const int n = ot * OT + o;
                             if (p.sample_major)
-                                p.out[static_cast<size_t>(n) * p.Tg + p.toff + t] = v[i];
+                                p.out[static_cast<size_t>(ot * OT + o) * p.Tg + p.toff + t] = v[i];
                             else
                                 p.out[tile_off + o] = v[i];
-                            if (p.bus.mix) p.bus.ybus[tile_off + o] = v[i];
                         }
                     }
                     if (p.ring_w) {  // ring[t][swz(pos + n)] = in[t][n] for this tile's columns, one float4 per thread
@@ -308,7 +322,6 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
                         const uint32_t f0 = static_cast<uint32_t>(p.pos + ot * OT) >> 2;
                         for (int c = tid; c < OT / 4; c += NC) ring4[swz_chunk(f0 + c)] = src[c];
                     }
-                    if (p.bus.mix) bus_tree_arrive(p.bus, t, ot, tid, NC, 1, &s_flag);
                 }
             }
             if (++k == p.NS) {

@@ -20,6 +20,7 @@ constexpr int kFirMaxStages = 8;                          // mbarrier slots rese
 constexpr int kFirCtasPerSm = B200CONV_FIR_CTAS_PER_SM;   // persistent grid = kFirCtasPerSm * SM count
 constexpr size_t kFirMaxSmem = (kFirCtasPerSm >= 3 ? 74 : 112) * 1024;  // per CTA; kFirCtasPerSm CTAs fit in 227 KB
 constexpr int kMixChunk = 8;                              // tracks a warp handles per step of the bus/finish kernels
+constexpr int kFirMaxSegRows = 4;                         // partial rows of a shared tile loaded in one batch (planner: MS <= 4)
 constexpr int kBusWarps = 4;                              // warps per CTA of the bus/finish kernels
 
 // All "block" quantities are in units of 16 floats (64 B).

@@ -99,7 +99,7 @@ struct b200conv_engine {
     float* d_gains = nullptr;
     // stereo-bus tree (bus_tree.cuh): scratch rows, group partials, tickets
     float* d_ybus = nullptr;      // [T][B]
-    float* d_gpart = nullptr;     // [NG][2][B]
+    float4* d_gpart = nullptr;    // [NG + 1][B/2] {l0, r0, l1, r1}; the last row is the chain's running bus
     unsigned* d_gcount = nullptr; // [NG][NC]
     unsigned* d_ccount = nullptr; // [NC]
     int bus_G1 = 1, bus_NG = 1, bus_CH = 0, bus_NC = 1;
@@ -291,6 +291,8 @@ BusTreeParams bus_params(const b200conv_engine* e, float* d_mix) {
     b.gpart = e->d_gpart;
     b.gcount = e->d_gcount;
     b.ccount = e->d_ccount;
+    b.running = e->d_gpart + static_cast<size_t>(e->bus_NG) * (e->B / 2);
+    b.chain = (e->cfg.algo == B200CONV_ALGO_UPOLS) ? 1 : 0;  // UPOLS tracks finish progressively, FIR tiles all at the end
     b.T = e->T;
     b.B = e->B;
     b.G1 = e->bus_G1;
@@ -440,7 +442,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         }
         if (e->bus_NC > kBusMaxChunks) return bail(fail(B200CONV_ERR_INVALID, "b200conv_create: block too large for the bus tree"));
         if ((rc = dev_alloc(e, &e->d_ybus, tb))) return bail(rc);
-        if ((rc = dev_alloc(e, &e->d_gpart, static_cast<size_t>(e->bus_NG) * 2 * e->B))) return bail(rc);
+        if ((rc = dev_alloc(e, &e->d_gpart, static_cast<size_t>(e->bus_NG + 1) * (e->B / 2)))) return bail(rc);
         if ((rc = dev_alloc(e, &e->d_gcount, static_cast<size_t>(e->bus_NG) * e->bus_NC))) return bail(rc);
         if ((rc = dev_alloc(e, &e->d_ccount, static_cast<size_t>(e->bus_NC)))) return bail(rc);
         err = cudaHostAlloc(reinterpret_cast<void**>(&e->d_bus_err), sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable);

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 constexpr int kPrefetchParts = B200CONV_FUSED_PREFETCH;  // partitions pulled into L2 under the forward FFT
 
 template <int kFusedUnroll, int kMinCtas, bool kStrip>
-__global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(FusedParams p) {
+__global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
     __shared__ int s_last;
     const int M = p.M, half = M >> 1, U = M >> 1, G = 256 / U;
@@ -501,6 +501,14 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(FusedParams 
         if (tid == 0) strip_track_in_smem(p.strip, t, const_cast<float*>(reinterpret_cast<const float*>(z + half)), M);
         __syncthreads();
     }
+    if (p.bus.mix) {
+        // stereo bus first (its tickets are the critical path after the last track): this track's row goes to the
+        // tree's scratch; the last track of a group sums the group, groups are folded in order into the running bus,
+        // and on a multi-GPU job the last one exchanges the bus over NVLink (bus_tree.cuh) — no further launch
+        float2* yb = reinterpret_cast<float2*>(p.bus.ybus + static_cast<size_t>(t) * M);
+        for (int n = tid; n < half; n += 256) yb[n] = z[half + n];
+        bus_tree_arrive(p.bus, t, 0, tid, 256, 0, &s_last);
+    }
     for (int copy = 0; copy < 2; ++copy) {
         float* dst = copy ? p.out2 : p.out;
         if (!dst) continue;
@@ -515,13 +523,6 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(FusedParams 
                 col[static_cast<size_t>(2 * n + 1) * p.Tg] = v.y;
             }
         }
-    }
-    if (p.bus.mix) {
-        // stereo bus: this track's row goes to the tree's scratch; the last track of a group / the last
-        // group sums, and on a multi-GPU job exchanges the bus over NVLink (bus_tree.cuh) — no further launch
-        float2* yb = reinterpret_cast<float2*>(p.bus.ybus + static_cast<size_t>(t) * M);
-        for (int n = tid; n < half; n += 256) yb[n] = z[half + n];
-        bus_tree_arrive(p.bus, t, 0, tid, 256, 0, &s_last);
     }
 }
 

@@ -37,6 +37,33 @@ def test_two_gpu_group_matches_streaming_oracle_and_bus(oracle, algo, layout):
 
 
 @needs2
+def test_two_gpu_group_with_full_pipeline_depth_and_opt_in_shared_memory(oracle):
+    """256 tracks x 16384 taps x 512 on 2 GPUs: every member's FIR launch needs the > 48 KB dynamic shared
+    memory opt-in (nbuf = 4, 59.5 KB per CTA) — the attribute is per DEVICE, and round 1 set it once per process,
+    so device 1 never got it.  Also the first 2-GPU job whose spans cross tracks and whose bus tree has several
+    groups per member."""
+    from scipy.signal import fftconvolve
+    Tg, B, L, M = 256, 512, 16384, 35
+    p = g.plan(Tg // 2, B, L, g.ALGO_DIRECT)
+    assert p["nbuf"] == 4 and p["smem"] > 48 * 1024, p
+    rng = np.random.default_rng(3)
+    xs = rng.uniform(-1, 1, size=(M, Tg, B)).astype(np.float32)
+    h = oracle.generate_ir(Tg, L, "direct")
+    with g.ConvGroup(Tg, B, L, g.ALGO_DIRECT, 2) as grp:
+        grp.load_ir(h)
+        outs = [grp.process_host(xs[m]) for m in range(M)]
+    got = np.concatenate([y for y, _ in outs], axis=1)
+    for t in (0, 127, 128, 255):
+        want = oracle.stream(xs[:, t, :].ravel(), h[t])
+        assert snr_db(got[t], want) >= 100, t
+    truth = np.stack([fftconvolve(xs[:, t, :].ravel().astype(np.float64), h[t].astype(np.float64))[:M * B][-B:] for t in range(Tg)])
+    assert snr_db(got[:, -B:], truth) >= 100
+    theta = (np.arange(Tg) + 0.5) / Tg * np.pi / 2
+    gains = np.stack([np.cos(theta), np.sin(theta)]) / np.sqrt(Tg)
+    assert snr_db(outs[-1][1], gains @ truth) >= 95
+
+
+@needs2
 def test_plugin_on_two_gpus_validates_against_r1_and_r2():
     plugin.set_ngpus(2)
     try:
