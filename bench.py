@@ -42,6 +42,7 @@ FS = 48000
 WORKLOADS = {
     # name: (algo, tracks per GPU, B, L, layout, BASELINE config label)
     "c2": ("direct", 128, 512, 16384, "track_major", "bench_conv1d direct FIR: 128 tracks x 512-sample buffers x 16k-tap IR per GPU"),
+    "c2tc": ("direct_tc", 128, 512, 16384, "track_major", "bench_conv1d direct FIR on the tensor cores (tcgen05 kind::tf32, 3-term split): 128 tracks x 512-sample buffers x 16k-tap IR per GPU"),
     "c3": ("upols", 1024, 256, 65536, "sample_major", "bench_conv1d_accel partitioned FFT convolution: 1024 tracks x 256-sample blocks x 64k-tap IR per GPU"),
     "c4": ("upols", 512, 512, 96000, "track_major", "4096 tracks x 96k-tap IR over 8 GPUs: 512 tracks per GPU, 512-sample buffers, stereo mix-bus reduce"),
 }
@@ -223,7 +224,7 @@ def parity_leg(name, eng, bus, step_fn, d_y, d_mix, rank, world, dev, dist, with
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MIN)
     snr_min, rel_max, bus_snr = float(stats[0]), -float(stats[1]), float(stats[2])
-    min_snr, max_rel = (100.0, 1e-5) if algo_name == "direct" else (90.0, 1e-4)
+    min_snr, max_rel = (100.0, 1e-5) if algo_name.startswith("direct") else (90.0, 1e-4)
     ok = bool(snr_min >= min_snr and rel_max <= max_rel and bus_snr >= 100.0 and identical)
     del d_x, kept
     return {"ok": ok, "snr_db_min": snr_min if with_oracle else None, "max_abs_err_rel": rel_max if with_oracle else None, "bus_snr_db": bus_snr, "ranks_bit_identical": identical,
@@ -241,7 +242,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, s
     from gpuaudiobench_b200.distributed import EngineBusGroup
 
     algo_name, T, B, L, layout_name, label = WORKLOADS[name]
-    algo = g.ALGO_DIRECT if algo_name == "direct" else g.ALGO_UPOLS
+    algo = {"direct": g.ALGO_DIRECT, "direct_tc": g.ALGO_DIRECT_TC, "upols": g.ALGO_UPOLS}[algo_name]
     layout = g.OUT_SAMPLE_MAJOR if layout_name == "sample_major" else g.OUT_TRACK_MAJOR
     Tg, t0 = T * world, T * rank
     K, W = args.steps, args.warmup
@@ -364,7 +365,24 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, s
     stage_ms = [m / max(1, q["stage_calls"]) for m in q["stage_ms"][:q["stage_count"]]]
     dom_ms = stage_ms[dom]
     peaks, peak_src = measured_peaks()
-    if algo == g.ALGO_DIRECT:
+    if algo == g.ALGO_DIRECT_TC:
+        # tensor pipe: the kernel ISSUES 3 TF32 products (hi/lo split) per algorithmic MAC, on L padded to 128 taps
+        # and N padded to the 144-column MMA; the roofline is the dense TF32 rate = half the measured bf16 rate
+        tf32_peak = float(peaks.get("bf16_tflops", 2250.0 * 0.72)) / 2.0
+        plan = g.plan(T, B, L, algo)
+        issued = 3.0 * 2.0 * T * (plan["A"] * 128) * 128 * 144 * plan["NGRP"] * 1.0  # per block: A row blocks x 128 K x (128 x 144) x 3
+        achieved = issued / (dom_ms * 1e-3) / 1e12
+        fp32_peak, _ = g.measure_fp32_peak(local_rank)
+        alg = q["flops_per_block"] / (dom_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": q["stage_name"][dom], "achieved": achieved, "peak": tf32_peak,
+                    "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+                    "peak_source": f"dense TF32 = bf16_tflops of {peak_src} / 2 (kind::tf32 has K = 8 per dispatch against 16 for bf16)",
+                    "issued_flops_per_launch": issued, "algorithmic_flops_per_launch": q["flops_per_block"],
+                    "algorithmic_tflops": alg, "algorithmic_frac_of_fp32_fma_peak": alg / fp32_peak,
+                    "step_frac_of_nominal": q["flops_per_block"] / (ms_per_step * 1e-3) / 1e12 / NOMINAL_FP32_TFLOPS,
+                    "note": "algorithmic_frac_of_fp32_fma_peak > 1 means the tensor-core variant runs the fp32-accurate "
+                            "direct form faster than the FP32 FMA pipe could at 100 %"}
+    elif algo == g.ALGO_DIRECT:
         fp32_peak, _ = g.measure_fp32_peak(local_rank)
         achieved = q["flops_per_block"] / (dom_ms * 1e-3) / 1e12
         roofline = {"bound": "fp32_fma", "kernel": q["stage_name"][dom], "achieved": achieved, "peak": fp32_peak,
@@ -490,7 +508,7 @@ def _cpu_lib():
 
 
 def cpu_time_block(lib, algo_name, x, h, L, B, T, threads):
-    fn = lib.time_r1 if algo_name == "direct" else lib.time_r2
+    fn = lib.time_r1 if algo_name.startswith("direct") else lib.time_r2
     return fn(x, h, L, B, T, threads)
 
 
@@ -523,7 +541,7 @@ def cpu_baseline(name, budget_s, threads=None, reps=5):
     return {"value": gmacs, "unit": "GMAC/s", "cores": cores, "kind": kind,
             "spread": {"reps": reps, "min": Ts * iters_per_track / runs[-1] / 1e9, "max": Ts * iters_per_track / runs[0] / 1e9},
             "value_1_thread": gmacs1, "sample_1_thread": f"{T1} tracks on one thread, median of 3, {secs1:.2f} s",
-            "sample": f"{'R1 bench_conv1d.cu:188-208' if algo_name == 'direct' else 'R2 bench_conv1d_accel.cu:234-252'} "
+            "sample": f"{'R1 bench_conv1d.cu:188-208' if algo_name.startswith('direct') else 'R2 bench_conv1d_accel.cu:234-252'} "
                       f"on {Ts} of {T} tracks at full B={B}, L={L}, {cores} threads over contiguous track ranges; one warm-up "
                       f"pass, median of {reps} ({secs:.2f} s each); GMAC/s counts T*B*L loop iterations (time-domain equivalent)",
             "seconds": secs, "ms_per_block_scaled_to_T": secs * 1e3 * T / Ts,
@@ -551,7 +569,7 @@ def run_reference(args, rank, world):
     mean_s = float(np.mean(secs))
     value = Ts * iters_per_track / mean_s / 1e9
     ms_full = mean_s * 1e3 * (T * world) / Ts
-    sample = (f"{kind}: {'R1' if algo_name == 'direct' else 'R2'} CPU loop, {Ts} of {T * world} tracks per step at full "
+    sample = (f"{kind}: {'R1' if algo_name.startswith('direct') else 'R2'} CPU loop, {Ts} of {T * world} tracks per step at full "
               f"B={B}, L={L}, {cores} host threads; ms_per_step is scaled linearly to all tracks")
     return {"impl": "reference", "metric": "conv_tracks_x_ir_taps_gmac_per_s", "value": value, "unit": "GMAC/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_full, "higher_is_better": True,

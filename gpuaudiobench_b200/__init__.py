@@ -7,9 +7,9 @@ Layout (only what the hot path needs):
           benchmark_constants / thread_config) over that ABI               -> bin/gpubench
   engine.py / plugin.py   ctypes bindings used by the tests and bench.py (harness, not product)
 """
-from .engine import (ALGO_DIRECT, ALGO_UPOLS, OUT_SAMPLE_MAJOR, OUT_TRACK_MAJOR, PEEK, STRIP_BIQUAD, STRIP_GAIN,  # noqa: F401
+from .engine import (ALGO_DIRECT, ALGO_DIRECT_TC, ALGO_UPOLS, OUT_SAMPLE_MAJOR, OUT_TRACK_MAJOR, PEEK, STRIP_BIQUAD, STRIP_GAIN,  # noqa: F401
                      STRIP_STATS, B200ConvError, ConvEngine, ConvGroup, load_library, measure_fp32_peak, plan, rfft,
                      strip_process)
 
-__all__ = ["ConvEngine", "ConvGroup", "B200ConvError", "load_library", "plan", "measure_fp32_peak", "ALGO_DIRECT", "ALGO_UPOLS",
+__all__ = ["ConvEngine", "ConvGroup", "B200ConvError", "load_library", "plan", "measure_fp32_peak", "ALGO_DIRECT", "ALGO_DIRECT_TC", "ALGO_UPOLS",
            "OUT_TRACK_MAJOR", "OUT_SAMPLE_MAJOR", "PEEK"]

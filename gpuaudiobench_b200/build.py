@@ -22,7 +22,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
 
-ENGINE_SRCS = ["engine.cu", "direct_fir.cu", "upols.cu", "strip.cu", "peak.cu", "bus_allreduce.cu", "group.cu"]
+ENGINE_SRCS = ["engine.cu", "direct_fir.cu", "tc_toeplitz.cu", "upols.cu", "strip.cu", "peak.cu", "bus_allreduce.cu", "group.cu"]
 HOST_SRCS = ["bench_utils.cu", "globals.cu", "bench_base.cu", "conv_common.cu", "bench_conv1d.cu", "bench_conv1d_accel.cu",
              "bench_fft.cu", "bench_strip.cu", "registry.cu", "plugin_capi.cu"]
 

@@ -10,9 +10,9 @@
 //            ybus[t][..] (device scratch, track-major) and calls bus_tree_arrive();
 //   level 1  tracks are grouped G1 at a time; the LAST arriver of a (group, chunk) sums the group's
 //            rows in track order -> gpart[group][c][n];
-//   level 2  tree (direct FIR, whose tracks all finish at the end): the LAST group of a chunk sums the group
-//            partials in group order;  chain (UPOLS, whose tracks finish progressively): every group is folded,
-//            in group order, into a running bus as it completes -> the local bus chunk;
+//   level 2  the LAST group of a chunk sums the group partials in group order -> the local bus chunk
+//            (an ordered running sum over groups was tried for UPOLS and lost: the CTAs of a wave retire
+//            together, so the chain serialised ~14 groups at the end of C3: 171 -> 183 us);
 //   level 3  (world > 1) that CTA pushes the chunk into its slot of EVERY peer's symmetric buffer over
 //            NVLink (plain P2P stores), fences, raises its flag on every peer, acquire-polls the
 //            world flags of its own buffer and adds the world slots in rank order.
@@ -42,16 +42,11 @@ struct BusTreeParams {
     float* ybus;         // [T][B] rows the bus is summed from (track-major, device memory)
     float4* gpart;       // [NG][B/2] group partials, one float4 {l0, r0, l1, r1} per column pair
     unsigned* gcount;    // [NG][NC] arrival tickets, zero between launches
-    unsigned* ccount;    // [NC] tree: group tickets;  chain: number of groups already folded into `running`
-    float4* running;     // [B/2] chain: the bus of groups 0 .. seq-1
+    unsigned* ccount;    // [NC] group tickets
     float* mix;          // [2][B] destination (device, or pinned host); null: no bus wanted, tree disabled
     int T, B;
     int G1, NG;          // tracks per group, groups
     int CH, NC;          // columns per chunk, chunks
-    int chain;           // 0: the last group to arrive adds the NG partials (kernels whose tracks all finish at the
-                         //    end: direct FIR).  1: groups are folded in group order into a running bus as they finish
-                         //    (kernels whose tracks finish progressively: UPOLS) — after the last track only its own
-                         //    group's sum and one add remain on the critical path
     // multi-GPU exchange (world == 1: none)
     float* peers[kBusMaxWorld];
     int rank, world;
@@ -66,11 +61,6 @@ __device__ __forceinline__ void bus_st_release_sys(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ uint32_t bus_ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t bus_ld_acquire_gpu(const unsigned* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void bus_bar(uint32_t id, uint32_t nthreads) {
@@ -194,64 +184,35 @@ __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, 
     }
     if (bt.NG > 1) {
         const size_t hp = static_cast<size_t>(bt.B) >> 1;  // column pairs per bus row
-        if (!bt.chain) {
-            // ---- level 2, tree: the last group of the chunk adds the NG partials in group order ----
-            if (active) bt.gpart[static_cast<size_t>(g) * hp + (c0 >> 1) + pair] = part;
-            bus_bar(bar_id, nthr);
-            if (tid == 0) {
+        // ---- level 2, tree: the last group of the chunk adds the NG partials in group order ----
+        if (active) bt.gpart[static_cast<size_t>(g) * hp + (c0 >> 1) + pair] = part;
+        bus_bar(bar_id, nthr);
+        if (tid == 0) {
+            __threadfence();
+            const int last = (atomicAdd(bt.ccount + chunk, 1u) == static_cast<unsigned>(bt.NG) - 1u);
+            if (last) {
+                bt.ccount[chunk] = 0;
                 __threadfence();
-                const int last = (atomicAdd(bt.ccount + chunk, 1u) == static_cast<unsigned>(bt.NG) - 1u);
-                if (last) {
-                    bt.ccount[chunk] = 0;
-                    __threadfence();
-                }
-                *flag = last;
             }
-            bus_bar(bar_id, nthr);
-            if (!*flag) return;
-            part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (active) {
-                const float4* gp = bt.gpart + (c0 >> 1) + pair;
-                for (int g0 = 0; g0 < bt.NG; g0 += 8) {
-                    float4 v[8];
+            *flag = last;
+        }
+        bus_bar(bar_id, nthr);
+        if (!*flag) return;
+        part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (active) {
+            const float4* gp = bt.gpart + (c0 >> 1) + pair;
+            for (int g0 = 0; g0 < bt.NG; g0 += 8) {
+                float4 v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        v[j] = (g0 + j < bt.NG) ? __ldcg(gp + static_cast<size_t>(g0 + j) * hp) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                for (int j = 0; j < 8; ++j)
+                    v[j] = (g0 + j < bt.NG) ? __ldcg(gp + static_cast<size_t>(g0 + j) * hp) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (g0 + j < bt.NG) {
-                            part.x += v[j].x; part.y += v[j].y; part.z += v[j].z; part.w += v[j].w;
-                        }
+                for (int j = 0; j < 8; ++j) {
+                    if (g0 + j < bt.NG) {
+                        part.x += v[j].x; part.y += v[j].y; part.z += v[j].z; part.w += v[j].w;
                     }
                 }
             }
-        } else {
-            // ---- level 2, chain: fold this group into the running bus when groups 0 .. g-1 are in ----
-            if (tid == 0) {
-                unsigned spins = 0;
-                while (bus_ld_acquire_gpu(bt.ccount + chunk) != static_cast<unsigned>(g)) {
-                    if (++spins > kBusSpinLimit) {
-                        *reinterpret_cast<volatile uint32_t*>(bt.err) = 2u;
-                        break;
-                    }
-                }
-                __threadfence();
-            }
-            bus_bar(bar_id, nthr);
-            if (active && g > 0) {
-                const float4 run = __ldcg(bt.running + (c0 >> 1) + pair);
-                part.x += run.x; part.y += run.y; part.z += run.z; part.w += run.w;
-            }
-            if (g < bt.NG - 1) {
-                if (active) bt.running[(c0 >> 1) + pair] = part;
-                bus_bar(bar_id, nthr);
-                if (tid == 0) {
-                    __threadfence();
-                    atomicExch(bt.ccount + chunk, static_cast<unsigned>(g) + 1u);
-                }
-                return;
-            }
-            if (tid == 0) bt.ccount[chunk] = 0;  // last group: re-armed for the next launch
         }
     }
     bus_finish_chunk(bt, chunk, pair, active, part, tid, nthr, bar_id);

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "direct_fir.cuh"
 #include "strip.cuh"
+#include "tc_toeplitz.cuh"
 #include "upols.cuh"
 
 using namespace b200conv;
@@ -72,6 +73,15 @@ struct DirectState {
     int pos = 0;
 };
 
+struct TcState {
+    TcGeometry g{};
+    float* bimg = nullptr;   // [T][NGRP][2][32][R][4]
+    float* pend = nullptr;   // [T][capP]
+    float* xprev = nullptr;  // [T][128]
+    int ppos = 0;
+    int grid = 0;
+};
+
 struct UpolsState {
     int P = 0, M = 0, logM = 0, S = 1;
     float2* H = nullptr;
@@ -99,7 +109,7 @@ struct b200conv_engine {
     float* d_gains = nullptr;
     // stereo-bus tree (bus_tree.cuh): scratch rows, group partials, tickets
     float* d_ybus = nullptr;      // [T][B]
-    float4* d_gpart = nullptr;    // [NG + 1][B/2] {l0, r0, l1, r1}; the last row is the chain's running bus
+    float4* d_gpart = nullptr;    // [NG][B/2] {l0, r0, l1, r1}
     unsigned* d_gcount = nullptr; // [NG][NC]
     unsigned* d_ccount = nullptr; // [NC]
     int bus_G1 = 1, bus_NG = 1, bus_CH = 0, bus_NC = 1;
@@ -111,6 +121,8 @@ struct b200conv_engine {
                                     // reads it after its stream synchronise without a copy
     DirectState dir;
     UpolsState up;
+    TcState tc;
+    bool bus_in_kernel_single = false;  // B200CONV_BUS_TREE=1: run the in-kernel bus tree on a stand-alone UPOLS engine too
     // channel strip (b200conv_set_strip): device copies of the per-track parameters
     uint32_t strip_ops = 0;
     float strip_gain = 1.0f;
@@ -221,6 +233,17 @@ int plan_upols(b200conv_engine* e) {
     return B200CONV_OK;
 }
 
+int plan_tc(b200conv_engine* e) {
+    const int B = e->B;
+    if (B % kTcRows || B < kTcRows || B > kTcRows * kTcMaxA)
+        return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: block must be a multiple of 128 in [128, 1024]");
+    TcState& c = e->tc;
+    c.g = tc_geometry(B, e->L);
+    if (c.g.smem_bytes > 227 * 1024) return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: tile does not fit shared memory");
+    c.grid = std::max(1, std::min(e->T, e->sm_count));
+    return B200CONV_OK;
+}
+
 int set_default_gains(b200conv_engine* e) {
     std::vector<float> g(static_cast<size_t>(e->T) * 2);
     const double half_pi = 1.5707963267948966192313216916398;
@@ -240,6 +263,10 @@ int reset_state(b200conv_engine* e) {
     if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
         CU_TRY(cudaMemset(e->dir.ring, 0, static_cast<size_t>(e->T) * e->dir.cap * sizeof(float)));
         e->dir.pos = 0;
+    } else if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+        CU_TRY(cudaMemset(e->tc.pend, 0, static_cast<size_t>(e->T) * e->tc.g.capP * sizeof(float)));
+        CU_TRY(cudaMemset(e->tc.xprev, 0, static_cast<size_t>(e->T) * 128 * sizeof(float)));
+        e->tc.ppos = 0;
     } else {
         CU_TRY(cudaMemset(e->up.X, 0, static_cast<size_t>(e->T) * e->up.P * e->up.M * sizeof(float2)));
         CU_TRY(cudaMemset(e->up.prev, 0, static_cast<size_t>(e->T) * e->B * sizeof(float)));
@@ -291,8 +318,6 @@ BusTreeParams bus_params(const b200conv_engine* e, float* d_mix) {
     b.gpart = e->d_gpart;
     b.gcount = e->d_gcount;
     b.ccount = e->d_ccount;
-    b.running = e->d_gpart + static_cast<size_t>(e->bus_NG) * (e->B / 2);
-    b.chain = (e->cfg.algo == B200CONV_ALGO_UPOLS) ? 1 : 0;  // UPOLS tracks finish progressively, FIR tiles all at the end
     b.T = e->T;
     b.B = e->B;
     b.G1 = e->bus_G1;
@@ -372,6 +397,12 @@ int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]) {
         plan[1] = tmp.up.M;
         plan[2] = tmp.up.logM;
         plan[3] = tmp.up.S;
+    } else if (cfg->algo == B200CONV_ALGO_DIRECT_TC) {
+        int rc = plan_tc(&tmp);
+        if (rc) return rc;
+        const TcGeometry& g = tmp.tc.g;
+        const int32_t v[8] = {g.A, g.C, g.NE, g.NGRP, g.R, g.capP, static_cast<int32_t>(g.smem_bytes), tmp.tc.grid};
+        std::copy(v, v + 8, plan);
     } else {
         return fail(B200CONV_ERR_INVALID, "b200conv_plan: unknown algo");
     }
@@ -385,7 +416,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         return fail(B200CONV_ERR_ABI, "b200conv_create: abi_version mismatch");
     if (cfg->tracks == 0 || cfg->block == 0 || cfg->ir_len == 0)
         return fail(B200CONV_ERR_INVALID, "b200conv_create: tracks, block and ir_len must be > 0");
-    if (cfg->algo > B200CONV_ALGO_UPOLS || cfg->out_layout > B200CONV_OUT_SAMPLE_MAJOR)
+    if (cfg->algo > B200CONV_ALGO_DIRECT_TC || cfg->out_layout > B200CONV_OUT_SAMPLE_MAJOR)
         return fail(B200CONV_ERR_INVALID, "b200conv_create: unknown algo or layout");
     const uint32_t Tg = cfg->total_tracks ? cfg->total_tracks : cfg->tracks;
     if (cfg->track_offset + cfg->tracks > Tg)
@@ -414,7 +445,8 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
     e->toff = static_cast<int>(cfg->track_offset);
     e->sm_count = prop.multiProcessorCount;
 
-    int rc = (cfg->algo == B200CONV_ALGO_DIRECT) ? plan_direct(e) : plan_upols(e);
+    int rc = (cfg->algo == B200CONV_ALGO_DIRECT) ? plan_direct(e) : (cfg->algo == B200CONV_ALGO_UPOLS ? plan_upols(e) : plan_tc(e));
+    e->bus_in_kernel_single = env_int("B200CONV_BUS_TREE", 0) != 0;
     auto bail = [&](int code) {
         b200conv_destroy(e);
         return code;
@@ -436,13 +468,16 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if (cfg->algo == B200CONV_ALGO_DIRECT) {
             e->bus_CH = e->dir.A * 16;
             e->bus_NC = e->dir.ntiles;
+        } else if (cfg->algo == B200CONV_ALGO_DIRECT_TC) {
+            e->bus_CH = std::min(e->B, 256);  // 128 epilogue threads own one column pair each
+            e->bus_NC = e->B / e->bus_CH;
         } else {
             e->bus_CH = e->B;
             e->bus_NC = 1;
         }
         if (e->bus_NC > kBusMaxChunks) return bail(fail(B200CONV_ERR_INVALID, "b200conv_create: block too large for the bus tree"));
         if ((rc = dev_alloc(e, &e->d_ybus, tb))) return bail(rc);
-        if ((rc = dev_alloc(e, &e->d_gpart, static_cast<size_t>(e->bus_NG + 1) * (e->B / 2)))) return bail(rc);
+        if ((rc = dev_alloc(e, &e->d_gpart, static_cast<size_t>(e->bus_NG) * (e->B / 2)))) return bail(rc);
         if ((rc = dev_alloc(e, &e->d_gcount, static_cast<size_t>(e->bus_NG) * e->bus_NC))) return bail(rc);
         if ((rc = dev_alloc(e, &e->d_ccount, static_cast<size_t>(e->bus_NC)))) return bail(rc);
         err = cudaHostAlloc(reinterpret_cast<void**>(&e->d_bus_err), sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable);
@@ -456,6 +491,11 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if ((rc = dev_alloc(e, &d.ring, static_cast<size_t>(e->T) * d.cap))) return bail(rc);
         if ((rc = dev_alloc(e, &d.partial, static_cast<size_t>(d.MS) * tb))) return bail(rc);
         if ((rc = dev_alloc(e, &d.tcount, static_cast<size_t>(e->T) * d.ntiles))) return bail(rc);
+    } else if (cfg->algo == B200CONV_ALGO_DIRECT_TC) {
+        TcState& c = e->tc;
+        if ((rc = dev_alloc(e, &c.bimg, static_cast<size_t>(e->T) * c.g.NGRP * 2 * c.g.image_floats))) return bail(rc);
+        if ((rc = dev_alloc(e, &c.pend, static_cast<size_t>(e->T) * c.g.capP))) return bail(rc);
+        if ((rc = dev_alloc(e, &c.xprev, static_cast<size_t>(e->T) * 128))) return bail(rc);
     } else {
         UpolsState& u = e->up;
         const size_t spec = static_cast<size_t>(e->T) * u.P * u.M;
@@ -511,6 +551,19 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
             }
             CU_TRY(cudaMemcpy(d.h + static_cast<size_t>(t0) * row, stage.data(), static_cast<size_t>(nt) * row * sizeof(float),
                               cudaMemcpyHostToDevice));
+        }
+    } else if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+        // hi / lo TF32 tap images in the tensor core's K-major core-matrix layout, one per (track, column group)
+        TcState& c = e->tc;
+        const size_t per_track = static_cast<size_t>(c.g.NGRP) * 2 * c.g.image_floats;
+        const int chunk = static_cast<int>(std::max<size_t>(1, (64u << 20) / (per_track * sizeof(float))));
+        std::vector<float> stage(static_cast<size_t>(std::min(chunk, T)) * per_track);
+        for (int t0 = 0; t0 < T; t0 += chunk) {
+            const int nt = std::min(chunk, T - t0);
+            for (int t = 0; t < nt; ++t)
+                tc_build_images(host_ir + static_cast<size_t>(t0 + t) * L, L, c.g, stage.data() + static_cast<size_t>(t) * per_track);
+            CU_TRY(cudaMemcpy(c.bimg + static_cast<size_t>(t0) * per_track, stage.data(),
+                              static_cast<size_t>(nt) * per_track * sizeof(float), cudaMemcpyHostToDevice));
         }
     } else {
         UpolsState& u = e->up;
@@ -569,6 +622,26 @@ int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
     int rc = reset_state(e);
     if (rc || !host_hist || e->L < 2) return rc;
     const int T = e->T, L = e->L, B = e->B, H = L - 1;
+    if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+        // the state of this engine is the pending OUTPUT of past input (overlap-add), so history is primed by
+        // streaming it: ceil((L-1)/B) buffers, zero padded at the front, outputs discarded
+        const int nb = (H + B - 1) / B;
+        const size_t tb = static_cast<size_t>(T) * B;
+        std::vector<float> blk(tb);
+        for (int m = 0; m < nb; ++m) {
+            for (int t = 0; t < T; ++t)
+                for (int i = 0; i < B; ++i) {
+                    const long long src = static_cast<long long>(m) * B + i - (static_cast<long long>(nb) * B - H);
+                    blk[static_cast<size_t>(t) * B + i] = (src >= 0) ? host_hist[static_cast<size_t>(t) * H + src] : 0.0f;
+                }
+            CU_TRY(cudaMemcpy(e->d_in_stage, blk.data(), tb * sizeof(float), cudaMemcpyHostToDevice));
+            rc = b200conv_process(e, e->d_in_stage, e->d_out_stage, nullptr, 0, e->own_stream);
+            if (rc) return rc;
+            CU_TRY(cudaStreamSynchronize(e->own_stream));
+        }
+        e->blocks = 0;
+        return B200CONV_OK;
+    }
     if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
         // ring position pos = 0 is the next block; history occupies the last L-1 floats of the ring.
         DirectState& d = e->dir;
@@ -631,7 +704,16 @@ int b200conv_set_mix_gains(b200conv_engine* e, const float* host_gains) {
     return B200CONV_OK;
 }
 
+static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, float* d_out2, float* d_mix, uint32_t flags,
+                        void* stream);
+
 int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float* d_mix, uint32_t flags, void* stream) {
+    return process_impl(e, d_in, d_out, nullptr, d_mix, flags, stream);
+}
+
+// d_out2: optional second copy of the output (fused UPOLS kernel only; null otherwise)
+static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, float* d_out2, float* d_mix, uint32_t flags,
+                        void* stream) {
     if (!e || !d_in || !d_out) return fail(B200CONV_ERR_INVALID, "b200conv_process: null argument");
     if (!e->ir_loaded) return fail(B200CONV_ERR_STATE, "b200conv_process: call b200conv_load_ir first");
     ENGINE_DEVICE(e->cfg.device);  // launches, smem opt-ins and the null stream are those of the engine's device
@@ -693,6 +775,44 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
         }
         marks = tm.idx;
         if (commit) d.pos = (d.pos + e->B) % d.cap;
+    } else if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+        TcState& c = e->tc;
+        tm.mark();
+        TcParams p{};
+        p.d_in = d_in;
+        p.xprev = c.xprev;
+        p.bimg = c.bimg;
+        p.pend = c.pend;
+        p.out = d_out;
+        p.T = e->T;
+        p.B = e->B;
+        p.A = c.g.A;
+        p.C = c.g.C;
+        p.NE = c.g.NE;
+        p.NGRP = c.g.NGRP;
+        p.R = c.g.R;
+        p.capP = c.g.capP;
+        p.ppos = c.ppos;
+        p.commit = commit ? 1 : 0;
+        p.sample_major = sample_major;
+        p.Tg = e->Tg;
+        p.toff = e->toff;
+        p.bus = bus_params(e, e->strip_ops ? nullptr : d_mix);
+        CU_TRY(launch_tc_toeplitz(p, c.grid, st));
+        e->launches += 1;
+        tm.mark();
+        if (e->strip_ops) {
+            int rc = run_strip(e, d_out, commit, st);
+            if (rc) return rc;
+            if (d_mix) {
+                CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
+                e->launches += 1;
+                if ((rc = allreduce_local_bus(e, d_mix, st))) return rc;
+            }
+            tm.mark();
+        }
+        marks = tm.idx;
+        if (commit) c.ppos = (c.ppos + e->B) % c.g.capP;
     } else {
         UpolsState& u = e->up;
         const int slot0 = static_cast<int>((u.P - (e->blocks % u.P)) % u.P);
@@ -706,7 +826,7 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
             fp.Ypart = u.Ypart;
             fp.counters = u.counters;
             fp.out = d_out;
-            fp.out2 = nullptr;
+            fp.out2 = d_out2;
             fp.T = e->T;
             fp.P = u.P;
             fp.M = u.M;
@@ -718,7 +838,11 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
             fp.Tg = e->Tg;
             fp.toff = e->toff;
             if (e->strip_ops) fp.strip = strip_params(e, d_out, commit);  // strip runs inside the kernel's epilogue
-            fp.bus = bus_params(e, d_mix);                                // ... and so do the bus and its all-reduce
+            // ... and, on a multi-GPU job, so do the bus and its all-reduce.  A stand-alone engine keeps the
+            // PDL-launched bus kernel: per track the tree costs a ticket round trip that the streaming CTA
+            // cannot hide, measured 128 -> 133 us on the C4 shard and 166 -> 171 us at C3 on one GPU
+            const bool tree = (e->bus_world > 1) || e->bus_in_kernel_single;
+            fp.bus = bus_params(e, tree ? d_mix : nullptr);
             CU_TRY(launch_upols_fused(fp, st));
             e->launches += 1;
             tm.mark();
@@ -766,12 +890,13 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
             int rc = run_strip(e, d_out, commit, st);
             if (rc) return rc;
         }
-        if (d_mix && !u.fused) {
+        const bool tree_done = u.fused && ((e->bus_world > 1) || e->bus_in_kernel_single);
+        if (d_mix && !tree_done) {
             CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
             e->launches += 1;
             if (int rc = allreduce_local_bus(e, d_mix, st)) return rc;
         }
-        if (!u.fused) tm.mark();
+        if (!u.fused || (d_mix && !tree_done)) tm.mark();
         marks = tm.idx;
     }
     if (commit) e->blocks += 1;
@@ -799,7 +924,7 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     cudaStream_t st = e->own_stream;
     const size_t tb = static_cast<size_t>(e->T) * e->B;
     const int zc = env_int("B200CONV_ZEROCOPY", 3);  // bit 0: read the input in place; bit 1: write results in place
-    const bool direct = (e->cfg.algo == B200CONV_ALGO_DIRECT);
+    const bool direct = (e->cfg.algo == B200CONV_ALGO_DIRECT || e->cfg.algo == B200CONV_ALGO_DIRECT_TC);
     // input: every engine reads d_in once or twice -> read it straight from pinned host memory
     const bool in_place = (zc & 1) && is_pinned_host(h_in);
     // results: the kernels that finish a track in their own epilogue (direct FIR, fused UPOLS) can post the
@@ -808,8 +933,12 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     // place on the output), the three-kernel UPOLS path, and sample-major UPOLS (a column tile written track
     // by track is scattered 4-byte PCIe writes: measured 2x slower than the staged copy).
     const bool fused_ok = !direct && e->up.fused && e->cfg.out_layout == B200CONV_OUT_TRACK_MAJOR;
-    const bool out_place = (zc & 2) && ((direct && !e->strip_ops) || fused_ok) && h_out && is_pinned_host(h_out) &&
-                           (!h_mix || is_pinned_host(h_mix));
+    const bool tree = (e->bus_world > 1) || e->bus_in_kernel_single;  // UPOLS: the bus rides in the fused kernel
+    const bool pinned_results = (zc & 2) && h_out && is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
+    const bool out_place = pinned_results && ((direct && !e->strip_ops) || (fused_ok && (tree || !h_mix)));
+    // stand-alone fused UPOLS with a bus: the PDL-launched bus kernel reads the output back, so the fused kernel
+    // keeps a device copy and posts a SECOND copy of each finished row straight to the pinned host buffer
+    const bool dual = pinned_results && !out_place && fused_ok;
     const float* d_in = h_in;
     if (!in_place) {
         CU_TRY(cudaMemcpyAsync(e->d_in_stage, h_in, tb * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -829,8 +958,13 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
         return bus_ok();
     }
     const bool mix_place = (zc & 2) && h_mix && is_pinned_host(h_mix);  // 2*B floats: written in place whatever the output path
-    int rc = b200conv_process(e, d_in, e->d_out_stage, h_mix ? (mix_place ? h_mix : e->d_mix_stage) : nullptr, flags, st);
+    int rc = process_impl(e, d_in, e->d_out_stage, dual ? h_out : nullptr, h_mix ? (mix_place ? h_mix : e->d_mix_stage) : nullptr,
+                          flags, st);
     if (rc) return rc;
+    if (dual) {
+        CU_TRY(cudaStreamSynchronize(st));
+        return bus_ok();
+    }
     if (h_out) {
         if (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR && e->Tg != e->T) {
             CU_TRY(cudaMemcpy2DAsync(h_out + e->toff, static_cast<size_t>(e->Tg) * sizeof(float), e->d_out_stage + e->toff,
@@ -994,7 +1128,17 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
     info->dominant_stage = 1;
     info->stage_calls = e->stage_calls;
     for (int i = 0; i < 4; ++i) info->stage_ms[i] = e->stage_ms[i];
-    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+    if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+        info->flops_per_block = 2 * T * B * L;  // algorithmic; the tensor cores issue 3x (TF32 split) on L padded to 128
+        info->alg_bytes_per_block = 0;
+        info->partitions = e->tc.g.NGRP;
+        info->fft_size = 0;
+        info->kernels_per_block = e->strip_ops ? 3 : 1;
+        info->stage_count = e->strip_ops ? 2 : 1;
+        info->dominant_stage = 0;
+        std::snprintf(info->stage_name[0], 24, "tc_toeplitz");
+        std::snprintf(info->stage_name[1], 24, "strip+mix");
+    } else if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
         info->flops_per_block = 2 * T * B * L;
         info->alg_bytes_per_block = 0;
         info->partitions = e->dir.MS;
@@ -1011,10 +1155,12 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
         info->partitions = e->up.P;
         info->fft_size = 2 * e->B;
         if (e->up.fused) {
-            info->kernels_per_block = 1;
-            info->stage_count = 1;
+            const bool tree = (e->bus_world > 1) || e->bus_in_kernel_single;
+            info->kernels_per_block = tree ? 1 : 2;
+            info->stage_count = tree ? 1 : 2;
             info->dominant_stage = 0;
             std::snprintf(info->stage_name[0], 24, "upols_fused");
+            std::snprintf(info->stage_name[1], 24, "mix");
         } else {
             info->kernels_per_block = 3;
             std::snprintf(info->stage_name[0], 24, "rfft_fwd");

@@ -1,0 +1,49 @@
+// tc_toeplitz.cuh — launch interface of the tensor-core direct-form FIR (tc_toeplitz.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "bus_tree.cuh"
+
+namespace b200conv {
+
+constexpr int kTcRows = 128;    // MMA M: rows of a slab = samples per tap column (K depth of one row-block)
+constexpr int kTcCols = 144;    // MMA N: output-slab columns per group (TMEM accumulator columns)
+constexpr int kTcKSteps = 16;   // 128 taps / 8 (K of one kind::tf32 instruction)
+constexpr int kTcPlanes = 32;   // 128 taps / 4 (16-byte K chunks)
+constexpr int kTcThreads = 160; // 4 epilogue/band warps + 1 load/MMA warp
+constexpr int kTcMaxA = 8;      // block <= 1024
+
+struct TcGeometry {
+    int A;      // row blocks per buffer = B / 128
+    int C;      // tap columns = ceil(L / 128)
+    int NE;     // slab columns that receive a contribution = C + A - 1
+    int NGRP;   // column groups of kTcCols
+    int R;      // image rows per group = kTcCols + A - 1
+    int capP;   // pending-output ring capacity in floats: roundup(128 * NE, B)
+    size_t image_floats;  // floats of one (track, group, part) image = 32 * R * 4
+    size_t smem_bytes;
+};
+TcGeometry tc_geometry(int B, int L);
+
+struct TcParams {
+    const float* d_in;   // [T][B]
+    float* xprev;        // [T][128] the 128 samples before the current buffer
+    const float* bimg;   // [T][NGRP][2][32][R][4] tap images (hi part, lo part), zero padded
+    float* pend;         // [T][capP] pending-output ring
+    float* out;          // [T][B] or column tile of [B][Tg]
+    int T, B, A, C, NE, NGRP, R, capP;
+    int ppos;            // ring index of output sample 0 of the current buffer
+    int commit;
+    int sample_major, Tg, toff;
+    BusTreeParams bus;   // bus.mix == null: no bus
+};
+
+cudaError_t launch_tc_toeplitz(const TcParams& p, int grid, cudaStream_t st);
+
+// Host: the hi/lo TF32 images of one track's taps for every group, in the layout above.
+void tc_build_images(const float* h, int L, const TcGeometry& g, float* dst);
+
+}  // namespace b200conv

@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libb200conv.so")
 
 ABI_VERSION = 1
-ALGO_DIRECT, ALGO_UPOLS = 0, 1
+ALGO_DIRECT, ALGO_UPOLS, ALGO_DIRECT_TC = 0, 1, 2
 OUT_TRACK_MAJOR, OUT_SAMPLE_MAJOR = 0, 1
 PEEK = 1
 STRIP_STATS, STRIP_GAIN, STRIP_BIQUAD, STRIP_SHARED_COEFFS = 1, 2, 4, 8
@@ -116,6 +116,8 @@ def plan(tracks, block, ir_len, algo, sm_count=148):
     _check(load_library().b200conv_plan(C.byref(cfg), sm_count, arr))
     if algo == ALGO_DIRECT:
         keys = ("A", "CL", "SPS", "JSb", "NS", "G", "Lc", "cap", "nbuf", "xtile_blocks", "ntiles", "smem", "MS")
+    elif algo == ALGO_DIRECT_TC:
+        keys = ("A", "C", "NE", "NGRP", "R", "capP", "smem", "grid")
     else:
         keys = ("P", "M", "logM", "S")
     return dict(zip(keys, list(arr)))

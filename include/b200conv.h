@@ -53,7 +53,11 @@ typedef enum b200conv_status {
 
 typedef enum b200conv_algo {
     B200CONV_ALGO_DIRECT = 0, /* direct-form FIR      — replaces Conv1DTextureMemoryImplKernel, cuda/bench_conv1d.cu:7-27 */
-    B200CONV_ALGO_UPOLS = 1   /* partitioned overlap-save — replaces the cuFFT pipeline, cuda/bench_conv1d_accel.cu:258-304 */
+    B200CONV_ALGO_UPOLS = 1,  /* partitioned overlap-save — replaces the cuFFT pipeline, cuda/bench_conv1d_accel.cu:258-304 */
+    B200CONV_ALGO_DIRECT_TC = 2 /* the same direct-form sum as ALGO_DIRECT on the tensor cores (tcgen05 kind::tf32 with a
+                                   3-term hi/lo split, accumulators in TMEM): input-side Toeplitz GEMM per track and buffer,
+                                   state = pending-output ring.  block: multiple of 128 in [128, 1024].
+                                   Replaces cuda/bench_conv1d.cu:7-27 like ALGO_DIRECT (csrc/tc_toeplitz.cu) */
 } b200conv_algo;
 
 typedef enum b200conv_layout {
@@ -249,7 +253,8 @@ const char* b200conv_group_last_error(void);
 
 /* Launch plan the engine would use for `cfg` on a device with `sm_count` SMs; needs no GPU.
  * plan[0..15] = direct: {A, CL, SPS, JSb, NS, G, Lc, cap, nbuf, xtile_blocks, ntiles, smem_bytes, MS, 0...}
- *               UPOLS : {P, M, logM, S, 0...}.  Used by the host-logic tests and by capacity planning. */
+ *               UPOLS : {P, M, logM, S, 0...};  DIRECT_TC: {A, C, NE, NGRP, R, capP, smem_bytes, grid, 0...}.
+ * Used by the host-logic tests and by capacity planning. */
 int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]);
 
 /* Measured FP32 FMA peak of `device` (dependent-free FFMA loop on every SM), TFLOP/s: the

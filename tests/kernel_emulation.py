@@ -339,3 +339,95 @@ class UpolsEmu:
             self.prev[:] = x
             self.m += 1
         return y
+
+
+# ------------------------------------------------------------------------------------------------
+# Tensor-core direct FIR (csrc/tc_toeplitz.cu): byte-level emulation of the operand addressing
+# ------------------------------------------------------------------------------------------------
+class TcEmu:
+    """Mirrors tc_toeplitz_kernel: the band of 4-sample windows (A operand, Hankel via SBO = 128 B / LBO = 64 B),
+    the tap images (B operand, rows 16 B apart, planes LBO apart, row block a read A-1-a rows down), the K-major
+    no-swizzle core-matrix address rule of the tcgen05 shared-memory descriptor, TMEM accumulation over
+    (a, K-step), and the pending-output ring.  float64, no hi/lo split: this checks addressing, not rounding."""
+    ROWS, COLS, KSTEPS, PLANES = 128, 144, 16, 32
+
+    def __init__(self, T, B, L):
+        assert B % 128 == 0
+        self.T, self.B, self.L = T, B, L
+        self.A = B // 128
+        self.C = (L + 127) // 128
+        self.NE = self.C + self.A - 1
+        self.NGRP = (self.NE + self.COLS - 1) // self.COLS
+        self.R = self.COLS + self.A - 1
+        self.capP = (128 * self.NE + B - 1) // B * B
+        self.pend = np.zeros((T, self.capP))
+        self.xprev = np.zeros((T, 128))
+        self.ppos = 0
+        self.images = None
+
+    def load_ir(self, h):
+        # image[grp][S][row][j] = h[128 (e0 + row - (A-1)) + 127 - (4 S + j)], zero outside [0, L)
+        img = np.zeros((self.T, self.NGRP, self.PLANES, self.R, 4))
+        for grp in range(self.NGRP):
+            for S in range(self.PLANES):
+                for row in range(self.R):
+                    c = grp * self.COLS + row - (self.A - 1)
+                    for j in range(4):
+                        k = 128 * c + 127 - (4 * S + j)
+                        if 0 <= c < self.C and 0 <= k < self.L:
+                            img[:, grp, S, row, j] = h[:, k]
+        self.images = img
+
+    @staticmethod
+    def _operand(flat, start, rows, lbo, sbo):
+        """rows x 8 operand tile of one MMA read through a K-major no-swizzle descriptor (bytes -> float index)."""
+        out = np.empty((rows, 8))
+        for r in range(rows):
+            for kk in range(8):
+                addr = start + (r // 8) * sbo + (r % 8) * 16 + (kk // 4) * lbo + (kk % 4) * 4
+                assert addr % 4 == 0 and 0 <= addr // 4 < flat.size, (addr, flat.size)
+                out[r, kk] = flat[addr // 4]
+        return out
+
+    def process(self, x, commit=True):
+        T, B, A = self.T, self.B, self.A
+        y = np.full((T, B), np.nan)
+        new_pend = self.pend.copy()
+        plane_bytes = self.R * 16
+        for t in range(T):
+            xw = np.concatenate([self.xprev[t], x[t]])          # xw[i] = x[i - 128]
+            band = np.empty((B + 124, 4))           # band[g] = x[g-127 .. g-124]; the last window ends at x[B-1]
+            for g in range(B + 124):
+                band[g] = xw[g + 1:g + 5]
+            band = band.ravel()
+            for grp in range(self.NGRP):
+                img = self.images[t, grp].ravel()
+                D = np.zeros((self.ROWS, self.COLS))
+                for a in range(A):
+                    boff = 16 * (A - 1 - a)
+                    for q in range(self.KSTEPS):
+                        Aop = self._operand(band, 2048 * a + 128 * q, self.ROWS, 64, 128)
+                        Bop = self._operand(img, 2 * q * plane_bytes + boff, self.COLS, plane_bytes, 128)
+                        D += Aop @ Bop.T
+                e0 = grp * self.COLS
+                for k in range(self.COLS):
+                    e = e0 + k
+                    if e >= self.NE:
+                        assert not D[:, k].any(), "a column beyond NE received a contribution"
+                        continue
+                    idx = self.ppos + 128 * e
+                    if idx >= self.capP:
+                        idx -= self.capP
+                    v = D[:, k] + self.pend[t, idx:idx + 128]
+                    if e < A:
+                        y[t, 128 * e:128 * e + 128] = v
+                        new_pend[t, idx:idx + 128] = 0.0
+                    else:
+                        new_pend[t, idx:idx + 128] = v
+            if commit:
+                self.xprev[t] = xw[B:B + 128]
+        if commit:
+            self.pend = new_pend
+            self.ppos = (self.ppos + B) % self.capP
+        assert not np.isnan(y).any()
+        return y

@@ -156,3 +156,21 @@ def test_upols_kernel_index_math(T, B, L, nb):
         e.prime(hist)
         ys = np.stack([e.process(xs[m]) for m in range(nb)])
         assert np.abs(ys - _truth(xs, h, hist)).max() < 1e-11
+
+
+@pytest.mark.parametrize("T,B,L,nb", [(2, 128, 300, 5), (1, 256, 1000, 6), (1, 512, 2048, 6), (1, 128, 1, 3),
+                                      (1, 256, 18500, 3)])
+def test_tensor_core_fir_operand_addressing(T, B, L, nb):
+    """tc_toeplitz.cu: the Hankel band read through overlapping core matrices, the shifted tap images, the
+    accumulation over row blocks and K-steps, and the pending-output ring reproduce a plain convolution
+    (L not a multiple of 128, a single tap, more than one column group)."""
+    from kernel_emulation import TcEmu
+    rng = np.random.default_rng(5)
+    h, xs = rng.standard_normal((T, L)), rng.standard_normal((nb, T, B))
+    e = TcEmu(T, B, L)
+    p = g.plan(T, B, L, g.ALGO_DIRECT_TC)
+    assert (p["A"], p["C"], p["NE"], p["NGRP"], p["R"], p["capP"]) == (e.A, e.C, e.NE, e.NGRP, e.R, e.capP)
+    e.load_ir(h)
+    assert np.array_equal(e.process(xs[0], commit=False), e.process(xs[0], commit=False))  # PEEK is idempotent
+    ys = np.stack([e.process(xs[m]) for m in range(nb)])
+    assert np.abs(ys - _truth(xs, h)).max() < 1e-10
