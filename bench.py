@@ -42,7 +42,7 @@ FS = 48000
 WORKLOADS = {
     # name: (algo, tracks per GPU, B, L, layout, BASELINE config label)
     "c2": ("direct", 128, 512, 16384, "track_major", "bench_conv1d direct FIR: 128 tracks x 512-sample buffers x 16k-tap IR per GPU"),
-    "c2tc": ("direct_tc", 128, 512, 16384, "track_major", "bench_conv1d direct FIR on the tensor cores (tcgen05 kind::tf32, 3-term split): 128 tracks x 512-sample buffers x 16k-tap IR per GPU"),
+    "c2ffma": ("direct_ffma", 128, 512, 16384, "track_major", "bench_conv1d direct FIR, FP32-FMA kernel forced (B200CONV_FLAG_FFMA_ONLY): 128 tracks x 512-sample buffers x 16k-tap IR per GPU"),
     "c3": ("upols", 1024, 256, 65536, "sample_major", "bench_conv1d_accel partitioned FFT convolution: 1024 tracks x 256-sample blocks x 64k-tap IR per GPU"),
     "c4": ("upols", 512, 512, 96000, "track_major", "4096 tracks x 96k-tap IR over 8 GPUs: 512 tracks per GPU, 512-sample buffers, stereo mix-bus reduce"),
 }
@@ -242,7 +242,8 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, s
     from gpuaudiobench_b200.distributed import EngineBusGroup
 
     algo_name, T, B, L, layout_name, label = WORKLOADS[name]
-    algo = {"direct": g.ALGO_DIRECT, "direct_tc": g.ALGO_DIRECT_TC, "upols": g.ALGO_UPOLS}[algo_name]
+    algo = {"direct": g.ALGO_DIRECT, "direct_ffma": g.ALGO_DIRECT, "upols": g.ALGO_UPOLS}[algo_name]
+    eng_flags = g.engine.FLAG_FFMA_ONLY if algo_name == "direct_ffma" else 0
     layout = g.OUT_SAMPLE_MAJOR if layout_name == "sample_major" else g.OUT_TRACK_MAJOR
     Tg, t0 = T * world, T * rank
     K, W = args.steps, args.warmup
@@ -253,7 +254,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, s
     ir = synth.make_ir(Tg, L, t0, t0 + T)
     NB = 8  # distinct input buffers cycled through, resident in HBM
     x_host = synth.make_input(NB * T * B, seed=42 + rank).reshape(NB, T, B)
-    eng = g.ConvEngine(T, B, L, algo, layout, device=local_rank, track_offset=t0, total_tracks=Tg)
+    eng = g.ConvEngine(T, B, L, algo, layout, device=local_rank, track_offset=t0, total_tracks=Tg, flags=eng_flags)
     eng.load_ir(ir)
     del ir
     d_x = torch.from_numpy(x_host).to(dev)
@@ -365,12 +366,12 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, s
     stage_ms = [m / max(1, q["stage_calls"]) for m in q["stage_ms"][:q["stage_count"]]]
     dom_ms = stage_ms[dom]
     peaks, peak_src = measured_peaks()
-    if algo == g.ALGO_DIRECT_TC:
+    if q["stage_name"][dom] == "tc_toeplitz":  # ALGO_DIRECT as the planner dispatched it: the tensor-core kernel
         # tensor pipe: the kernel ISSUES 3 TF32 products (hi/lo split) per algorithmic MAC, on L padded to 128 taps
         # and N padded to the 144-column MMA; the roofline is the dense TF32 rate = half the measured bf16 rate
         tf32_peak = float(peaks.get("bf16_tflops", 2250.0 * 0.72)) / 2.0
-        plan = g.plan(T, B, L, algo)
-        issued = 3.0 * 2.0 * T * (plan["A"] * 128) * 128 * 144 * plan["NGRP"] * 1.0  # per block: A row blocks x 128 K x (128 x 144) x 3
+        plan = g.plan(T, B, L, algo, flags=eng_flags)
+        issued = 3.0 * 2.0 * T * (plan["A"] * 128) * 128 * 80 * plan["NGRP"] * 1.0  # per block: A row blocks x 128 K x (128 x 80) x 3
         achieved = issued / (dom_ms * 1e-3) / 1e12
         fp32_peak, _ = g.measure_fp32_peak(local_rank)
         alg = q["flops_per_block"] / (dom_ms * 1e-3) / 1e12
@@ -620,7 +621,7 @@ def run_latency(args, rank, world, local_rank, dist):
     from gpuaudiobench_b200.distributed import EngineBusGroup
 
     algo_name, T, B, L, layout_name, label = WORKLOADS[args.workload]
-    algo = g.ALGO_DIRECT if algo_name == "direct" else g.ALGO_UPOLS
+    algo = {"direct": g.ALGO_DIRECT, "direct_ffma": g.ALGO_DIRECT, "upols": g.ALGO_UPOLS}[algo_name]
     Tg, t0 = T * world, T * rank
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream(dev)

@@ -72,14 +72,20 @@ __device__ __forceinline__ void bus_bar(uint32_t id, uint32_t nthreads) {
 // keeps 255 redundant membars off the critical path.  Loads of a level are issued in batches (all in flight,
 // then added in the fixed order): the tail after the last track is a chain of L2 round trips, not of bytes.
 
-// The chunk's final local bus {l0, r0, l1, r1} of this thread's column pair -> mix, or over NVLink first.
-__device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int chunk, int pair, bool active, float4 v,
-                                                 int tid, int nthr, uint32_t bar_id) {
-    const int col = chunk * bt.CH + 2 * pair;
+// The chunk's final local bus {l0, r0, l1, r1} of this thread's NP column pairs -> mix, or over NVLink first.
+// Thread `tid` owns the pairs tid + q * nthr (q < NP) of the chunk; a pair is active when 2 * pair < CH.
+template <int NP>
+__device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int chunk, const float4 (&v)[NP], int tid, int nthr,
+                                                 uint32_t bar_id) {
+    const int c0 = chunk * bt.CH;
     if (bt.world == 1) {
-        if (active) {
-            *reinterpret_cast<float2*>(bt.mix + col) = make_float2(v.x, v.z);
-            *reinterpret_cast<float2*>(bt.mix + bt.B + col) = make_float2(v.y, v.w);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int pair = tid + q * nthr;
+            if (2 * pair < bt.CH) {
+                *reinterpret_cast<float2*>(bt.mix + c0 + 2 * pair) = make_float2(v[q].x, v[q].z);
+                *reinterpret_cast<float2*>(bt.mix + bt.B + c0 + 2 * pair) = make_float2(v[q].y, v[q].w);
+            }
         }
         return;
     }
@@ -87,11 +93,16 @@ __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int ch
     const int slot = bt.epoch & 1u;
     const size_t data_floats = static_cast<size_t>(2) * bt.world * n;
     const size_t my_off = (static_cast<size_t>(slot) * bt.world + bt.rank) * n;
-    if (active) {  // push: my chunk into my slot of EVERY rank's buffer (mine included), straight from registers
-        for (int p = 0; p < bt.world; ++p) {
-            float* dst = bt.peers[p] + my_off;
-            *reinterpret_cast<float2*>(dst + col) = make_float2(v.x, v.z);
-            *reinterpret_cast<float2*>(dst + bt.B + col) = make_float2(v.y, v.w);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {  // push: my chunk into my slot of EVERY rank's buffer (mine included), straight from registers
+        const int pair = tid + q * nthr;
+        if (2 * pair < bt.CH) {
+            const int col = c0 + 2 * pair;
+            for (int p = 0; p < bt.world; ++p) {
+                float* dst = bt.peers[p] + my_off;
+                *reinterpret_cast<float2*>(dst + col) = make_float2(v[q].x, v[q].z);
+                *reinterpret_cast<float2*>(dst + bt.B + col) = make_float2(v[q].y, v[q].w);
+            }
         }
     }
     bus_bar(bar_id, nthr);
@@ -109,40 +120,44 @@ __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int ch
         }
     }
     bus_bar(bar_id, nthr);
-    if (active) {  // fixed rank order: every rank computes the bit-identical sum
-        const float* base = bt.peers[bt.rank] + static_cast<size_t>(slot) * bt.world * n;
-        float2 l = make_float2(0.0f, 0.0f), r = make_float2(0.0f, 0.0f);
-        for (int q0 = 0; q0 < bt.world; q0 += 8) {
-            float2 vl[8], vr[8];
+    const float* base = bt.peers[bt.rank] + static_cast<size_t>(slot) * bt.world * n;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const bool ok = q0 + j < bt.world;
-                vl[j] = ok ? __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(q0 + j) * n + col)) : make_float2(0.0f, 0.0f);
-                vr[j] = ok ? __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(q0 + j) * n + bt.B + col)) : make_float2(0.0f, 0.0f);
-            }
+    for (int q = 0; q < NP; ++q) {  // fixed rank order: every rank computes the bit-identical sum
+        const int pair = tid + q * nthr;
+        if (2 * pair < bt.CH) {
+            const int col = c0 + 2 * pair;
+            float2 l = make_float2(0.0f, 0.0f), r = make_float2(0.0f, 0.0f);
+            for (int q0 = 0; q0 < bt.world; q0 += 8) {
+                float2 vl[8], vr[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (q0 + j < bt.world) {
-                    l.x += vl[j].x; l.y += vl[j].y;
-                    r.x += vr[j].x; r.y += vr[j].y;
+                for (int j = 0; j < 8; ++j) {
+                    const bool ok = q0 + j < bt.world;
+                    vl[j] = ok ? __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(q0 + j) * n + col)) : make_float2(0.0f, 0.0f);
+                    vr[j] = ok ? __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(q0 + j) * n + bt.B + col)) : make_float2(0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (q0 + j < bt.world) {
+                        l.x += vl[j].x; l.y += vl[j].y;
+                        r.x += vr[j].x; r.y += vr[j].y;
+                    }
                 }
             }
+            *reinterpret_cast<float2*>(bt.mix + col) = l;
+            *reinterpret_cast<float2*>(bt.mix + bt.B + col) = r;
         }
-        *reinterpret_cast<float2*>(bt.mix + col) = l;
-        *reinterpret_cast<float2*>(bt.mix + bt.B + col) = r;
     }
 }
 
 // Called by all `nthr` threads of the arriving group (tid = 0 .. nthr-1; they synchronise on hardware
 // barrier `bar_id`) after they have written ybus[t][chunk*CH .. +CH).  `flag` is one int of shared memory.
-// Thread `tid` owns the column pair (2 tid, 2 tid + 1) of the chunk; nthr >= CH/2 is required.
+// Thread `tid` owns the column pairs tid + q * nthr, q < NP; NP * nthr >= CH / 2 is required.
+template <int NP = 1>
 __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, int chunk, int tid, int nthr,
                                                 uint32_t bar_id, int* flag) {
     const int g = t / bt.G1;
     const int gsize = min(bt.G1, bt.T - g * bt.G1);
     const int c0 = chunk * bt.CH;
-    const int pair = tid;
-    const bool active = (2 * pair < bt.CH);
     // ---- level 1: last arriver of (group, chunk) ----
     bus_bar(bar_id, nthr);
     if (tid == 0) {
@@ -160,32 +175,44 @@ __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, 
     }
     bus_bar(bar_id, nthr);
     if (!*flag) return;
-    float4 part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // {l0, r0, l1, r1}
-    if (active) {
-        const float* row = bt.ybus + static_cast<size_t>(g) * bt.G1 * bt.B + c0 + 2 * pair;
-        const float2* gn = reinterpret_cast<const float2*>(bt.gains) + g * bt.G1;
-        for (int t0 = 0; t0 < gsize; t0 += 16) {  // 16 rows in flight, then the adds in track order
-            float2 v[16];
+    float4 part[NP];  // {l0, r0, l1, r1} per pair
+    const float2* gn = reinterpret_cast<const float2*>(bt.gains) + g * bt.G1;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) part[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int t0 = 0; t0 < gsize; t0 += 16) {  // 16 rows (x NP pairs) in flight, then the adds in track order
+        float2 v[NP][16];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int pair = tid + q * nthr;
+            const float* row = bt.ybus + static_cast<size_t>(g) * bt.G1 * bt.B + c0 + 2 * pair;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                v[j] = (t0 + j < gsize) ? __ldcg(reinterpret_cast<const float2*>(row + static_cast<size_t>(t0 + j) * bt.B))
-                                        : make_float2(0.0f, 0.0f);
+                v[q][j] = (t0 + j < gsize && 2 * pair < bt.CH)
+                              ? __ldcg(reinterpret_cast<const float2*>(row + static_cast<size_t>(t0 + j) * bt.B))
+                              : make_float2(0.0f, 0.0f);
+        }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (t0 + j < gsize) {
-                    const float2 gg = gn[t0 + j];
-                    part.x = fmaf(gg.x, v[j].x, part.x);
-                    part.y = fmaf(gg.y, v[j].x, part.y);
-                    part.z = fmaf(gg.x, v[j].y, part.z);
-                    part.w = fmaf(gg.y, v[j].y, part.w);
+        for (int j = 0; j < 16; ++j) {
+            if (t0 + j < gsize) {
+                const float2 gg = gn[t0 + j];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    part[q].x = fmaf(gg.x, v[q][j].x, part[q].x);
+                    part[q].y = fmaf(gg.y, v[q][j].x, part[q].y);
+                    part[q].z = fmaf(gg.x, v[q][j].y, part[q].z);
+                    part[q].w = fmaf(gg.y, v[q][j].y, part[q].w);
                 }
             }
         }
     }
     if (bt.NG > 1) {
         const size_t hp = static_cast<size_t>(bt.B) >> 1;  // column pairs per bus row
-        // ---- level 2, tree: the last group of the chunk adds the NG partials in group order ----
-        if (active) bt.gpart[static_cast<size_t>(g) * hp + (c0 >> 1) + pair] = part;
+        // ---- level 2: the last group of the chunk adds the NG partials in group order ----
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int pair = tid + q * nthr;
+            if (2 * pair < bt.CH) bt.gpart[static_cast<size_t>(g) * hp + (c0 >> 1) + pair] = part[q];
+        }
         bus_bar(bar_id, nthr);
         if (tid == 0) {
             __threadfence();
@@ -198,24 +225,28 @@ __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, 
         }
         bus_bar(bar_id, nthr);
         if (!*flag) return;
-        part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (active) {
-            const float4* gp = bt.gpart + (c0 >> 1) + pair;
-            for (int g0 = 0; g0 < bt.NG; g0 += 8) {
-                float4 v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    v[j] = (g0 + j < bt.NG) ? __ldcg(gp + static_cast<size_t>(g0 + j) * hp) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int q = 0; q < NP; ++q) {
+            const int pair = tid + q * nthr;
+            part[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (2 * pair < bt.CH) {
+                const float4* gp = bt.gpart + (c0 >> 1) + pair;
+                for (int g0 = 0; g0 < bt.NG; g0 += 8) {
+                    float4 v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (g0 + j < bt.NG) {
-                        part.x += v[j].x; part.y += v[j].y; part.z += v[j].z; part.w += v[j].w;
+                    for (int j = 0; j < 8; ++j)
+                        v[j] = (g0 + j < bt.NG) ? __ldcg(gp + static_cast<size_t>(g0 + j) * hp) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (g0 + j < bt.NG) {
+                            part[q].x += v[j].x; part[q].y += v[j].y; part[q].z += v[j].z; part[q].w += v[j].w;
+                        }
                     }
                 }
             }
         }
     }
-    bus_finish_chunk(bt, chunk, pair, active, part, tid, nthr, bar_id);
+    bus_finish_chunk<NP>(bt, chunk, part, tid, nthr, bar_id);
 }
 #endif  // __CUDACC__
 

@@ -77,8 +77,8 @@ struct TcState {
     TcGeometry g{};
     float* bimg = nullptr;   // [T][NGRP][2][32][R][4]
     float* pend = nullptr;   // [T][capP]
-    float* xprev = nullptr;  // [T][128]
-    int ppos = 0;
+    float* xprev = nullptr;  // [2][T][128] ping-pong
+    int ppos = 0, xpar = 0;
     int grid = 0;
 };
 
@@ -96,6 +96,7 @@ struct UpolsState {
 
 struct b200conv_engine {
     b200conv_config cfg{};
+    uint32_t impl = 0;  // the engine actually built: cfg.algo, or DIRECT_TC when the planner dispatches ALGO_DIRECT to it
     int T = 0, B = 0, L = 0, Tg = 0, toff = 0;
     int sm_count = 0;
     bool ir_loaded = false;
@@ -156,6 +157,19 @@ int dev_alloc(b200conv_engine* e, Tp** out, size_t count, bool zero = true) {
     e->device_bytes += bytes;
     *out = static_cast<Tp*>(p);
     return B200CONV_OK;
+}
+
+// ALGO_DIRECT is a request for the direct-form sum; the planner picks the kernel.  The tensor-core variant
+// (tc_toeplitz.cu) wins once the job amortises its ~15 us of fixed cost (launch, prologue, TMEM epilogue):
+// measured at C2 (128 x 512 x 16384, 1.07e9 MAC) 36.7 us against 57.4 us for the FFMA kernel; below ~2.5e8 MAC
+// per buffer the FFMA kernel's shorter fixed path is faster.  cfg.flags & B200CONV_FLAG_FFMA_ONLY or
+// B200CONV_DIRECT_TC=0 keep the FFMA kernel (bit-exact impulse behaviour, 126-131 dB instead of ~110 dB).
+uint32_t resolve_impl(const b200conv_config& cfg) {
+    if (cfg.algo != B200CONV_ALGO_DIRECT) return cfg.algo;
+    if ((cfg.flags & B200CONV_FLAG_FFMA_ONLY) || env_int("B200CONV_DIRECT_TC", 1) == 0) return B200CONV_ALGO_DIRECT;
+    const bool shape_ok = cfg.block % kTcRows == 0 && cfg.block >= kTcRows && cfg.block <= kTcRows * kTcMaxA;
+    const double macs = static_cast<double>(cfg.tracks) * cfg.block * cfg.ir_len;
+    return (shape_ok && macs >= 2.5e8) ? B200CONV_ALGO_DIRECT_TC : B200CONV_ALGO_DIRECT;
 }
 
 int plan_direct(b200conv_engine* e) {
@@ -240,7 +254,7 @@ int plan_tc(b200conv_engine* e) {
     TcState& c = e->tc;
     c.g = tc_geometry(B, e->L);
     if (c.g.smem_bytes > 227 * 1024) return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: tile does not fit shared memory");
-    c.grid = std::max(1, std::min(e->T, e->sm_count));
+    c.grid = std::max(1, std::min(e->T * c.g.NGRP, 2 * e->sm_count));  // persistent over (track, column group) items
     return B200CONV_OK;
 }
 
@@ -260,13 +274,14 @@ int set_default_gains(b200conv_engine* e) {
 int reset_state(b200conv_engine* e) {
     // engine streams are non-blocking: fence explicitly around the (legacy-stream) memsets
     CU_TRY(cudaDeviceSynchronize());
-    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+    if (e->impl == B200CONV_ALGO_DIRECT) {
         CU_TRY(cudaMemset(e->dir.ring, 0, static_cast<size_t>(e->T) * e->dir.cap * sizeof(float)));
         e->dir.pos = 0;
-    } else if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+    } else if (e->impl == B200CONV_ALGO_DIRECT_TC) {
         CU_TRY(cudaMemset(e->tc.pend, 0, static_cast<size_t>(e->T) * e->tc.g.capP * sizeof(float)));
-        CU_TRY(cudaMemset(e->tc.xprev, 0, static_cast<size_t>(e->T) * 128 * sizeof(float)));
+        CU_TRY(cudaMemset(e->tc.xprev, 0, static_cast<size_t>(2) * e->T * 128 * sizeof(float)));
         e->tc.ppos = 0;
+        e->tc.xpar = 0;
     } else {
         CU_TRY(cudaMemset(e->up.X, 0, static_cast<size_t>(e->T) * e->up.P * e->up.M * sizeof(float2)));
         CU_TRY(cudaMemset(e->up.prev, 0, static_cast<size_t>(e->T) * e->B * sizeof(float)));
@@ -383,21 +398,22 @@ int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]) {
     tmp.L = static_cast<int>(cfg->ir_len);
     tmp.sm_count = sm_count;
     std::fill(plan, plan + 16, 0);
-    if (cfg->algo == B200CONV_ALGO_DIRECT) {
+    const uint32_t impl = resolve_impl(*cfg);
+    if (impl == B200CONV_ALGO_DIRECT) {
         int rc = plan_direct(&tmp);
         if (rc) return rc;
         const DirectState& d = tmp.dir;
         const int32_t v[13] = {d.A, d.CL, d.SPS, d.JSb, d.NS, d.G, d.Lc, d.cap, d.nbuf, d.xtile_blocks, d.ntiles,
                                static_cast<int32_t>(d.smem), d.MS};
         std::copy(v, v + 13, plan);
-    } else if (cfg->algo == B200CONV_ALGO_UPOLS) {
+    } else if (impl == B200CONV_ALGO_UPOLS) {
         int rc = plan_upols(&tmp);
         if (rc) return rc;
         plan[0] = tmp.up.P;
         plan[1] = tmp.up.M;
         plan[2] = tmp.up.logM;
         plan[3] = tmp.up.S;
-    } else if (cfg->algo == B200CONV_ALGO_DIRECT_TC) {
+    } else if (impl == B200CONV_ALGO_DIRECT_TC) {
         int rc = plan_tc(&tmp);
         if (rc) return rc;
         const TcGeometry& g = tmp.tc.g;
@@ -406,6 +422,7 @@ int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]) {
     } else {
         return fail(B200CONV_ERR_INVALID, "b200conv_plan: unknown algo");
     }
+    plan[15] = static_cast<int32_t>(impl);  // which engine the planner chose (b200conv_algo value)
     return B200CONV_OK;
 }
 
@@ -445,7 +462,9 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
     e->toff = static_cast<int>(cfg->track_offset);
     e->sm_count = prop.multiProcessorCount;
 
-    int rc = (cfg->algo == B200CONV_ALGO_DIRECT) ? plan_direct(e) : (cfg->algo == B200CONV_ALGO_UPOLS ? plan_upols(e) : plan_tc(e));
+    const uint32_t impl = resolve_impl(*cfg);
+    e->impl = impl;
+    int rc = (impl == B200CONV_ALGO_DIRECT) ? plan_direct(e) : (impl == B200CONV_ALGO_UPOLS ? plan_upols(e) : plan_tc(e));
     e->bus_in_kernel_single = env_int("B200CONV_BUS_TREE", 0) != 0;
     auto bail = [&](int code) {
         b200conv_destroy(e);
@@ -465,11 +484,11 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         while (g1 < 64 && g1 * g1 < e->T) g1 *= 2;
         e->bus_G1 = g1;
         e->bus_NG = (e->T + g1 - 1) / g1;
-        if (cfg->algo == B200CONV_ALGO_DIRECT) {
+        if (impl == B200CONV_ALGO_DIRECT) {
             e->bus_CH = e->dir.A * 16;
             e->bus_NC = e->dir.ntiles;
-        } else if (cfg->algo == B200CONV_ALGO_DIRECT_TC) {
-            e->bus_CH = std::min(e->B, 256);  // 128 epilogue threads own one column pair each
+        } else if (impl == B200CONV_ALGO_DIRECT_TC) {
+            e->bus_CH = std::min(e->B, 512);  // 128 epilogue threads own two column pairs each
             e->bus_NC = e->B / e->bus_CH;
         } else {
             e->bus_CH = e->B;
@@ -485,17 +504,17 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         *e->d_bus_err = 0;
     }
 
-    if (cfg->algo == B200CONV_ALGO_DIRECT) {
+    if (impl == B200CONV_ALGO_DIRECT) {
         DirectState& d = e->dir;
         if ((rc = dev_alloc(e, &d.h, static_cast<size_t>(e->T) * d.Lc * 16))) return bail(rc);
         if ((rc = dev_alloc(e, &d.ring, static_cast<size_t>(e->T) * d.cap))) return bail(rc);
         if ((rc = dev_alloc(e, &d.partial, static_cast<size_t>(d.MS) * tb))) return bail(rc);
         if ((rc = dev_alloc(e, &d.tcount, static_cast<size_t>(e->T) * d.ntiles))) return bail(rc);
-    } else if (cfg->algo == B200CONV_ALGO_DIRECT_TC) {
+    } else if (impl == B200CONV_ALGO_DIRECT_TC) {
         TcState& c = e->tc;
         if ((rc = dev_alloc(e, &c.bimg, static_cast<size_t>(e->T) * c.g.NGRP * 2 * c.g.image_floats))) return bail(rc);
         if ((rc = dev_alloc(e, &c.pend, static_cast<size_t>(e->T) * c.g.capP))) return bail(rc);
-        if ((rc = dev_alloc(e, &c.xprev, static_cast<size_t>(e->T) * 128))) return bail(rc);
+        if ((rc = dev_alloc(e, &c.xprev, static_cast<size_t>(2) * e->T * 128))) return bail(rc);
     } else {
         UpolsState& u = e->up;
         const size_t spec = static_cast<size_t>(e->T) * u.P * u.M;
@@ -531,7 +550,7 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
     if (!e || !host_ir) return fail(B200CONV_ERR_INVALID, "b200conv_load_ir: null argument");
     ENGINE_DEVICE(e->cfg.device);
     const int T = e->T, L = e->L, B = e->B;
-    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+    if (e->impl == B200CONV_ALGO_DIRECT) {
         DirectState& d = e->dir;
         const size_t row = static_cast<size_t>(d.Lc) * 16;
         const int chunk = static_cast<int>(std::max<size_t>(1, (64u << 20) / (row * sizeof(float))));
@@ -552,7 +571,7 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
             CU_TRY(cudaMemcpy(d.h + static_cast<size_t>(t0) * row, stage.data(), static_cast<size_t>(nt) * row * sizeof(float),
                               cudaMemcpyHostToDevice));
         }
-    } else if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+    } else if (e->impl == B200CONV_ALGO_DIRECT_TC) {
         // hi / lo TF32 tap images in the tensor core's K-major core-matrix layout, one per (track, column group)
         TcState& c = e->tc;
         const size_t per_track = static_cast<size_t>(c.g.NGRP) * 2 * c.g.image_floats;
@@ -622,7 +641,7 @@ int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
     int rc = reset_state(e);
     if (rc || !host_hist || e->L < 2) return rc;
     const int T = e->T, L = e->L, B = e->B, H = L - 1;
-    if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+    if (e->impl == B200CONV_ALGO_DIRECT_TC) {
         // the state of this engine is the pending OUTPUT of past input (overlap-add), so history is primed by
         // streaming it: ceil((L-1)/B) buffers, zero padded at the front, outputs discarded
         const int nb = (H + B - 1) / B;
@@ -642,7 +661,7 @@ int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
         e->blocks = 0;
         return B200CONV_OK;
     }
-    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+    if (e->impl == B200CONV_ALGO_DIRECT) {
         // ring position pos = 0 is the next block; history occupies the last L-1 floats of the ring.
         DirectState& d = e->dir;
         const size_t row = d.cap;
@@ -729,7 +748,7 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
     int marks = 0;
     if (d_mix && e->bus_world > 1) e->bus_epoch += 1;  // one exchange per block with a bus, in lockstep on every rank
 
-    if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+    if (e->impl == B200CONV_ALGO_DIRECT) {
         DirectState& d = e->dir;
         tm.mark();
         FirParams p{};
@@ -775,7 +794,7 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         }
         marks = tm.idx;
         if (commit) d.pos = (d.pos + e->B) % d.cap;
-    } else if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+    } else if (e->impl == B200CONV_ALGO_DIRECT_TC) {
         TcState& c = e->tc;
         tm.mark();
         TcParams p{};
@@ -793,10 +812,12 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         p.R = c.g.R;
         p.capP = c.g.capP;
         p.ppos = c.ppos;
+        p.xpar = c.xpar;
         p.commit = commit ? 1 : 0;
         p.sample_major = sample_major;
         p.Tg = e->Tg;
         p.toff = e->toff;
+        p.debug = env_int("B200CONV_TC_DEBUG", 0);  // measurement only (skip phases)
         p.bus = bus_params(e, e->strip_ops ? nullptr : d_mix);
         CU_TRY(launch_tc_toeplitz(p, c.grid, st));
         e->launches += 1;
@@ -812,7 +833,10 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             tm.mark();
         }
         marks = tm.idx;
-        if (commit) c.ppos = (c.ppos + e->B) % c.g.capP;
+        if (commit) {
+            c.ppos = (c.ppos + e->B) % c.g.capP;
+            c.xpar ^= 1;
+        }
     } else {
         UpolsState& u = e->up;
         const int slot0 = static_cast<int>((u.P - (e->blocks % u.P)) % u.P);
@@ -924,7 +948,7 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     cudaStream_t st = e->own_stream;
     const size_t tb = static_cast<size_t>(e->T) * e->B;
     const int zc = env_int("B200CONV_ZEROCOPY", 3);  // bit 0: read the input in place; bit 1: write results in place
-    const bool direct = (e->cfg.algo == B200CONV_ALGO_DIRECT || e->cfg.algo == B200CONV_ALGO_DIRECT_TC);
+    const bool direct = (e->impl == B200CONV_ALGO_DIRECT || e->impl == B200CONV_ALGO_DIRECT_TC);
     // input: every engine reads d_in once or twice -> read it straight from pinned host memory
     const bool in_place = (zc & 1) && is_pinned_host(h_in);
     // results: the kernels that finish a track in their own epilogue (direct FIR, fused UPOLS) can post the
@@ -1128,7 +1152,7 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
     info->dominant_stage = 1;
     info->stage_calls = e->stage_calls;
     for (int i = 0; i < 4; ++i) info->stage_ms[i] = e->stage_ms[i];
-    if (e->cfg.algo == B200CONV_ALGO_DIRECT_TC) {
+    if (e->impl == B200CONV_ALGO_DIRECT_TC) {
         info->flops_per_block = 2 * T * B * L;  // algorithmic; the tensor cores issue 3x (TF32 split) on L padded to 128
         info->alg_bytes_per_block = 0;
         info->partitions = e->tc.g.NGRP;
@@ -1138,7 +1162,7 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
         info->dominant_stage = 0;
         std::snprintf(info->stage_name[0], 24, "tc_toeplitz");
         std::snprintf(info->stage_name[1], 24, "strip+mix");
-    } else if (e->cfg.algo == B200CONV_ALGO_DIRECT) {
+    } else if (e->impl == B200CONV_ALGO_DIRECT) {
         info->flops_per_block = 2 * T * B * L;
         info->alg_bytes_per_block = 0;
         info->partitions = e->dir.MS;

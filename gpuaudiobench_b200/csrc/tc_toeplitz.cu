@@ -14,7 +14,8 @@
 //
 // The future outputs live in a per-track pending-output ring (overlap-add in the time domain): a buffer adds
 // S to it, emits its own B samples and hands the rest on.  S accumulates over (a, d) inside TMEM — 64 K-steps
-// of one 128 x 144 x 8 kind::tf32 MMA each — so the skewed sum costs nothing outside the tensor core.
+// of one 128 x 80 x 8 kind::tf32 MMA each per 80-column group — so the skewed sum costs nothing outside the
+// tensor core.
 //
 // Operands, both K-major, no swizzle ("interleaved" canonical layout: 8-row x 16-byte core matrices, 8-row
 // groups SBO apart, the two 16-byte K chunks of an instruction LBO apart):
@@ -39,7 +40,8 @@ namespace b200conv {
 
 namespace {
 
-constexpr int kTmemCols = 256;  // allocation: power of two >= kTcCols
+constexpr int kTmemCols = 256;  // allocation: power of two >= 2 * kTcCols (two accumulators; two CTAs per SM use all 512 columns)
+constexpr int kTmemAcc1 = 128;  // column of the second accumulator
 
 __host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -120,7 +122,7 @@ __host__ __device__ inline SmemMap smem_map(int B, int R) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 2) tc_toeplitz_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bfull = reinterpret_cast<uint64_t*>(smem);       // tap images of a group have landed (TMA bytes)
     uint64_t* dfull = bfull + 1;                               // the group's MMAs have completed
@@ -153,18 +155,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
     auto load_images = [&](int t, int grp) {  // one elected thread: 8 bulk copies of 8 planes each
         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.bimg) +
                                    (static_cast<size_t>(t) * p.NGRP + grp) * 2 * part_bytes;
+        if (p.debug & 4) {
+            mbar_arrive(bfull);
+            return;
+        }
         mbar_arrive_expect_tx(bfull, 2 * part_bytes);
         const uint32_t piece = 8 * plane_bytes;
         for (int i = 0; i < 8; ++i) bulk_g2s(bimg_s + i * piece, src + static_cast<size_t>(i) * piece, piece, bfull);
     };
 
-    for (int t = blockIdx.x; t < p.T; t += gridDim.x) {
+    // Work items are (track, column group): the kTcCols-column groups of one track are independent GEMMs over the
+    // same band, so they go to different CTAs (two CTAs fit an SM: one's MMAs overlap the other's prologue /
+    // epilogue; at C2 that is 256 items for 148 SMs instead of 128 tracks).  Each item rebuilds the small band.
+    const int n_items = p.T * p.NGRP;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int t = item / p.NGRP, grp = item - t * p.NGRP;
         if (warp == 4) {
-            if (lane == 0) load_images(t, 0);  // the image buffer is free: the previous track's MMAs completed
+            if (lane == 0) load_images(t, grp);  // the image buffer is free: the previous item's MMAs completed
         } else {
             // ---- band of 4-sample windows of [previous 128 | this buffer], split hi + lo ----
             const float4* xin4 = reinterpret_cast<const float4*>(p.d_in + static_cast<size_t>(t) * B);
-            const float4* xp4 = reinterpret_cast<const float4*>(p.xprev + static_cast<size_t>(t) * 128);
+            const float4* xp4 = reinterpret_cast<const float4*>(p.xprev + (static_cast<size_t>(p.xpar) * p.T + t) * 128);
             float4* xw4 = reinterpret_cast<float4*>(xw);
             for (int i = tid; i < 32; i += 128) xw4[i] = xp4[i];
             for (int i = tid; i < B / 4; i += 128) xw4[32 + i] = xin4[i];
@@ -180,8 +191,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
                 *reinterpret_cast<float4*>(band_hi + g * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<float4*>(band_lo + g * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
-            if (p.commit) {  // the next buffer's "previous 128": everyone has read xprev (barrier above)
-                float4* xpw = reinterpret_cast<float4*>(p.xprev + static_cast<size_t>(t) * 128);
+            if (p.commit && grp == 0) {
+                // the next buffer's "previous 128" goes to the OTHER half of the ping-pong: the CTAs that work on
+                // this track's other column groups may still be reading the current one
+                float4* xpw = reinterpret_cast<float4*>(p.xprev + (static_cast<size_t>(p.xpar ^ 1) * p.T + t) * 128);
                 for (int i = tid; i < 32; i += 128) xpw[i] = xw4[B / 4 + i];
             }
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -190,15 +203,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
 
         float* pring = p.pend + static_cast<size_t>(t) * p.capP;
         const int row = warp * 32 + lane;  // r (epilogue warps)
-        for (int grp = 0; grp < p.NGRP; ++grp) {
+        {
             if (warp == 4) {
                 if (lane == 0) {
                     mbar_wait(bfull, bphase);
                     tc_fence_after();
                     const uint32_t a_hi0 = smem_u32(band_hi), a_lo0 = smem_u32(band_lo);
                     const uint32_t b_hi0 = smem_u32(bimg_s), b_lo0 = b_hi0 + part_bytes;
-                    uint32_t acc = 0;
-                    for (int a = 0; a < p.A; ++a) {
+                    // Two accumulators, even / odd K-steps, added in the epilogue in fp32 RN: the tensor core adds each
+                    // MMA into TMEM with truncation, an error that grows with the number of accumulation steps
+                    // (measured 102 dB at B = 1024 with one accumulator: 384 steps) — two chains of half the length
+                    for (int a = 0; a < ((p.debug & 1) ? 0 : p.A); ++a) {
                         const uint32_t boff = 16u * static_cast<uint32_t>(p.A - 1 - a);
 #pragma unroll 4
                         for (int q = 0; q < kTcKSteps; ++q) {
@@ -207,54 +222,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
                             const uint64_t da_lo = smem_desc(a_lo0 + aoff, 64, 128);
                             const uint64_t db_hi = smem_desc(b_hi0 + 2u * q * plane_bytes + boff, plane_bytes, 128);
                             const uint64_t db_lo = smem_desc(b_lo0 + 2u * q * plane_bytes + boff, plane_bytes, 128);
-                            mma_tf32(tmem, da_lo, db_hi, idesc, acc);  // small terms first
-                            mma_tf32(tmem, da_hi, db_lo, idesc, 1u);
-                            mma_tf32(tmem, da_hi, db_hi, idesc, 1u);
-                            acc = 1u;
+                            const uint32_t d = tmem + ((q & 1) ? kTmemAcc1 : 0);
+                            mma_tf32(d, da_lo, db_hi, idesc, (a > 0 || q > 1) ? 1u : 0u);  // small terms first
+                            mma_tf32(d, da_hi, db_lo, idesc, 1u);
+                            mma_tf32(d, da_hi, db_hi, idesc, 1u);
                         }
                     }
                     mma_commit(dfull);
-                    if (grp + 1 < p.NGRP) {  // next group's images as soon as the MMAs have stopped reading these
-                        mbar_wait(dfull, dphase);
-                        load_images(t, grp + 1);
-                    }
                 }
                 __syncwarp();
             } else {
-                // pending-output values of this group's columns, fetched while the MMAs run
-                float pv[kTcCols];
+                // ---- epilogue: S (TMEM) + pending ring -> this buffer's samples and the new pending ring.
+                // Kept a compact LOOP over 16-column batches: the first version unrolled all 144 columns with
+                // their ring arithmetic into 14 K instructions per warp and ncu showed 58 % of the stall samples
+                // as "no instruction" (instruction-cache misses; cold they come from DRAM): 82 us for 6 us of MMA.
                 const int e0 = grp * kTcCols;
+                const int capP = p.capP, NE = p.NE, nA = p.A, ppos = p.ppos;
+                const bool commit = p.commit != 0, ring_io = !(p.debug & 2);
+                float* prow = pring + row;
+                auto ring_index = [&](int e) {
+                    int idx = ppos + 128 * e;
+                    return idx >= capP ? idx - capP : idx;
+                };
+                // the ring lines this warp will read: into L2 while the MMAs run (first touch after a flush is DRAM)
+                for (int k = lane; k < kTcCols; k += 32)
+                    if (e0 + k < NE && ring_io)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pring + ring_index(e0 + k) + warp * 32));
+                float pn[16];
 #pragma unroll
-                for (int k = 0; k < kTcCols; ++k) {
-                    const int e = e0 + k;
-                    int idx = p.ppos + 128 * e;
-                    if (idx >= p.capP) idx -= p.capP;
-                    pv[k] = (e < p.NE) ? __ldcg(pring + idx + row) : 0.0f;
-                }
+                for (int j = 0; j < 16; ++j) pn[j] = (e0 + j < NE && ring_io) ? __ldcg(prow + ring_index(e0 + j)) : 0.0f;
                 mbar_wait(dfull, dphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-#pragma unroll
+#pragma unroll 1
                 for (int cb = 0; cb < kTcCols / 16; ++cb) {
-                    uint32_t r[16];
+                    float pv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pv[j] = pn[j];
+                    const int eb = e0 + cb * 16;
+                    if (cb + 1 < kTcCols / 16) {  // next batch's ring values in flight while this one is finished
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            pn[j] = (eb + 16 + j < NE && ring_io) ? __ldcg(prow + ring_index(eb + 16 + j)) : 0.0f;
+                    }
+                    uint32_t r[16], r1[16];
                     tmem_ld16(taddr + cb * 16, r);
+                    tmem_ld16(taddr + kTmemAcc1 + cb * 16, r1);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int e = e0 + cb * 16 + j;
-                        if (e < p.NE) {
-                            int idx = p.ppos + 128 * e;
-                            if (idx >= p.capP) idx -= p.capP;
-                            const float v = __uint_as_float(r[j]) + pv[cb * 16 + j];
-                            if (e < p.A) {  // this buffer's own samples: n = 128 e + row < B
+                        const int e = eb + j;
+                        if (e < NE) {
+                            const float v = (__uint_as_float(r[j]) + __uint_as_float(r1[j])) + pv[j];
+                            if (e < nA) {  // this buffer's own samples: n = 128 e + row < B
                                 const int n = 128 * e + row;
                                 if (p.sample_major)
                                     p.out[static_cast<size_t>(n) * p.Tg + p.toff + t] = v;
                                 else
                                     p.out[static_cast<size_t>(t) * B + n] = v;
                                 if (p.bus.mix) p.bus.ybus[static_cast<size_t>(t) * B + n] = v;
-                                if (p.commit) pring[idx + row] = 0.0f;  // becomes the farthest future slot
-                            } else if (p.commit) {
-                                pring[idx + row] = v;
+                                if (commit) prow[ring_index(e)] = 0.0f;  // becomes the farthest future slot
+                            } else if (commit && ring_io) {
+                                prow[ring_index(e)] = v;
                             }
                         }
                     }
@@ -263,10 +291,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
             }
             bphase ^= 1u;
             dphase ^= 1u;
-            __syncthreads();  // TMEM drained (and, for the next track, band / x window free) before it is overwritten
+            __syncthreads();  // TMEM drained, band / x window / images free before the next item overwrites them
         }
-        if (warp < 4 && p.bus.mix) {
-            for (int chunk = 0; chunk < p.bus.NC; ++chunk) bus_tree_arrive(p.bus, t, chunk, tid, 128, 1, s_flag);
+        if (warp < 4 && p.bus.mix && grp == 0) {  // group 0 carries this buffer's own samples
+            for (int chunk = 0; chunk < p.bus.NC; ++chunk) bus_tree_arrive<2>(p.bus, t, chunk, tid, 128, 1, s_flag);
         }
     }
     __syncthreads();

@@ -10,7 +10,7 @@
 namespace b200conv {
 
 constexpr int kTcRows = 128;    // MMA M: rows of a slab = samples per tap column (K depth of one row-block)
-constexpr int kTcCols = 144;    // MMA N: output-slab columns per group (TMEM accumulator columns)
+constexpr int kTcCols = 80;     // MMA N: output-slab columns per group (TMEM accumulator columns); one group = one work item
 constexpr int kTcKSteps = 16;   // 128 taps / 8 (K of one kind::tf32 instruction)
 constexpr int kTcPlanes = 32;   // 128 taps / 4 (16-byte K chunks)
 constexpr int kTcThreads = 160; // 4 epilogue/band warps + 1 load/MMA warp
@@ -30,14 +30,16 @@ TcGeometry tc_geometry(int B, int L);
 
 struct TcParams {
     const float* d_in;   // [T][B]
-    float* xprev;        // [T][128] the 128 samples before the current buffer
+    float* xprev;        // [2][T][128] the 128 samples before the current buffer, ping-pong: read [xpar], write [xpar ^ 1]
     const float* bimg;   // [T][NGRP][2][32][R][4] tap images (hi part, lo part), zero padded
     float* pend;         // [T][capP] pending-output ring
     float* out;          // [T][B] or column tile of [B][Tg]
     int T, B, A, C, NE, NGRP, R, capP;
     int ppos;            // ring index of output sample 0 of the current buffer
+    int xpar;            // which half of xprev holds the previous buffer's tail
     int commit;
     int sample_major, Tg, toff;
+    int debug;           // B200CONV_TC_DEBUG (measurement only): 1 skip the MMAs, 2 skip the pending-ring traffic, 4 skip the image load
     BusTreeParams bus;   // bus.mix == null: no bus
 };
 

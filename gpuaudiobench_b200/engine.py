@@ -105,15 +105,26 @@ def _check(rc):
         raise B200ConvError(rc, load_library().b200conv_last_error().decode(errors="replace"))
 
 
-def make_config(tracks, block, ir_len, algo, out_layout=OUT_TRACK_MAJOR, device=0, track_offset=0, total_tracks=0):
-    return Config(ABI_VERSION, device, tracks, track_offset, total_tracks, block, ir_len, algo, out_layout, 0)
+FLAG_FFMA_ONLY = 1
 
 
-def plan(tracks, block, ir_len, algo, sm_count=148):
-    """The engine's launch plan (needs no GPU): dict of the fields documented in b200conv.h."""
-    cfg = make_config(tracks, block, ir_len, algo)
+def make_config(tracks, block, ir_len, algo, out_layout=OUT_TRACK_MAJOR, device=0, track_offset=0, total_tracks=0, flags=0):
+    return Config(ABI_VERSION, device, tracks, track_offset, total_tracks, block, ir_len, algo, out_layout, flags)
+
+
+def plan(tracks, block, ir_len, algo, sm_count=148, flags=0):
+    """The engine's launch plan (needs no GPU): dict of the fields documented in b200conv.h; "impl" is the
+    kernel family the planner chose (ALGO_DIRECT may resolve to ALGO_DIRECT_TC)."""
+    cfg = make_config(tracks, block, ir_len, algo, flags=flags)
     arr = (C.c_int32 * 16)()
     _check(load_library().b200conv_plan(C.byref(cfg), sm_count, arr))
+    d = _plan_dict(arr)
+    d["impl"] = arr[15]
+    return d
+
+
+def _plan_dict(arr):
+    algo = arr[15]
     if algo == ALGO_DIRECT:
         keys = ("A", "CL", "SPS", "JSb", "NS", "G", "Lc", "cap", "nbuf", "xtile_blocks", "ntiles", "smem", "MS")
     elif algo == ALGO_DIRECT_TC:
@@ -231,9 +242,9 @@ class ConvEngine:
     torch.Tensor.data_ptr()); host buffers as C-contiguous float32 numpy arrays."""
 
     def __init__(self, tracks, block, ir_len, algo, out_layout=OUT_TRACK_MAJOR, device=0, track_offset=0,
-                 total_tracks=0):
+                 total_tracks=0, flags=0):
         self.lib = load_library()
-        self.cfg = make_config(tracks, block, ir_len, algo, out_layout, device, track_offset, total_tracks)
+        self.cfg = make_config(tracks, block, ir_len, algo, out_layout, device, track_offset, total_tracks, flags)
         self.T, self.B, self.L = tracks, block, ir_len
         self.Tg = total_tracks or tracks
         self.toff = track_offset

@@ -65,6 +65,11 @@ typedef enum b200conv_layout {
     B200CONV_OUT_SAMPLE_MAJOR = 1
 } b200conv_layout;
 
+/* b200conv_config.flags */
+#define B200CONV_FLAG_FFMA_ONLY 1u /* ALGO_DIRECT: never dispatch to the tensor-core kernel (keeps the FFMA kernel's bit-exact
+                                      impulse behaviour and its 126-131 dB; the default planner picks DIRECT_TC for blocks that
+                                      are a multiple of 128 up to 1024 once tracks*block*ir_len >= 2.5e8, ~110 dB) */
+
 /* b200conv_process flags */
 #define B200CONV_PEEK 1u /* compute this block but do not advance the stream state: repeated calls
                             are idempotent, which is what the reference's stateless iteration loop
@@ -80,7 +85,7 @@ typedef struct b200conv_config {
     uint32_t ir_len;       /* L: taps (ir_length_, cuda/bench_conv1d.cuh:11 / bench_conv1d_accel.cuh:11) */
     uint32_t algo;         /* b200conv_algo */
     uint32_t out_layout;   /* b200conv_layout */
-    uint32_t flags;        /* reserved, 0 */
+    uint32_t flags;        /* B200CONV_FLAG_* */
 } b200conv_config;
 
 typedef struct b200conv_info {
@@ -254,6 +259,7 @@ const char* b200conv_group_last_error(void);
 /* Launch plan the engine would use for `cfg` on a device with `sm_count` SMs; needs no GPU.
  * plan[0..15] = direct: {A, CL, SPS, JSb, NS, G, Lc, cap, nbuf, xtile_blocks, ntiles, smem_bytes, MS, 0...}
  *               UPOLS : {P, M, logM, S, 0...};  DIRECT_TC: {A, C, NE, NGRP, R, capP, smem_bytes, grid, 0...}.
+ * plan[15] = the b200conv_algo value of the kernel family the planner chose (ALGO_DIRECT may resolve to DIRECT_TC).
  * Used by the host-logic tests and by capacity planning. */
 int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]);
 

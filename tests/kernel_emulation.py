@@ -349,7 +349,7 @@ class TcEmu:
     the tap images (B operand, rows 16 B apart, planes LBO apart, row block a read A-1-a rows down), the K-major
     no-swizzle core-matrix address rule of the tcgen05 shared-memory descriptor, TMEM accumulation over
     (a, K-step), and the pending-output ring.  float64, no hi/lo split: this checks addressing, not rounding."""
-    ROWS, COLS, KSTEPS, PLANES = 128, 144, 16, 32
+    ROWS, COLS, KSTEPS, PLANES = 128, 80, 16, 32
 
     def __init__(self, T, B, L):
         assert B % 128 == 0

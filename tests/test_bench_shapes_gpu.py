@@ -61,19 +61,19 @@ def stream_on_device(engine, xs, keep, layout=g.OUT_TRACK_MAJOR):
 
 
 def check_shape(oracle, algo, T, B, L, oracle_tracks, fp64_tracks, Tg=None, t0=0, layout=g.OUT_TRACK_MAJOR, seed=5,
-                expect_plan=None):
+                expect_plan=None, flags=0):
     Tg = Tg or T
     P = (L + B - 1) // B
     M = P + 2
     rng = np.random.default_rng(seed)
     xs = rng.uniform(-1, 1, size=(M, T, B)).astype(np.float32)
     h = synth.make_ir(Tg, L, t0, t0 + T)
-    plan = g.plan(T, B, L, algo)
+    plan = g.plan(T, B, L, algo, flags=flags)
     if expect_plan:
         for k, v in expect_plan.items():
             assert plan[k] == v, f"plan[{k}] = {plan[k]}, test was written for {v}: {plan}"
     keep = sorted(set(oracle_tracks) | set(fp64_tracks))
-    with g.ConvEngine(T, B, L, algo, layout, track_offset=t0, total_tracks=Tg) as e:
+    with g.ConvEngine(T, B, L, algo, layout, track_offset=t0, total_tracks=Tg, flags=flags) as e:
         e.load_ir(h)
         got, last, bus = stream_on_device(e, xs, keep, layout)
     min_snr, rel = TOL[algo]
@@ -123,11 +123,20 @@ def test_upols_large_buffers_at_96000_taps(oracle, B):
 
 
 @pytest.mark.parametrize("B,A", [(32, 2), (64, 4), (128, 8), (256, 16), (512, 32), (4096, 32)])
-def test_direct_sweep_points_at_16384_taps(oracle, B, A):
-    """The direct engine's sweep points at C2's T and L: the small-buffer plans (A = 2 / 4 / 8 / 16 tap-group
+def test_ffma_direct_sweep_points_at_16384_taps(oracle, B, A):
+    """The FFMA direct kernel's sweep points at C2's T and L: the small-buffer plans (A = 2 / 4 / 8 / 16 tap-group
     layouts, swizzled taps) were only tested at L <= 960 in round 1."""
     check_shape(oracle, g.ALGO_DIRECT, 128, B, 16384, oracle_tracks=[0, 127], fp64_tracks=[1, 64, 126],
-                expect_plan={"A": A})
+                expect_plan={"A": A, "impl": g.ALGO_DIRECT}, flags=g.engine.FLAG_FFMA_ONLY)
+
+
+@pytest.mark.parametrize("B,impl", [(32, g.ALGO_DIRECT), (128, g.ALGO_DIRECT_TC), (256, g.ALGO_DIRECT_TC), (512, g.ALGO_DIRECT_TC),
+                                    (1024, g.ALGO_DIRECT_TC), (2048, g.ALGO_DIRECT)])
+def test_direct_sweep_points_as_the_planner_dispatches_them(oracle, B, impl):
+    """The same sweep points through plain ALGO_DIRECT, i.e. what bench.py --sweep measures: the tensor-core kernel for
+    128 <= B <= 1024, the FFMA kernel elsewhere; one tolerance for both (100 dB, 1e-5 of max|y|)."""
+    check_shape(oracle, g.ALGO_DIRECT, 128, B, 16384, oracle_tracks=[0, 127], fp64_tracks=[1, 64, 126],
+                expect_plan={"impl": impl})
 
 
 def test_two_sharded_engines_on_one_device_equal_the_unsharded_job(oracle):

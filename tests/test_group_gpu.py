@@ -37,15 +37,18 @@ def test_two_gpu_group_matches_streaming_oracle_and_bus(oracle, algo, layout):
 
 
 @needs2
-def test_two_gpu_group_with_full_pipeline_depth_and_opt_in_shared_memory(oracle):
-    """256 tracks x 16384 taps x 512 on 2 GPUs: every member's FIR launch needs the > 48 KB dynamic shared
-    memory opt-in (nbuf = 4, 59.5 KB per CTA) — the attribute is per DEVICE, and round 1 set it once per process,
-    so device 1 never got it.  Also the first 2-GPU job whose spans cross tracks and whose bus tree has several
-    groups per member."""
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_two_gpu_group_with_full_pipeline_depth_and_opt_in_shared_memory(oracle, monkeypatch, tensor_cores):
+    """256 tracks x 16384 taps x 512 on 2 GPUs: every member's launch needs the > 48 KB dynamic shared memory
+    opt-in (FFMA kernel: nbuf = 4, 59.5 KB per CTA; tensor-core kernel: 106 KB) — the attribute is per DEVICE, and
+    round 1 set it once per process, so device 1 never got it.  Also the first 2-GPU job whose spans cross tracks
+    and whose bus tree has several groups per member."""
     from scipy.signal import fftconvolve
     Tg, B, L, M = 256, 512, 16384, 35
+    monkeypatch.setenv("B200CONV_DIRECT_TC", "1" if tensor_cores else "0")
     p = g.plan(Tg // 2, B, L, g.ALGO_DIRECT)
-    assert p["nbuf"] == 4 and p["smem"] > 48 * 1024, p
+    assert p["impl"] == (g.ALGO_DIRECT_TC if tensor_cores else g.ALGO_DIRECT) and p["smem"] > 48 * 1024, p
+    assert tensor_cores or p["nbuf"] == 4
     rng = np.random.default_rng(3)
     xs = rng.uniform(-1, 1, size=(M, Tg, B)).astype(np.float32)
     h = oracle.generate_ir(Tg, L, "direct")

@@ -72,7 +72,8 @@ def test_plan_rejects_bad_sizes():
 @pytest.mark.parametrize("T,B,L", [(128, 512, 16384), (1, 512, 1024), (4096, 512, 96000), (128, 32, 96000),
                                     (7, 4096, 5000), (3, 256, 17)])
 def test_direct_plan_invariants(T, B, L):
-    p = g.plan(T, B, L, g.ALGO_DIRECT)
+    p = g.plan(T, B, L, g.ALGO_DIRECT, flags=g.engine.FLAG_FFMA_ONLY)  # the FFMA kernel's plan
+    assert p["impl"] == g.ALGO_DIRECT
     assert p["A"] * p["CL"] == 32 and p["SPS"] % 2 == 0
     assert p["JSb"] == 8 * p["CL"] * p["SPS"]
     assert p["Lc"] == p["NS"] * p["JSb"] and p["Lc"] * 16 >= L
@@ -158,8 +159,25 @@ def test_upols_kernel_index_math(T, B, L, nb):
         assert np.abs(ys - _truth(xs, h, hist)).max() < 1e-11
 
 
+def test_planner_dispatches_the_direct_form_between_ffma_and_tensor_cores(monkeypatch):
+    """ALGO_DIRECT is a request for the direct-form sum; the planner picks the tensor-core kernel for blocks that
+    are a multiple of 128 (<= 1024) once tracks*block*taps >= 2.5e8 MAC, the FFMA kernel otherwise or on request."""
+    D, TC = g.ALGO_DIRECT, g.ALGO_DIRECT_TC
+    assert g.plan(128, 512, 16384, D)["impl"] == TC            # C2
+    assert g.plan(128, 512, 16384, D, flags=g.engine.FLAG_FFMA_ONLY)["impl"] == D
+    assert g.plan(1, 512, 1024, D)["impl"] == D                # C1: far too small to amortise the fixed cost
+    assert g.plan(128, 64, 16384, D)["impl"] == D              # block not a multiple of 128
+    assert g.plan(128, 4096, 16384, D)["impl"] == D            # block > 1024
+    assert g.plan(128, 128, 16384, D)["impl"] == TC
+    assert g.plan(128, 512, 16384, TC)["impl"] == TC and g.plan(2, 128, 40, TC)["impl"] == TC  # explicit request
+    with pytest.raises(g.B200ConvError):
+        g.plan(4, 64, 100, TC)
+    monkeypatch.setenv("B200CONV_DIRECT_TC", "0")
+    assert g.plan(128, 512, 16384, D)["impl"] == D
+
+
 @pytest.mark.parametrize("T,B,L,nb", [(2, 128, 300, 5), (1, 256, 1000, 6), (1, 512, 2048, 6), (1, 128, 1, 3),
-                                      (1, 256, 18500, 3)])
+                                      (1, 256, 10500, 3)])
 def test_tensor_core_fir_operand_addressing(T, B, L, nb):
     """tc_toeplitz.cu: the Hankel band read through overlapping core matrices, the shifted tap images, the
     accumulation over row blocks and K-steps, and the pending-output ring reproduce a plain convolution
