@@ -268,6 +268,7 @@ int set_default_gains(b200conv_engine* e) {
         g[2 * t + 1] = static_cast<float>(std::sin(theta) * scale);
     }
     CU_TRY(cudaMemcpy(e->d_gains, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(cudaDeviceSynchronize());
     return B200CONV_OK;
 }
 
@@ -653,7 +654,9 @@ int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
                     const long long src = static_cast<long long>(m) * B + i - (static_cast<long long>(nb) * B - H);
                     blk[static_cast<size_t>(t) * B + i] = (src >= 0) ? host_hist[static_cast<size_t>(t) * H + src] : 0.0f;
                 }
-            CU_TRY(cudaMemcpy(e->d_in_stage, blk.data(), tb * sizeof(float), cudaMemcpyHostToDevice));
+            // stream-ordered with the kernel that reads it: a plain cudaMemcpy from PAGEABLE memory may return before
+            // its DMA has landed, and the engine's stream is non-blocking (does not wait for the legacy stream)
+            CU_TRY(cudaMemcpyAsync(e->d_in_stage, blk.data(), tb * sizeof(float), cudaMemcpyHostToDevice, e->own_stream));
             rc = b200conv_process(e, e->d_in_stage, e->d_out_stage, nullptr, 0, e->own_stream);
             if (rc) return rc;
             CU_TRY(cudaStreamSynchronize(e->own_stream));
@@ -712,6 +715,7 @@ int b200conv_prime_history(b200conv_engine* e, const float* host_hist) {
         cudaFree(d_hb);
         if (err != cudaSuccess) return fail(B200CONV_ERR_CUDA, std::string("prime_history (UPOLS): ") + cudaGetErrorString(err));
     }
+    CU_TRY(cudaDeviceSynchronize());  // pageable H2D copies may still be in flight when cudaMemcpy returns
     return B200CONV_OK;
 }
 
@@ -720,6 +724,7 @@ int b200conv_set_mix_gains(b200conv_engine* e, const float* host_gains) {
     ENGINE_DEVICE(e->cfg.device);
     if (!host_gains) return set_default_gains(e);
     CU_TRY(cudaMemcpy(e->d_gains, host_gains, static_cast<size_t>(2) * e->T * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(cudaDeviceSynchronize());  // pageable H2D: the DMA may still be in flight when cudaMemcpy returns
     return B200CONV_OK;
 }
 
@@ -1042,6 +1047,7 @@ int b200conv_set_strip(b200conv_engine* e, const b200conv_strip* strip) {
                           cudaMemcpyHostToDevice));
     e->strip_use_gains = gains != nullptr;
     e->strip_ops = strip->ops & (B200CONV_STRIP_STATS | B200CONV_STRIP_GAIN | B200CONV_STRIP_BIQUAD);
+    CU_TRY(cudaDeviceSynchronize());  // pageable H2D copies above
     return B200CONV_OK;
 }
 
@@ -1051,9 +1057,10 @@ int b200conv_strip_state(b200conv_engine* e, float* host_state, int set) {
     ENGINE_DEVICE(e->cfg.device);
     CU_TRY(cudaDeviceSynchronize());
     const size_t bytes = static_cast<size_t>(2) * e->T * sizeof(float);
-    if (set)
+    if (set) {
         CU_TRY(cudaMemcpy(e->d_strip_state, host_state, bytes, cudaMemcpyHostToDevice));
-    else
+        CU_TRY(cudaDeviceSynchronize());
+    } else
         CU_TRY(cudaMemcpy(host_state, e->d_strip_state, bytes, cudaMemcpyDeviceToHost));
     return B200CONV_OK;
 }
