@@ -14,18 +14,21 @@
 //            (an ordered running sum over groups was tried for UPOLS and lost: the CTAs of a wave retire
 //            together, so the chain serialised ~14 groups at the end of C3: 171 -> 183 us);
 //   level 3  (world > 1) that CTA pushes the chunk into its slot of EVERY peer's symmetric buffer over
-//            NVLink (plain P2P stores), fences, raises its flag on every peer, acquire-polls the
-//            world flags of its own buffer and adds the world slots in rank order.
+//            NVLink and adds the world slots of its own buffer in rank order (bus_ll_* below).
 //
 // Every sum runs in a fixed order whoever executes it, so the bus is deterministic run to run and
 // bit-identical on all ranks; no float atomics.  Counters re-arm themselves (the last arriver
 // stores 0), so a launch needs no memset.  Per-track work is O(B) reads of L2-resident rows; the
 // critical path after the last track is two ticket round trips (+ one NVLink flag round trip).
 //
-// Symmetric buffer layout per rank (b200conv_bus_buffer_bytes): float data[2][world][n] with n = 2*B,
-// then uint32 flags[2][world][kBusMaxChunks]; slot = epoch & 1.  Two slots suffice: a rank cannot
-// finish epoch e+1 before every peer has signalled e+1, which a peer only does after it has consumed
-// epoch e.
+// Exchange protocol ("LL": data and flag travel in ONE 8-byte store, as in NCCL's low-latency protocol):
+// the symmetric buffer of a rank is uint64 ll[2][world][n], n = 2*B, slot = epoch & 1; a value is written as
+// (epoch << 32) | float bits with a single 8-byte store — 8-byte stores are single-copy atomic, so a reader
+// that sees the epoch in the upper half has the value in the lower half.  No fence, no separate flag store,
+// no barrier: every thread pushes its own values to all ranks and polls its own values from all ranks, and
+// the cost is ONE NVLink one-way latency (the first version — P2P stores, __threadfence_system, flag store,
+// acquire poll — paid ~5 us for two hops and a system fence).  Two slots suffice: a rank cannot push epoch e+2
+// before it has read every peer's epoch e+1, which a peer only writes after it has consumed epoch e.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -35,7 +38,15 @@ namespace b200conv {
 
 constexpr int kBusMaxWorld = 16;
 constexpr int kBusMaxChunks = 16;            // B <= 8192 in chunks of >= 512 columns (or one chunk of B < 512)
-constexpr unsigned kBusSpinLimit = 1u << 22;  // bounded wait for a peer (system-scope acquire polls: seconds)
+constexpr unsigned kBusSpinLimit = 1u << 22;  // bounded wait for a peer (volatile polls: seconds)
+
+// The multi-GPU half of the bus: who the peers are.  world == 1: no exchange.
+struct BusExchange {
+    unsigned long long* peers[kBusMaxWorld];  // rank p's symmetric buffer uint64 [2][world][n], mapped on this device
+    int rank, world;
+    uint32_t epoch;  // >= 1, advances by one per exchanged block on every rank
+    uint32_t* err;   // set to 1 if a peer's value did not arrive within the spin bound
+};
 
 struct BusTreeParams {
     const float* gains;  // [T][2]
@@ -47,24 +58,39 @@ struct BusTreeParams {
     int T, B;
     int G1, NG;          // tracks per group, groups
     int CH, NC;          // columns per chunk, chunks
-    // multi-GPU exchange (world == 1: none)
-    float* peers[kBusMaxWorld];
-    int rank, world;
-    uint32_t epoch;
-    uint32_t* err;       // set to 1 if a peer did not signal within the spin bound
+    BusExchange x;       // multi-GPU exchange (x.world == 1: none)
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void bus_st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t bus_ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void bus_bar(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// value i (0 <= i < n) of this rank's bus -> slot [epoch & 1][rank][i] of EVERY rank's buffer (own included)
+__device__ __forceinline__ void bus_ll_push(const BusExchange& x, int n, int i, float v) {
+    const unsigned long long word = (static_cast<unsigned long long>(x.epoch) << 32) | __float_as_uint(v);
+    const size_t off = (static_cast<size_t>(x.epoch & 1u) * x.world + x.rank) * n + i;
+    for (int p = 0; p < x.world; ++p)
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(x.peers[p] + off), "l"(word) : "memory");
+}
+// sum over ranks, in rank order, of value i — polls this rank's own buffer until every rank's word carries the epoch
+__device__ __forceinline__ float bus_ll_sum(const BusExchange& x, int n, int i) {
+    const unsigned long long* mine = x.peers[x.rank] + static_cast<size_t>(x.epoch & 1u) * x.world * n + i;
+    float acc = 0.0f;
+    unsigned spins = 0;
+    for (int q = 0; q < x.world; ++q) {
+        unsigned long long w;
+        for (;;) {
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(mine + static_cast<size_t>(q) * n) : "memory");
+            if (static_cast<uint32_t>(w >> 32) == x.epoch) break;
+            if (++spins > kBusSpinLimit) {
+                *reinterpret_cast<volatile uint32_t*>(x.err) = 1u;  // mapped host memory: a plain store
+                break;
+            }
+        }
+        acc += __uint_as_float(static_cast<uint32_t>(w));
+    }
+    return acc;
 }
 
 // Every level is "data, barrier, ONE thread fences and takes the ticket, barrier" — the barrier orders the other
@@ -75,76 +101,36 @@ __device__ __forceinline__ void bus_bar(uint32_t id, uint32_t nthreads) {
 // The chunk's final local bus {l0, r0, l1, r1} of this thread's NP column pairs -> mix, or over NVLink first.
 // Thread `tid` owns the pairs tid + q * nthr (q < NP) of the chunk; a pair is active when 2 * pair < CH.
 template <int NP>
-__device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int chunk, const float4 (&v)[NP], int tid, int nthr,
-                                                 uint32_t bar_id) {
+__device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int chunk, const float4 (&v)[NP], int tid, int nthr) {
     const int c0 = chunk * bt.CH;
-    if (bt.world == 1) {
+    const int n = 2 * bt.B;
+    if (bt.x.world > 1) {
 #pragma unroll
-        for (int q = 0; q < NP; ++q) {
+        for (int q = 0; q < NP; ++q) {  // all pushes first, then the polls: the NVLink latencies overlap
             const int pair = tid + q * nthr;
             if (2 * pair < bt.CH) {
-                *reinterpret_cast<float2*>(bt.mix + c0 + 2 * pair) = make_float2(v[q].x, v[q].z);
-                *reinterpret_cast<float2*>(bt.mix + bt.B + c0 + 2 * pair) = make_float2(v[q].y, v[q].w);
+                const int col = c0 + 2 * pair;
+                bus_ll_push(bt.x, n, col, v[q].x);
+                bus_ll_push(bt.x, n, col + 1, v[q].z);
+                bus_ll_push(bt.x, n, bt.B + col, v[q].y);
+                bus_ll_push(bt.x, n, bt.B + col + 1, v[q].w);
             }
         }
-        return;
     }
-    const int n = 2 * bt.B;
-    const int slot = bt.epoch & 1u;
-    const size_t data_floats = static_cast<size_t>(2) * bt.world * n;
-    const size_t my_off = (static_cast<size_t>(slot) * bt.world + bt.rank) * n;
 #pragma unroll
-    for (int q = 0; q < NP; ++q) {  // push: my chunk into my slot of EVERY rank's buffer (mine included), straight from registers
+    for (int q = 0; q < NP; ++q) {
         const int pair = tid + q * nthr;
         if (2 * pair < bt.CH) {
             const int col = c0 + 2 * pair;
-            for (int p = 0; p < bt.world; ++p) {
-                float* dst = bt.peers[p] + my_off;
-                *reinterpret_cast<float2*>(dst + col) = make_float2(v[q].x, v[q].z);
-                *reinterpret_cast<float2*>(dst + bt.B + col) = make_float2(v[q].y, v[q].w);
+            float4 s = v[q];
+            if (bt.x.world > 1) {  // fixed rank order: every rank computes the bit-identical sum
+                s.x = bus_ll_sum(bt.x, n, col);
+                s.z = bus_ll_sum(bt.x, n, col + 1);
+                s.y = bus_ll_sum(bt.x, n, bt.B + col);
+                s.w = bus_ll_sum(bt.x, n, bt.B + col + 1);
             }
-        }
-    }
-    bus_bar(bar_id, nthr);
-    if (tid < bt.world) {  // signal rank `tid`, then wait for rank `tid`'s signal
-        __threadfence_system();
-        uint32_t* peer_flags = reinterpret_cast<uint32_t*>(bt.peers[tid] + data_floats);
-        bus_st_release_sys(peer_flags + (slot * bt.world + bt.rank) * kBusMaxChunks + chunk, bt.epoch);
-        const uint32_t* my_flags = reinterpret_cast<const uint32_t*>(bt.peers[bt.rank] + data_floats);
-        unsigned spins = 0;
-        while (bus_ld_acquire_sys(my_flags + (slot * bt.world + tid) * kBusMaxChunks + chunk) != bt.epoch) {
-            if (++spins > kBusSpinLimit) {
-                *reinterpret_cast<volatile uint32_t*>(bt.err) = 1u;  // mapped host memory: a plain store
-                break;
-            }
-        }
-    }
-    bus_bar(bar_id, nthr);
-    const float* base = bt.peers[bt.rank] + static_cast<size_t>(slot) * bt.world * n;
-#pragma unroll
-    for (int q = 0; q < NP; ++q) {  // fixed rank order: every rank computes the bit-identical sum
-        const int pair = tid + q * nthr;
-        if (2 * pair < bt.CH) {
-            const int col = c0 + 2 * pair;
-            float2 l = make_float2(0.0f, 0.0f), r = make_float2(0.0f, 0.0f);
-            for (int q0 = 0; q0 < bt.world; q0 += 8) {
-                float2 vl[8], vr[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const bool ok = q0 + j < bt.world;
-                    vl[j] = ok ? __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(q0 + j) * n + col)) : make_float2(0.0f, 0.0f);
-                    vr[j] = ok ? __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(q0 + j) * n + bt.B + col)) : make_float2(0.0f, 0.0f);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (q0 + j < bt.world) {
-                        l.x += vl[j].x; l.y += vl[j].y;
-                        r.x += vr[j].x; r.y += vr[j].y;
-                    }
-                }
-            }
-            *reinterpret_cast<float2*>(bt.mix + col) = l;
-            *reinterpret_cast<float2*>(bt.mix + bt.B + col) = r;
+            *reinterpret_cast<float2*>(bt.mix + col) = make_float2(s.x, s.z);
+            *reinterpret_cast<float2*>(bt.mix + bt.B + col) = make_float2(s.y, s.w);
         }
     }
 }
@@ -246,7 +232,7 @@ __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, 
             }
         }
     }
-    bus_finish_chunk<NP>(bt, chunk, part, tid, nthr, bar_id);
+    bus_finish_chunk<NP>(bt, chunk, part, tid, nthr);
 }
 #endif  // __CUDACC__
 

@@ -333,13 +333,15 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stand-alone stereo bus of an output that is already in memory — only the paths that cannot take
-// the bus tree in their last compute kernel use it (a channel strip between convolution and bus on
-// the direct engine, the three-kernel UPOLS path).  Thread-block cluster per 32-sample column tile:
+// Stand-alone stereo bus of an output that is already in memory: the UPOLS engine (its tracks retire one by
+// one over the whole launch, and a per-track ticket in the streaming CTA cost more than this PDL-launched
+// kernel: measured 128 -> 133 us on the C4 shard) and a channel strip between convolution and bus.  On a
+// multi-GPU job the thread that holds a finished bus sample exchanges it over NVLink right here
+// (bus_ll_push / bus_ll_sum) — the collective needs no launch of its own.  Thread-block cluster per 32-sample column tile:
 // grid (B/32, CY), cluster (1, CY); the partials are reduced warp -> CTA (shared memory) -> cluster
 // (rank 0 reads the other CTAs' shared memory over DSMEM) in a fixed order.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cluster_bus_reduce(float l, float r, float* mix, int n0, int B) {
+__device__ __forceinline__ void cluster_bus_reduce(float l, float r, float* mix, int n0, int B, const BusExchange& x) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float part[kBusWarps][2][32];
@@ -361,14 +363,22 @@ __device__ __forceinline__ void cluster_bus_reduce(float l, float r, float* mix,
         float v = 0.0f;
         const unsigned nranks = cluster.num_blocks();
         for (unsigned rk = 0; rk < nranks; ++rk) v += cluster.map_shared_rank(&csum[0][0], rk)[c * 32 + lane];
-        if (n0 + lane < B) mix[static_cast<size_t>(c) * B + n0 + lane] = v;
+        if (n0 + lane < B) {
+            const int i = c * B + n0 + lane;
+            if (x.world > 1) {  // multi-GPU: this thread's bus sample over NVLink, summed in rank order
+                bus_ll_push(x, 2 * B, i, v);
+                v = bus_ll_sum(x, 2 * B, i);
+            }
+            mix[i] = v;
+        }
     }
     cluster.sync();  // nobody's shared memory may go away before rank 0 has read it
 }
 
 __global__ void __launch_bounds__(kBusWarps * 32) mix_cluster_kernel(const float* __restrict__ y, int sample_major, int Tg,
                                                                       int toff, const float* __restrict__ gains,
-                                                                      float* __restrict__ mix, int T, int B) {
+                                                                      float* __restrict__ mix, int T, int B,
+                                                                      const __grid_constant__ BusExchange x) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n0 = blockIdx.x * 32, n = n0 + lane;
     const int ngroups = (T + kMixChunk - 1) / kMixChunk;
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(kBusWarps * 32) mix_cluster_kernel(const float
             }
         }
     }
-    cluster_bus_reduce(l, r, mix, n0, B);
+    cluster_bus_reduce(l, r, mix, n0, B, x);
 }
 
 // Sample-major output y[n][Tg]: a row holds one sample of every track, so the bus is a plain row
@@ -403,7 +413,8 @@ __global__ void __launch_bounds__(kBusWarps * 32) mix_cluster_kernel(const float
 // No cross-CTA step is needed at all (measured: 6.2 us -> ~3 us at C3 against the column-tile kernel).
 __global__ void __launch_bounds__(kBusWarps * 32) mix_rows_kernel(const float* __restrict__ y, int Tg, int toff,
                                                                    const float* __restrict__ gains,
-                                                                   float* __restrict__ mix, int T, int B) {
+                                                                   float* __restrict__ mix, int T, int B,
+                                                                   const __grid_constant__ BusExchange x) {
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * kBusWarps + (threadIdx.x >> 5);
     pdl_launch_dependents();
@@ -423,9 +434,14 @@ __global__ void __launch_bounds__(kBusWarps * 32) mix_rows_kernel(const float* _
         l += __shfl_xor_sync(0xffffffffu, l, off);
         r += __shfl_xor_sync(0xffffffffu, r, off);
     }
-    if (lane == 0) {
-        mix[n] = l;
-        mix[B + n] = r;
+    if (lane < 2) {  // lane 0: left, lane 1: right (both hold the full sums after the xor tree)
+        float v = lane ? r : l;
+        const int i = lane * B + n;
+        if (x.world > 1) {  // multi-GPU: over NVLink, summed in rank order
+            bus_ll_push(x, 2 * B, i, v);
+            v = bus_ll_sum(x, 2 * B, i);
+        }
+        mix[i] = v;
     }
 }
 
@@ -491,7 +507,7 @@ static cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, int cy,
 }
 
 cudaError_t launch_mix_cluster(const float* y, int sample_major, int Tg, int toff, const float* gains, float* mix, int T,
-                               int B, cudaStream_t st) {
+                               int B, const BusExchange& x, cudaStream_t st) {
     if (sample_major) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((B + kBusWarps - 1) / kBusWarps);
@@ -502,10 +518,10 @@ cudaError_t launch_mix_cluster(const float* y, int sample_major, int Tg, int tof
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, mix_rows_kernel, y, Tg, toff, gains, mix, T, B);
+        return cudaLaunchKernelEx(&cfg, mix_rows_kernel, y, Tg, toff, gains, mix, T, B, x);
     }
     const int cy = bus_cluster_height(T);
-    return launch_clustered(mix_cluster_kernel, dim3((B + 31) / 32, cy), cy, st, y, sample_major, Tg, toff, gains, mix, T, B);
+    return launch_clustered(mix_cluster_kernel, dim3((B + 31) / 32, cy), cy, st, y, sample_major, Tg, toff, gains, mix, T, B, x);
 }
 
 }  // namespace b200conv

@@ -54,7 +54,8 @@ cudaError_t launch_fir(const FirParams& p, int A, size_t smem, cudaStream_t st);
 // Most partial rows any track-tile receives when U = n_tiles_total * NS units are split over G CTAs.
 int fir_max_segments(int n_tiles_total, int NS, int G);
 // Deterministic stereo bus of an output already in memory: mix[c][n] = sum_t gains[t][c] * y_t[n].
+// x.world > 1: the bus is exchanged over NVLink and summed in rank order inside this kernel.
 cudaError_t launch_mix_cluster(const float* y, int sample_major, int Tg, int toff, const float* gains, float* mix, int T,
-                               int B, cudaStream_t st);
+                               int B, const BusExchange& x, cudaStream_t st);
 
 }  // namespace b200conv

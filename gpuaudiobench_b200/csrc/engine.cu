@@ -323,6 +323,17 @@ StripParams strip_params(b200conv_engine* e, float* d_out, bool commit) {
     return sp;
 }
 
+// Who the peers are for this block's bus exchange (world == 1: none).  The epoch was advanced by the caller.
+BusExchange bus_exchange(const b200conv_engine* e) {
+    BusExchange x{};
+    x.rank = e->bus_rank;
+    x.world = e->bus_world;
+    for (int i = 0; i < e->bus_world; ++i) x.peers[i] = reinterpret_cast<unsigned long long*>(e->bus_peers[i]);
+    x.epoch = e->bus_epoch;
+    x.err = e->d_bus_err;
+    return x;
+}
+
 // The bus tree of this block (bus_tree.cuh).  d_mix == null disables it.  On a multi-GPU job the epoch was
 // advanced by the caller (once per block with a bus, in lockstep on every rank).
 BusTreeParams bus_params(const b200conv_engine* e, float* d_mix) {
@@ -340,23 +351,8 @@ BusTreeParams bus_params(const b200conv_engine* e, float* d_mix) {
     b.NG = e->bus_NG;
     b.CH = e->bus_CH;
     b.NC = e->bus_NC;
-    b.rank = e->bus_rank;
-    b.world = e->bus_world;
-    for (int i = 0; i < e->bus_world; ++i) b.peers[i] = reinterpret_cast<float*>(e->bus_peers[i]);
-    b.epoch = e->bus_epoch;
-    b.err = e->d_bus_err;
+    b.x = bus_exchange(e);
     return b;
-}
-
-// Stand-alone all-reduce of a local bus already in d_mix: only the paths whose last kernel cannot carry the
-// bus tree (direct engine with a channel strip, three-kernel UPOLS) need it on a multi-GPU job.
-int allreduce_local_bus(b200conv_engine* e, float* d_mix, cudaStream_t st) {
-    if (e->bus_world <= 1 || !d_mix) return B200CONV_OK;
-    const int rc = b200conv_bus_allreduce(d_mix, d_mix, e->bus_peers, e->bus_rank, e->bus_world, 2 * e->B, e->bus_epoch,
-                                          e->d_bus_err, st);
-    if (rc) return fail(rc, "b200conv_bus_allreduce launch failed");
-    e->launches += 1;
-    return B200CONV_OK;
 }
 
 struct StageTimer {
@@ -791,9 +787,8 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             int rc = run_strip(e, d_out, commit, st);
             if (rc) return rc;
             if (d_mix) {
-                CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
+                CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, bus_exchange(e), st));
                 e->launches += 1;
-                if ((rc = allreduce_local_bus(e, d_mix, st))) return rc;
             }
             tm.mark();
         }
@@ -831,9 +826,8 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             int rc = run_strip(e, d_out, commit, st);
             if (rc) return rc;
             if (d_mix) {
-                CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
+                CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, bus_exchange(e), st));
                 e->launches += 1;
-                if ((rc = allreduce_local_bus(e, d_mix, st))) return rc;
             }
             tm.mark();
         }
@@ -867,10 +861,11 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             fp.Tg = e->Tg;
             fp.toff = e->toff;
             if (e->strip_ops) fp.strip = strip_params(e, d_out, commit);  // strip runs inside the kernel's epilogue
-            // ... and, on a multi-GPU job, so do the bus and its all-reduce.  A stand-alone engine keeps the
-            // PDL-launched bus kernel: per track the tree costs a ticket round trip that the streaming CTA
-            // cannot hide, measured 128 -> 133 us on the C4 shard and 166 -> 171 us at C3 on one GPU
-            const bool tree = (e->bus_world > 1) || e->bus_in_kernel_single;
+            // The bus stays in the PDL-launched bus kernel (which also carries the NVLink exchange of a multi-GPU
+            // job): inside this kernel it costs a ticket round trip per track that the streaming CTA cannot hide,
+            // measured 128 -> 133 us on the C4 shard and 166 -> 171 us at C3.  B200CONV_BUS_TREE=1 selects the
+            // in-kernel tree anyway (one launch per block; kept for measurement and tested).
+            const bool tree = e->bus_in_kernel_single;
             fp.bus = bus_params(e, tree ? d_mix : nullptr);
             CU_TRY(launch_upols_fused(fp, st));
             e->launches += 1;
@@ -919,11 +914,10 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             int rc = run_strip(e, d_out, commit, st);
             if (rc) return rc;
         }
-        const bool tree_done = u.fused && ((e->bus_world > 1) || e->bus_in_kernel_single);
+        const bool tree_done = u.fused && e->bus_in_kernel_single;
         if (d_mix && !tree_done) {
-            CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, st));
+            CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, bus_exchange(e), st));
             e->launches += 1;
-            if (int rc = allreduce_local_bus(e, d_mix, st)) return rc;
         }
         if (!u.fused || (d_mix && !tree_done)) tm.mark();
         marks = tm.idx;
@@ -962,7 +956,7 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     // place on the output), the three-kernel UPOLS path, and sample-major UPOLS (a column tile written track
     // by track is scattered 4-byte PCIe writes: measured 2x slower than the staged copy).
     const bool fused_ok = !direct && e->up.fused && e->cfg.out_layout == B200CONV_OUT_TRACK_MAJOR;
-    const bool tree = (e->bus_world > 1) || e->bus_in_kernel_single;  // UPOLS: the bus rides in the fused kernel
+    const bool tree = e->bus_in_kernel_single;  // UPOLS: the bus rides in the fused kernel (measurement option)
     const bool pinned_results = (zc & 2) && h_out && is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
     const bool out_place = pinned_results && ((direct && !e->strip_ops) || (fused_ok && (tree || !h_mix)));
     // stand-alone fused UPOLS with a bus: the PDL-launched bus kernel reads the output back, so the fused kernel
@@ -1186,7 +1180,7 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
         info->partitions = e->up.P;
         info->fft_size = 2 * e->B;
         if (e->up.fused) {
-            const bool tree = (e->bus_world > 1) || e->bus_in_kernel_single;
+            const bool tree = e->bus_in_kernel_single;
             info->kernels_per_block = tree ? 1 : 2;
             info->stage_count = tree ? 1 : 2;
             info->dominant_stage = 0;

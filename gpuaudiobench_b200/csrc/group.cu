@@ -101,7 +101,16 @@ void worker_loop(b200conv_group* g, int idx) {
     }
 }
 
+// The calling thread's current device is left as it was found (the engine calls guard themselves; the few
+// runtime calls made here directly are bracketed by this).
+struct CallerDevice {
+    int dev = -1;
+    CallerDevice() { if (cudaGetDevice(&dev) != cudaSuccess) dev = -1; }
+    ~CallerDevice() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 template <typename F> int for_each_member(b200conv_group* g, F&& fn) {
+    CallerDevice keep;
     for (Member& m : g->members) {
         if (cudaSetDevice(m.device) != cudaSuccess) return gfail(B200CONV_ERR_CUDA, "cudaSetDevice failed");
         const int rc = fn(m);
@@ -124,6 +133,7 @@ int b200conv_group_create(const b200conv_config* cfg, int n_gpus, b200conv_group
         return gfail(B200CONV_ERR_NO_DEVICE, "b200conv_group_create: " + std::to_string(n_gpus) + " GPUs requested, " +
                                                  std::to_string(ndev) + " visible (no CPU fallback)");
     if (cfg->tracks < static_cast<uint32_t>(n_gpus)) return gfail(B200CONV_ERR_INVALID, "b200conv_group_create: fewer tracks than GPUs");
+    CallerDevice keep;
     auto* g = new b200conv_group();
     g->cfg = *cfg;
     g->n = n_gpus;
@@ -177,6 +187,7 @@ int b200conv_group_create(const b200conv_config* cfg, int n_gpus, b200conv_group
 
 void b200conv_group_destroy(b200conv_group* g) {
     if (!g) return;
+    CallerDevice keep;
     {
         std::lock_guard<std::mutex> lk(g->mu);
         g->stop = true;
