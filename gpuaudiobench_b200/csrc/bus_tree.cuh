@@ -73,24 +73,54 @@ __device__ __forceinline__ void bus_ll_push(const BusExchange& x, int n, int i, 
     for (int p = 0; p < x.world; ++p)
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(x.peers[p] + off), "l"(word) : "memory");
 }
-// sum over ranks, in rank order, of value i — polls this rank's own buffer until every rank's word carries the epoch
-__device__ __forceinline__ float bus_ll_sum(const BusExchange& x, int n, int i) {
-    const unsigned long long* mine = x.peers[x.rank] + static_cast<size_t>(x.epoch & 1u) * x.world * n + i;
-    float acc = 0.0f;
-    unsigned spins = 0;
-    for (int q = 0; q < x.world; ++q) {
-        unsigned long long w;
+// Sums over ranks, in rank order, of NV values of this thread (indices idx[j], ignored where !act[j]): polls this
+// rank's own buffer until every rank's word carries the epoch.  All NV x 4 words of a group of four ranks are
+// loaded together and checked together — the wait is one round trip per group of ranks, not one per word (the
+// first version polled word after word: 16 dependent L2 round trips, ~10 us, at the end of the C2 step).
+template <int NV>
+__device__ __forceinline__ void bus_ll_gather(const BusExchange& x, int n, const int (&idx)[NV], const bool (&act)[NV],
+                                              float (&acc)[NV]) {
+    const unsigned long long* mine = x.peers[x.rank] + static_cast<size_t>(x.epoch & 1u) * x.world * n;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
+    for (int q0 = 0; q0 < x.world; q0 += 4) {
+        unsigned long long w[4][NV];
+        unsigned spins = 0;
         for (;;) {
-            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(mine + static_cast<size_t>(q) * n) : "memory");
-            if (static_cast<uint32_t>(w >> 32) == x.epoch) break;
+            bool ok = true;
+#pragma unroll
+            for (int dq = 0; dq < 4; ++dq) {
+                const unsigned long long* src = mine + static_cast<size_t>(min(q0 + dq, x.world - 1)) * n;
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[dq][j]) : "l"(src + (act[j] ? idx[j] : 0)) : "memory");
+            }
+#pragma unroll
+            for (int dq = 0; dq < 4; ++dq)
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+                    if (q0 + dq < x.world && act[j] && static_cast<uint32_t>(w[dq][j] >> 32) != x.epoch) ok = false;
+            if (ok) break;
             if (++spins > kBusSpinLimit) {
                 *reinterpret_cast<volatile uint32_t*>(x.err) = 1u;  // mapped host memory: a plain store
                 break;
             }
         }
-        acc += __uint_as_float(static_cast<uint32_t>(w));
+#pragma unroll
+        for (int dq = 0; dq < 4; ++dq)
+            if (q0 + dq < x.world) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) acc[j] += __uint_as_float(static_cast<uint32_t>(w[dq][j]));
+            }
     }
-    return acc;
+}
+// one value
+__device__ __forceinline__ float bus_ll_sum(const BusExchange& x, int n, int i) {
+    const int idx[1] = {i};
+    const bool act[1] = {true};
+    float acc[1];
+    bus_ll_gather<1>(x, n, idx, act, acc);
+    return acc[0];
 }
 
 // Every level is "data, barrier, ONE thread fences and takes the ticket, barrier" — the barrier orders the other
@@ -117,20 +147,31 @@ __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int ch
             }
         }
     }
+    float sum[4 * NP];
+    if (bt.x.world > 1) {  // fixed rank order: every rank computes the bit-identical sum
+        int idx[4 * NP];
+        bool act[4 * NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int pair = tid + q * nthr;
+            const int col = c0 + 2 * pair;
+            idx[4 * q] = col; idx[4 * q + 1] = col + 1; idx[4 * q + 2] = bt.B + col; idx[4 * q + 3] = bt.B + col + 1;
+            act[4 * q] = act[4 * q + 1] = act[4 * q + 2] = act[4 * q + 3] = (2 * pair < bt.CH);
+        }
+        bus_ll_gather<4 * NP>(bt.x, n, idx, act, sum);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            sum[4 * q] = v[q].x; sum[4 * q + 1] = v[q].z; sum[4 * q + 2] = v[q].y; sum[4 * q + 3] = v[q].w;
+        }
+    }
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         const int pair = tid + q * nthr;
         if (2 * pair < bt.CH) {
             const int col = c0 + 2 * pair;
-            float4 s = v[q];
-            if (bt.x.world > 1) {  // fixed rank order: every rank computes the bit-identical sum
-                s.x = bus_ll_sum(bt.x, n, col);
-                s.z = bus_ll_sum(bt.x, n, col + 1);
-                s.y = bus_ll_sum(bt.x, n, bt.B + col);
-                s.w = bus_ll_sum(bt.x, n, bt.B + col + 1);
-            }
-            *reinterpret_cast<float2*>(bt.mix + col) = make_float2(s.x, s.z);
-            *reinterpret_cast<float2*>(bt.mix + bt.B + col) = make_float2(s.y, s.w);
+            *reinterpret_cast<float2*>(bt.mix + col) = make_float2(sum[4 * q], sum[4 * q + 1]);
+            *reinterpret_cast<float2*>(bt.mix + bt.B + col) = make_float2(sum[4 * q + 2], sum[4 * q + 3]);
         }
     }
 }

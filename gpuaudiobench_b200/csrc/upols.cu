@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 #endif
 constexpr int kPrefetchParts = B200CONV_FUSED_PREFETCH;  // partitions pulled into L2 under the forward FFT
 
-template <int kFusedUnroll, int kMinCtas, bool kStrip>
+template <int kFusedUnroll, int kMinCtas, bool kStrip, bool kBusTree = false>
 __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
     __shared__ int s_last;
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
         if (tid == 0) strip_track_in_smem(p.strip, t, const_cast<float*>(reinterpret_cast<const float*>(z + half)), M);
         __syncthreads();
     }
-    if (p.bus.mix) {
+    if (kBusTree && p.bus.mix) {  // measurement option (B200CONV_BUS_TREE=1): a separate instantiation, the product kernel has none of this
         // stereo bus first (its tickets are the critical path after the last track): this track's row goes to the
         // tree's scratch; the last track of a group sums the group, groups are folded in order into the running bus,
         // and on a multi-GPU job the last one exchanges the bus over NVLink (bus_tree.cuh) — no further launch
@@ -576,6 +576,13 @@ int upols_fused_occupancy() {
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st) {
     dim3 grid(p.S, p.T);
     const size_t smem = static_cast<size_t>(2) * p.M * sizeof(float2) + 256 * 8 * sizeof(float);
+    if (p.bus.mix) {  // in-kernel bus tree requested (B200CONV_BUS_TREE=1)
+        if (p.strip.ops)
+            upols_fused_kernel<4, 4, true, true><<<grid, 256, smem, st>>>(p);
+        else
+            upols_fused_kernel<4, 4, false, true><<<grid, 256, smem, st>>>(p);
+        return cudaGetLastError();
+    }
     if (p.strip.ops) {  // strip in the epilogue: one more instantiation of the product configuration
         upols_fused_kernel<4, 4, true><<<grid, 256, smem, st>>>(p);
         return cudaGetLastError();
