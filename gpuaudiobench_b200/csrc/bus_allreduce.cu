@@ -44,6 +44,7 @@ extern "C" int b200conv_bus_allreduce(const float* d_local, float* d_out, const 
     x.world = world;
     x.epoch = epoch;
     x.err = d_error_flag;
+    x.trace = nullptr;
     const int threads = n >= 1024 ? 1024 : ((n + 31) / 32 * 32 < 32 ? 32 : (n + 31) / 32 * 32);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1);

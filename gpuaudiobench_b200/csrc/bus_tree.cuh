@@ -46,7 +46,10 @@ struct BusExchange {
     int rank, world;
     uint32_t epoch;  // >= 1, advances by one per exchanged block on every rank
     uint32_t* err;   // set to 1 if a peer's value did not arrive within the spin bound
+    unsigned long long* trace;  // optional diagnostics (b200conv_bus_trace): [kBusTraceLen][2] = %globaltimer ns when this
+                                // rank's bus was ready to push / when the summed bus was complete, indexed by epoch
 };
+constexpr int kBusTraceLen = 4096;
 
 struct BusTreeParams {
     const float* gains;  // [T][2]
@@ -66,6 +69,12 @@ __device__ __forceinline__ void bus_bar(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// What the exchange costs (2 x B200 over NVLink, b200conv_bus_trace device timestamps, profiles/experiments/
+// n2_exchange_*.jsonl): push -> summed bus 0.5 us when blocks follow each other back to back, but 9.5-12 us when
+// bench.py's L2 flush (512 MB streamed through each GPU) sits between blocks — symmetric on both ranks while their
+// ready times differ by < 2 us, i.e. one-way latency of the first remote store after the flush, not rank skew.
+// None of these moved it: weak / relaxed.sys / volatile stores, a system fence after the push, prefetching the
+// receive slot into L2, a throw-away remote load at kernel start from one thread (from every CTA it cost +5 us).
 // value i (0 <= i < n) of this rank's bus -> slot [epoch & 1][rank][i] of EVERY rank's buffer (own included)
 __device__ __forceinline__ void bus_ll_push(const BusExchange& x, int n, int i, float v) {
     const unsigned long long word = (static_cast<unsigned long long>(x.epoch) << 32) | __float_as_uint(v);
@@ -134,6 +143,11 @@ template <int NP>
 __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int chunk, const float4 (&v)[NP], int tid, int nthr) {
     const int c0 = chunk * bt.CH;
     const int n = 2 * bt.B;
+    if (bt.x.world > 1 && bt.x.trace && tid == 0 && chunk == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        bt.x.trace[(bt.x.epoch % kBusTraceLen) * 2] = now;
+    }
     if (bt.x.world > 1) {
 #pragma unroll
         for (int q = 0; q < NP; ++q) {  // all pushes first, then the polls: the NVLink latencies overlap
@@ -159,6 +173,11 @@ __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int ch
             act[4 * q] = act[4 * q + 1] = act[4 * q + 2] = act[4 * q + 3] = (2 * pair < bt.CH);
         }
         bus_ll_gather<4 * NP>(bt.x, n, idx, act, sum);
+        if (bt.x.trace && tid == 0 && chunk == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            bt.x.trace[(bt.x.epoch % kBusTraceLen) * 2 + 1] = now;
+        }
     } else {
 #pragma unroll
         for (int q = 0; q < NP; ++q) {

@@ -118,6 +118,7 @@ struct b200conv_engine {
     int bus_world = 1, bus_rank = 0;
     uint64_t bus_peers[kBusMaxWorld] = {};
     uint32_t bus_epoch = 0;
+    unsigned long long* d_bus_trace = nullptr;  // B200CONV_BUS_TRACE=1: per-epoch (ready, done) %globaltimer stamps
     uint32_t* d_bus_err = nullptr;  // pinned, mapped host word (UVA): kernels store 1 on a spin timeout, the host
                                     // reads it after its stream synchronise without a copy
     DirectState dir;
@@ -331,6 +332,7 @@ BusExchange bus_exchange(const b200conv_engine* e) {
     for (int i = 0; i < e->bus_world; ++i) x.peers[i] = reinterpret_cast<unsigned long long*>(e->bus_peers[i]);
     x.epoch = e->bus_epoch;
     x.err = e->d_bus_err;
+    x.trace = e->d_bus_trace;
     return x;
 }
 
@@ -499,6 +501,8 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         err = cudaHostAlloc(reinterpret_cast<void**>(&e->d_bus_err), sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable);
         if (err != cudaSuccess) return bail(fail(B200CONV_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(err)));
         *e->d_bus_err = 0;
+        if (env_int("B200CONV_BUS_TRACE", 0))
+            if ((rc = dev_alloc(e, &e->d_bus_trace, static_cast<size_t>(2) * kBusTraceLen))) return bail(rc);
     }
 
     if (impl == B200CONV_ALGO_DIRECT) {
@@ -1125,6 +1129,23 @@ int b200conv_attach_bus(b200conv_engine* e, const uint64_t* peer_buffers, int ra
     e->bus_epoch = 0;
     for (int i = 0; i < world; ++i) e->bus_peers[i] = peer_buffers[i];
     *e->d_bus_err = 0;
+    return B200CONV_OK;
+}
+
+int b200conv_bus_trace(b200conv_engine* e, uint64_t* host_stamps, int count) {
+    if (!e || !host_stamps || count < 1) return fail(B200CONV_ERR_INVALID, "b200conv_bus_trace: bad argument");
+    if (!e->d_bus_trace) return fail(B200CONV_ERR_STATE, "b200conv_bus_trace: create the engine with B200CONV_BUS_TRACE=1 in the environment");
+    ENGINE_DEVICE(e->cfg.device);
+    CU_TRY(cudaDeviceSynchronize());
+    count = std::min(count, kBusTraceLen);
+    // rows = the last `count` epochs, oldest first
+    std::vector<unsigned long long> all(static_cast<size_t>(2) * kBusTraceLen);
+    CU_TRY(cudaMemcpy(all.data(), e->d_bus_trace, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < count; ++i) {
+        const uint32_t ep = e->bus_epoch - static_cast<uint32_t>(count - 1 - i);
+        host_stamps[2 * i] = all[(ep % kBusTraceLen) * 2];
+        host_stamps[2 * i + 1] = all[(ep % kBusTraceLen) * 2 + 1];
+    }
     return B200CONV_OK;
 }
 

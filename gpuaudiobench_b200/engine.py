@@ -84,6 +84,7 @@ def load_library():
                                          C.c_uint32, C.c_void_p, C.c_void_p]
     L.b200conv_attach_bus.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int]
     L.b200conv_bus_status.argtypes = [C.c_void_p]
+    L.b200conv_bus_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
     L.b200conv_group_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]
     L.b200conv_group_destroy.argtypes = [C.c_void_p]
     L.b200conv_group_destroy.restype = None
@@ -360,6 +361,12 @@ class ConvEngine:
 
     def bus_status(self):
         _check(self.lib.b200conv_bus_status(self.handle))
+
+    def bus_trace(self, count):
+        """(ready_ns, done_ns) device timestamps of the last `count` bus exchanges (B200CONV_BUS_TRACE=1), [count][2]."""
+        buf = (C.c_uint64 * (2 * count))()
+        _check(self.lib.b200conv_bus_trace(self.handle, buf, count))
+        return np.array(buf, dtype=np.uint64).reshape(count, 2)
 
     def set_profiling(self, on):
         _check(self.lib.b200conv_set_profiling(self.handle, 1 if on else 0))

@@ -234,6 +234,11 @@ int b200conv_attach_bus(b200conv_engine* e, const uint64_t* peer_buffers, int ra
  * call (bounded spin, a few seconds: the kernel gives up instead of hanging the GPU), else B200CONV_OK.
  * b200conv_process_host checks this itself on every block. */
 int b200conv_bus_status(b200conv_engine* e);
+/* Diagnostics: for the last `count` (<= 4096) blocks with a bus exchange, oldest first, host_stamps[2i] = device
+ * %globaltimer (ns) when this rank's local bus was complete and its push began, host_stamps[2i+1] = when the summed bus
+ * was complete; the difference is what the block spent on the exchange, rank skew included.  Tree-exchange kernels
+ * only (direct engines); the engine must have been created with B200CONV_BUS_TRACE=1 in the environment. */
+int b200conv_bus_trace(b200conv_engine* e, uint64_t* host_stamps, int count);
 
 /* ---- multi-GPU in one process: one engine per GPU over contiguous track ranges -------------------
  * cfg->tracks is the TOTAL track count Tg (cfg->device / track_offset / total_tracks are ignored);

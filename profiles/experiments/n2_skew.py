@@ -17,6 +17,7 @@ from gpuaudiobench_b200 import synth
 from gpuaudiobench_b200.distributed import EngineBusGroup
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+os.environ["B200CONV_BUS_TRACE"] = "1"
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 dev = torch.device("cuda", lr)
@@ -63,9 +64,19 @@ res["b_no_bus"] = run(0)
 grp = EngineBusGroup(e, mix)
 res["kind"] = grp.kind[:40]
 res["a_flush_exchange"] = run(mix.data_ptr())
-res["d_aligned_every_step"] = run(mix.data_ptr(), align=True)
+if wl == "c2":
+    tr = e.bus_trace(K).astype(np.int64)  # the K steps just timed
+    mine = torch.from_numpy(tr).to(dev)
+    both = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    a, b = both[0].cpu().numpy(), both[1].cpu().numpy()
+    res["trace_wait_us_rank0_[mean,median,p90]"] = [round(float(v) / 1e3, 2) for v in ((a[:, 1] - a[:, 0]).mean(), np.median(a[:, 1] - a[:, 0]), np.percentile(a[:, 1] - a[:, 0], 90))]
+    res["trace_wait_us_rank1_[mean,median,p90]"] = [round(float(v) / 1e3, 2) for v in ((b[:, 1] - b[:, 0]).mean(), np.median(b[:, 1] - b[:, 0]), np.percentile(b[:, 1] - b[:, 0], 90))]
+    d = (a[:, 0] - b[:, 0]) / 1e3  # ready-time difference between the ranks (if the two %globaltimers agree)
+    res["ready_time_rank0_minus_rank1_us_[mean,std,mean_abs]"] = [round(float(d.mean()), 2), round(float(d.std()), 2), round(float(np.abs(d - d.mean()).mean()), 2)]
 res["e_back_to_back_exchange"] = run(mix.data_ptr(), flush=False)
-res["a2_flush_exchange_again"] = run(mix.data_ptr())
+res["d_aligned_every_step"] = run(mix.data_ptr(), align=True)
+
 grp.check()
 grp.close()
 if rank == 0:
