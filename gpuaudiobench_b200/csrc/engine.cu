@@ -104,9 +104,17 @@ struct b200conv_engine {
     cudaStream_t own_stream = nullptr;
     cudaStream_t last_stream = nullptr;  // stream of the latest process(): state (ring, delay line) is ordered on it
     bool has_last_stream = false;
-    float* d_in_stage = nullptr;
+    float* d_in_stage = nullptr;   // staging slot 0 (slot 1 below: b200conv_submit double-buffers)
     float* d_out_stage = nullptr;
     float* d_mix_stage = nullptr;
+    float* d_in_stage1 = nullptr;
+    float* d_out_stage1 = nullptr;
+    float* d_mix_stage1 = nullptr;
+    cudaStream_t copy_stream = nullptr;              // device -> host copies of block m run here, under block m+1's kernels
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};     // kernels of the slot's block have finished
+    cudaEvent_t ev_out[2] = {nullptr, nullptr};      // the slot's results are on the host
+    uint64_t submitted = 0, completed = 0;           // tickets handed out / waited for
+    bool slot_has_bus[2] = {false, false};
     float* d_gains = nullptr;
     // stereo-bus tree (bus_tree.cuh): scratch rows, group partials, tickets
     float* d_ybus = nullptr;      // [T][B]
@@ -526,7 +534,13 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if ((rc = dev_alloc(e, &u.counters, static_cast<size_t>(e->T)))) return bail(rc);
     }
     err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) return bail(fail(B200CONV_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(err)));
+    for (int i = 0; i < 2; ++i) {
+        err = cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming);
+        if (err != cudaSuccess) return bail(fail(B200CONV_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(err)));
+    }
     for (auto& ev : e->ev) {
         err = cudaEventCreate(&ev);
         if (err != cudaSuccess) return bail(fail(B200CONV_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(err)));
@@ -543,6 +557,11 @@ void b200conv_destroy(b200conv_engine* e) {
     for (auto& ev : e->ev)
         if (ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+    }
     if (e->d_bus_err) cudaFreeHost(e->d_bus_err);
     delete e;
 }
@@ -945,20 +964,39 @@ bool is_pinned_host(const void* p) {
 }
 }  // namespace
 
-int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix, uint32_t flags) {
-    if (!e || !h_in) return fail(B200CONV_ERR_INVALID, "b200conv_process_host: null argument");
-    ENGINE_DEVICE(e->cfg.device);
+namespace {
+int wait_slot(b200conv_engine* e, int slot) {
+    CU_TRY(cudaEventSynchronize(e->ev_out[slot]));
+    if (e->bus_world > 1 && e->slot_has_bus[slot] && *static_cast<volatile uint32_t*>(e->d_bus_err)) {
+        *e->d_bus_err = 0;  // did a peer engine miss the bus exchange of this block?
+        return fail(B200CONV_ERR_CUDA, "bus all-reduce: a peer engine did not signal within the spin bound");
+    }
+    return B200CONV_OK;
+}
+
+// Enqueue one host-buffer block on staging slot `slot` and record ev_out[slot] when its results are on the host.
+int submit_slot(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix, uint32_t flags, int slot) {
     cudaStream_t st = e->own_stream;
     const size_t tb = static_cast<size_t>(e->T) * e->B;
+    const size_t out_elems = (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR) ? static_cast<size_t>(e->B) * e->Tg : tb;
+    if (slot == 1 && !e->d_in_stage1) {  // second staging set: allocated on the first pipelined submit
+        int rc = dev_alloc(e, &e->d_in_stage1, tb);
+        if (!rc) rc = dev_alloc(e, &e->d_out_stage1, out_elems);
+        if (!rc) rc = dev_alloc(e, &e->d_mix_stage1, static_cast<size_t>(2) * e->B);
+        if (rc) return rc;
+    }
+    float* in_stage = slot ? e->d_in_stage1 : e->d_in_stage;
+    float* out_stage = slot ? e->d_out_stage1 : e->d_out_stage;
+    float* mix_stage = slot ? e->d_mix_stage1 : e->d_mix_stage;
     const int zc = env_int("B200CONV_ZEROCOPY", 3);  // bit 0: read the input in place; bit 1: write results in place
     const bool direct = (e->impl == B200CONV_ALGO_DIRECT || e->impl == B200CONV_ALGO_DIRECT_TC);
     // input: every engine reads d_in once or twice -> read it straight from pinned host memory
     const bool in_place = (zc & 1) && is_pinned_host(h_in);
-    // results: the kernels that finish a track in their own epilogue (direct FIR, fused UPOLS) can post the
-    // output rows and the bus straight to pinned host memory — the bus tree sums from a device-side copy of
-    // the rows, so nothing is read back over PCIe.  Not for: a strip kernel after the direct FIR (it works in
-    // place on the output), the three-kernel UPOLS path, and sample-major UPOLS (a column tile written track
-    // by track is scattered 4-byte PCIe writes: measured 2x slower than the staged copy).
+    // results: the kernels that finish a track in their own epilogue (direct FIR, tensor-core FIR, fused UPOLS) can
+    // post the output rows and the bus straight to pinned host memory — the bus tree sums from a device-side copy
+    // of the rows, so nothing is read back over PCIe.  Not for: a strip kernel after the FIR (it works in place on
+    // the output), the three-kernel UPOLS path, and sample-major UPOLS (a column tile written track by track is
+    // scattered 4-byte PCIe writes: measured 2x slower than the staged copy).
     const bool fused_ok = !direct && e->up.fused && e->cfg.out_layout == B200CONV_OUT_TRACK_MAJOR;
     const bool tree = e->bus_in_kernel_single;  // UPOLS: the bus rides in the fused kernel (measurement option)
     const bool pinned_results = (zc & 2) && h_out && is_pinned_host(h_out) && (!h_mix || is_pinned_host(h_mix));
@@ -966,45 +1004,81 @@ int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, f
     // stand-alone fused UPOLS with a bus: the PDL-launched bus kernel reads the output back, so the fused kernel
     // keeps a device copy and posts a SECOND copy of each finished row straight to the pinned host buffer
     const bool dual = pinned_results && !out_place && fused_ok;
+    e->slot_has_bus[slot] = (h_mix != nullptr);
+    // the slot's staging buffers are free once the device -> host copies of the block that used them are done
+    CU_TRY(cudaStreamWaitEvent(st, e->ev_out[slot], 0));
     const float* d_in = h_in;
     if (!in_place) {
-        CU_TRY(cudaMemcpyAsync(e->d_in_stage, h_in, tb * sizeof(float), cudaMemcpyHostToDevice, st));
-        d_in = e->d_in_stage;
+        CU_TRY(cudaMemcpyAsync(in_stage, h_in, tb * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_in = in_stage;
     }
-    auto bus_ok = [&]() -> int {  // after the synchronise: did a peer engine miss the bus exchange of this block?
-        if (e->bus_world > 1 && h_mix && *static_cast<volatile uint32_t*>(e->d_bus_err)) {
-            *e->d_bus_err = 0;
-            return fail(B200CONV_ERR_CUDA, "bus all-reduce: a peer engine did not signal within the spin bound");
-        }
-        return B200CONV_OK;
-    };
     if (out_place) {
         int rc = b200conv_process(e, d_in, h_out, h_mix, flags, st);
         if (rc) return rc;
-        CU_TRY(cudaStreamSynchronize(st));
-        return bus_ok();
+        CU_TRY(cudaEventRecord(e->ev_out[slot], st));
+        return B200CONV_OK;
     }
     const bool mix_place = (zc & 2) && h_mix && is_pinned_host(h_mix);  // 2*B floats: written in place whatever the output path
-    int rc = process_impl(e, d_in, e->d_out_stage, dual ? h_out : nullptr, h_mix ? (mix_place ? h_mix : e->d_mix_stage) : nullptr,
-                          flags, st);
+    int rc = process_impl(e, d_in, out_stage, dual ? h_out : nullptr, h_mix ? (mix_place ? h_mix : mix_stage) : nullptr, flags, st);
     if (rc) return rc;
-    if (dual) {
-        CU_TRY(cudaStreamSynchronize(st));
-        return bus_ok();
+    const bool need_copy = (h_out && !dual) || (h_mix && !mix_place);
+    if (!need_copy) {
+        CU_TRY(cudaEventRecord(e->ev_out[slot], st));
+        return B200CONV_OK;
     }
-    if (h_out) {
+    // device -> host on the copy stream: it overlaps the kernels of the NEXT submitted block
+    CU_TRY(cudaEventRecord(e->ev_done[slot], st));
+    cudaStream_t cs = e->copy_stream;
+    CU_TRY(cudaStreamWaitEvent(cs, e->ev_done[slot], 0));
+    if (h_out && !dual) {
         if (e->cfg.out_layout == B200CONV_OUT_SAMPLE_MAJOR && e->Tg != e->T) {
-            CU_TRY(cudaMemcpy2DAsync(h_out + e->toff, static_cast<size_t>(e->Tg) * sizeof(float), e->d_out_stage + e->toff,
+            CU_TRY(cudaMemcpy2DAsync(h_out + e->toff, static_cast<size_t>(e->Tg) * sizeof(float), out_stage + e->toff,
                                      static_cast<size_t>(e->Tg) * sizeof(float), static_cast<size_t>(e->T) * sizeof(float),
-                                     e->B, cudaMemcpyDeviceToHost, st));
+                                     e->B, cudaMemcpyDeviceToHost, cs));
         } else {
-            CU_TRY(cudaMemcpyAsync(h_out, e->d_out_stage, tb * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(h_out, out_stage, tb * sizeof(float), cudaMemcpyDeviceToHost, cs));
         }
     }
     if (h_mix && !mix_place)
-        CU_TRY(cudaMemcpyAsync(h_mix, e->d_mix_stage, static_cast<size_t>(2) * e->B * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    return bus_ok();
+        CU_TRY(cudaMemcpyAsync(h_mix, mix_stage, static_cast<size_t>(2) * e->B * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CU_TRY(cudaEventRecord(e->ev_out[slot], cs));
+    return B200CONV_OK;
+}
+}  // namespace
+
+int b200conv_submit(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix, uint32_t flags, uint64_t* ticket) {
+    if (!e || !h_in || !ticket) return fail(B200CONV_ERR_INVALID, "b200conv_submit: null argument");
+    ENGINE_DEVICE(e->cfg.device);
+    if (e->submitted - e->completed >= 2) {  // both staging slots in flight: the oldest block has to land first
+        int rc = wait_slot(e, static_cast<int>(e->completed & 1));
+        if (rc) return rc;
+        e->completed += 1;
+    }
+    const int slot = static_cast<int>(e->submitted & 1);
+    int rc = submit_slot(e, h_in, h_out, h_mix, flags, slot);
+    if (rc) return rc;
+    *ticket = e->submitted++;
+    return B200CONV_OK;
+}
+
+int b200conv_wait(b200conv_engine* e, uint64_t ticket) {
+    if (!e) return fail(B200CONV_ERR_INVALID, "b200conv_wait: null engine");
+    if (ticket >= e->submitted) return fail(B200CONV_ERR_STATE, "b200conv_wait: no such ticket");
+    ENGINE_DEVICE(e->cfg.device);
+    while (e->completed <= ticket) {  // blocks complete in submission order
+        int rc = wait_slot(e, static_cast<int>(e->completed & 1));
+        e->completed += 1;
+        if (rc) return rc;
+    }
+    return B200CONV_OK;
+}
+
+int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix, uint32_t flags) {
+    if (!e || !h_in) return fail(B200CONV_ERR_INVALID, "b200conv_process_host: null argument");
+    uint64_t ticket = 0;
+    int rc = b200conv_submit(e, h_in, h_out, h_mix, flags, &ticket);
+    if (rc) return rc;
+    return b200conv_wait(e, ticket);
 }
 
 int b200conv_set_strip(b200conv_engine* e, const b200conv_strip* strip) {

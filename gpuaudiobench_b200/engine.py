@@ -68,6 +68,8 @@ def load_library():
     L.b200conv_set_mix_gains.argtypes = [C.c_void_p, C.c_void_p]
     L.b200conv_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.b200conv_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.b200conv_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
+    L.b200conv_wait.argtypes = [C.c_void_p, C.c_uint64]
     L.b200conv_query.argtypes = [C.c_void_p, C.POINTER(Info)]
     L.b200conv_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.b200conv_plan.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_int32)]
@@ -328,6 +330,16 @@ class ConvEngine:
         """Raw-address form (pinned torch tensors' data_ptr()); no per-call numpy work."""
         _check(self.lib.b200conv_process_host(self.handle, C.c_void_p(h_in), C.c_void_p(h_out) if h_out else None,
                                               C.c_void_p(h_mix) if h_mix else None, flags))
+
+    def submit_ptr(self, h_in, h_out=None, h_mix=None, flags=0):
+        """b200conv_submit on raw host addresses: returns the ticket for wait()."""
+        t = C.c_uint64()
+        _check(self.lib.b200conv_submit(self.handle, C.c_void_p(h_in), C.c_void_p(h_out) if h_out else None,
+                                        C.c_void_p(h_mix) if h_mix else None, flags, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        _check(self.lib.b200conv_wait(self.handle, ticket))
 
     def out_shape(self):
         return (self.B, self.Tg) if self.out_layout == OUT_SAMPLE_MAJOR else (self.T, self.B)

@@ -153,6 +153,16 @@ int b200conv_process(b200conv_engine* e, const float* d_in, float* d_out, float*
 int b200conv_process_host(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix,
                           uint32_t flags);
 
+/* The same, split: b200conv_submit enqueues the block (input copy or in-place read, kernels, result copies) and
+ * returns a ticket at once; b200conv_wait blocks until that block's results are in h_out / h_mix.  Two blocks may be
+ * in flight (staging is double-buffered; a third submit first waits for the oldest): the device -> host copies of
+ * block m run on a second stream under the kernels of block m+1, and the host prepares buffer m+1 meanwhile — the
+ * overlap the reference's transferToDevice -> launch -> transferToHost sequence (cuda/bench_base.cu:30-42) and its
+ * datacopy benchmarks (cuda/bench_datatransfer.cu:15-25) leave on the table.  Blocks complete in submission order;
+ * the caller's buffers of a block must stay untouched until its wait returns.  b200conv_process_host == submit + wait. */
+int b200conv_submit(b200conv_engine* e, const float* h_in, float* h_out, float* h_mix, uint32_t flags, uint64_t* ticket);
+int b200conv_wait(b200conv_engine* e, uint64_t ticket);
+
 /* Work / byte accounting for roofline figures, and per-stage CUDA-event times. */
 int b200conv_query(b200conv_engine* e, b200conv_info* info);
 

@@ -439,3 +439,38 @@ def test_error_codes():
 def test_fp32_peak_microbenchmark_runs():
     tf, ms = g.measure_fp32_peak(0)
     assert 20.0 < tf < 120.0, tf  # B200: 148 SMs x 128 lanes x 2 x (1.3..1.97 GHz) = 49..75 TFLOP/s
+
+
+@pytest.mark.parametrize("algo,layout", [(g.ALGO_DIRECT, g.OUT_TRACK_MAJOR), (g.ALGO_UPOLS, g.OUT_SAMPLE_MAJOR),
+                                         (g.ALGO_UPOLS, g.OUT_TRACK_MAJOR), (g.ALGO_DIRECT_TC, g.OUT_TRACK_MAJOR)])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_submit_wait_pipelines_two_blocks_and_matches_the_serial_call(oracle, algo, layout, pinned):
+    """b200conv_submit / b200conv_wait: two blocks in flight on double-buffered staging give the
+    bit-identical stream of outputs and buses as one b200conv_process_host per block."""
+    import torch
+    T, B, L, M = 12, 256, 1500, 9
+    xs = oracle.generate_input(M * T * B, 5).reshape(M, T, B)
+    h = oracle.generate_ir(T, L, "accel")
+    shape = (B, T) if layout == g.OUT_SAMPLE_MAJOR else (T, B)
+    with g.ConvEngine(T, B, L, algo, layout) as serial, g.ConvEngine(T, B, L, algo, layout) as piped:
+        serial.load_ir(h)
+        piped.load_ir(h)
+        want = [serial.process_host(xs[m], want_mix=True) for m in range(M)]
+        mk = (lambda *s: torch.zeros(*s).pin_memory()) if pinned else (lambda *s: torch.zeros(*s))
+        h_in = [torch.from_numpy(xs[m].copy()) for m in range(M)]
+        if pinned:
+            h_in = [t.pin_memory() for t in h_in]
+        outs = [mk(*shape) for _ in range(M)]
+        mixes = [mk(2, B) for _ in range(M)]
+        prev = None
+        for m in range(M):
+            tk = piped.submit_ptr(h_in[m].data_ptr(), outs[m].data_ptr(), mixes[m].data_ptr())
+            if prev is not None:
+                piped.wait(prev)
+            prev = tk
+        piped.wait(prev)
+        with pytest.raises(g.B200ConvError):
+            piped.wait(prev + 5)
+    for m in range(M):
+        assert np.array_equal(outs[m].numpy(), want[m][0]), f"block {m}"
+        assert np.array_equal(mixes[m].numpy(), want[m][1]), f"bus of block {m}"
