@@ -87,7 +87,8 @@ struct UpolsState {
     float2* H = nullptr;
     float2* X = nullptr;
     float2* Ypart = nullptr;
-    float* prev = nullptr;
+    float* prev = nullptr;        // [2][T][B] previous buffer, ping-pong (fused kernel: read [par], write [par ^ 1])
+    int par = 0;
     unsigned* counters = nullptr;
     bool fused = false;
 };
@@ -294,7 +295,8 @@ int reset_state(b200conv_engine* e) {
         e->tc.xpar = 0;
     } else {
         CU_TRY(cudaMemset(e->up.X, 0, static_cast<size_t>(e->T) * e->up.P * e->up.M * sizeof(float2)));
-        CU_TRY(cudaMemset(e->up.prev, 0, static_cast<size_t>(e->T) * e->B * sizeof(float)));
+        CU_TRY(cudaMemset(e->up.prev, 0, static_cast<size_t>(2) * e->T * e->B * sizeof(float)));
+        e->up.par = 0;
     }
     if (e->d_strip_state) CU_TRY(cudaMemset(e->d_strip_state, 0, static_cast<size_t>(2) * e->T * sizeof(float)));
     CU_TRY(cudaDeviceSynchronize());
@@ -530,7 +532,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if ((rc = dev_alloc(e, &u.H, spec))) return bail(rc);
         if ((rc = dev_alloc(e, &u.X, spec))) return bail(rc);
         if ((rc = dev_alloc(e, &u.Ypart, static_cast<size_t>(u.S) * e->T * u.M))) return bail(rc);
-        if ((rc = dev_alloc(e, &u.prev, tb))) return bail(rc);
+        if ((rc = dev_alloc(e, &u.prev, 2 * tb))) return bail(rc);
         if ((rc = dev_alloc(e, &u.counters, static_cast<size_t>(e->T)))) return bail(rc);
     }
     err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
@@ -866,7 +868,9 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             tm.mark();
             FusedParams fp{};
             fp.d_in = d_in;
-            fp.prev = u.prev;
+            fp.prev = u.prev + static_cast<size_t>(u.par) * e->T * e->B;
+            fp.prev_w = u.prev + static_cast<size_t>(u.par ^ 1) * e->T * e->B;
+            fp.KT = std::max(1, u.M / 512);
             fp.H = u.H;
             fp.X = u.X;
             fp.Ypart = u.Ypart;
@@ -891,18 +895,20 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             const bool tree = e->bus_in_kernel_single;
             fp.bus = bus_params(e, tree ? d_mix : nullptr);
             CU_TRY(launch_upols_fused(fp, st));
+            if (commit) u.par ^= 1;
             e->launches += 1;
             tm.mark();
         } else {
             tm.mark();
             RfftParams f{};
-            f.first = u.prev;
+            float* prev_cur = u.prev + static_cast<size_t>(u.par) * e->T * e->B;  // three-kernel path: in place, no flip
+            f.first = prev_cur;
             f.first_stride = e->B;
             f.second = d_in;
             f.second_stride = e->B;
             f.out = u.X + static_cast<size_t>(slot0) * u.M;
             f.out_stride = static_cast<size_t>(u.P) * u.M;
-            f.prev_out = commit ? u.prev : nullptr;
+            f.prev_out = commit ? prev_cur : nullptr;
             f.count = e->T;
             f.M = u.M;
             f.logM = u.logM;

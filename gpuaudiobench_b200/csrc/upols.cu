@@ -310,8 +310,12 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused block kernel (M = B <= 512): forward FFT -> FDL-MAC -> inverse FFT + overlap-save in ONE
-// launch; grid (S, T), 256 threads.  The newest spectrum X_m only enters the sum through
+// Fused block kernel (M = B <= 4096): forward FFT -> FDL-MAC -> inverse FFT + overlap-save in ONE
+// launch; grid (S * KT, T), 256 threads.  KT = max(1, M/512) bin tiles of 512 bins: for M > 512 a track's
+// spectrum is wider than the 256 float4 a CTA's threads cover, so the MAC of a (split, tile) pair is a CTA of
+// its own (the MAC is separable by bins; round 1 ran the 3-kernel path here at 0.63-0.81 of the HBM peak on the
+// step).  Every split-0 CTA runs the forward transform itself (redundant across the KT tiles, a few us each
+// while the other CTAs of the SM stream) and only tile 0 publishes it.  The newest spectrum X_m only enters the sum through
 // partition 0, which belongs to split 0, so only that CTA transforms the input (and publishes
 // X_m to the ring for later blocks); the other splits stream older ring slots straight away.
 // Each CTA leaves its partial spectrum in Ypart and takes a ticket on the track's counter; the
@@ -334,8 +338,10 @@ template <int kFusedUnroll, int kMinCtas, bool kStrip, bool kBusTree = false>
 __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
     __shared__ int s_last;
-    const int M = p.M, half = M >> 1, U = M >> 1, G = 256 / U;
-    const int s = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+    const int M = p.M, half = M >> 1, U = M >> 1;  // U: float4 (bin pairs) per partition row
+    const int KT = p.KT;                           // bin tiles (1 for M <= 512)
+    const int G = (U >= 256) ? 1 : 256 / U;        // partition lanes per bin pair
+    const int s = blockIdx.x / KT, kt = blockIdx.x - s * KT, t = blockIdx.y, tid = threadIdx.x;
     float2* a = fsm;
     float2* b = fsm + M;
     float* red = reinterpret_cast<float*>(fsm + 2 * M);
@@ -345,17 +351,18 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
     // Keep HBM busy while this CTA runs its forward FFT: pull the first kPrefetchParts partitions of
     // its H rows and ring slots into L2 (no registers, no waiting); the MAC loop then finds them there.
     {
-        const int Pp = p.P, Up = M >> 1;
+        const int Pp = p.P;
         const int pf0 = static_cast<int>(static_cast<long long>(Pp) * s / p.S);
         const int pf1 = static_cast<int>(static_cast<long long>(Pp) * (s + 1) / p.S);
-        const int lines_per_row = (Up * 16) >> 7;  // 128-byte lines per partition row (M*8 bytes)
+        const int lines_per_row = (min(U, 256) * 16) >> 7;  // 128-byte lines of this CTA's bin tile in a partition row
+        const int tile_off = kt * 256 * 16;                  // byte offset of the tile inside a row
         const int total = min(kPrefetchParts, pf1 - pf0) * lines_per_row;
         for (int i = tid; i < total; i += 256) {
             const int q = pf0 + i / lines_per_row, ln = i - (i / lines_per_row) * lines_per_row;
             int sl = p.slot0 + q;
             if (sl >= Pp) sl -= Pp;
-            const char* hrow = reinterpret_cast<const char*>(p.H + (static_cast<size_t>(t) * Pp + q) * M) + ln * 128;
-            const char* xrow = reinterpret_cast<const char*>(p.X + (static_cast<size_t>(t) * Pp + sl) * M) + ln * 128;
+            const char* hrow = reinterpret_cast<const char*>(p.H + (static_cast<size_t>(t) * Pp + q) * M) + tile_off + ln * 128;
+            const char* xrow = reinterpret_cast<const char*>(p.X + (static_cast<size_t>(t) * Pp + sl) * M) + tile_off + ln * 128;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(hrow));
             if (q != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow));  // slot0 itself is written below
         }
@@ -363,12 +370,14 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
 
     if (s == 0) {
         const float2* in2 = reinterpret_cast<const float2*>(p.d_in + static_cast<size_t>(t) * M);
-        float2* prev2 = reinterpret_cast<float2*>(p.prev + static_cast<size_t>(t) * M);
+        const float2* prev2 = reinterpret_cast<const float2*>(p.prev + static_cast<size_t>(t) * M);
+        float2* prevw2 = reinterpret_cast<float2*>(p.prev_w + static_cast<size_t>(t) * M);  // the OTHER half of the ping-pong:
+        const bool publish = (kt == 0);  // the other tiles' CTAs of this track may still be reading `prev`
         for (int n = tid; n < half; n += 256) {
             const float2 pv = prev2[n], cv = in2[n];
             a[n] = pv;          // window = [previous buffer | current buffer], even/odd packed
             a[n + half] = cv;
-            if (p.commit) prev2[n] = cv;
+            if (p.commit && publish) prevw2[n] = cv;
         }
         __syncthreads();
         float2* z = fft_stockham<false>(a, b, M, p.logM, tid, 256, true);
@@ -383,10 +392,15 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
             const float2 Xk = cadd(E, WO);
             const float2 Xmk = make_float2(E.x - WO.x, -(E.y - WO.y));
             if (k == 0) {
-                xo[0] = ring[0] = make_float2(Xk.x, Xmk.x);
+                xo[0] = make_float2(Xk.x, Xmk.x);
+                if (publish) ring[0] = xo[0];
             } else {
-                xo[k] = ring[k] = Xk;
-                if (k != half) xo[M - k] = ring[M - k] = Xmk;
+                xo[k] = Xk;
+                if (publish) ring[k] = Xk;
+                if (k != half) {
+                    xo[M - k] = Xmk;
+                    if (publish) ring[M - k] = Xmk;
+                }
             }
         }
         __syncthreads();
@@ -394,7 +408,8 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
     }
 
     // ---- FDL-MAC over this split's partitions (same loop as fdl_mac_kernel) ----
-    const int u = tid % U, g = tid / U;
+    const int u = (U >= 256) ? kt * 256 + tid : tid % U;  // this thread's bin pair inside a partition row
+    const int g = (U >= 256) ? 0 : tid / U;
     const int P = p.P;
     int p0 = static_cast<int>(static_cast<long long>(P) * s / p.S);
     const int p1 = static_cast<int>(static_cast<long long>(P) * (s + 1) / p.S);
@@ -450,7 +465,7 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
 
     __syncthreads();  // everyone is done with xsm / the FFT buffers
     float2* ysm = b;  // summed spectrum goes to b, the inverse pre-pass writes a
-    if (p.S == 1) {
+    if (p.S * KT == 1) {
         if (g == 0) reinterpret_cast<float4*>(ysm)[u] = y;
     } else {
         if (g == 0) reinterpret_cast<float4*>(p.Ypart)[(static_cast<size_t>(s) * p.T + t) * U + u] = y;
@@ -458,19 +473,22 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
         __syncthreads();
         if (tid == 0) {
             const unsigned ticket = atomicAdd(&p.counters[t], 1u);
-            s_last = (ticket == static_cast<unsigned>(p.S) - 1u);
+            s_last = (ticket == static_cast<unsigned>(p.S * KT) - 1u);  // every (split, bin tile) CTA of the track
             if (s_last) p.counters[t] = 0;  // re-armed for the next block
         }
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        if (g == 0) {
-            float4 sum = __ldcg(reinterpret_cast<const float4*>(p.Ypart) + static_cast<size_t>(t) * U + u);
-            for (int ss = 1; ss < p.S; ++ss) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.Ypart) + (static_cast<size_t>(ss) * p.T + t) * U + u);
-                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        // the whole spectrum of the track (all bin tiles), splits added in split order
+        for (int uu = (U >= 256) ? tid : u; uu < U; uu += 256) {
+            if (g == 0) {
+                float4 sum = __ldcg(reinterpret_cast<const float4*>(p.Ypart) + static_cast<size_t>(t) * U + uu);
+                for (int ss = 1; ss < p.S; ++ss) {
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(p.Ypart) + (static_cast<size_t>(ss) * p.T + t) * U + uu);
+                    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                }
+                reinterpret_cast<float4*>(ysm)[uu] = sum;
             }
-            reinterpret_cast<float4*>(ysm)[u] = sum;
         }
     }
     __syncthreads();
@@ -573,26 +591,28 @@ int upols_fused_occupancy() {
     return (forced == 8 || forced == 2) ? forced : 4;
 }
 
+template <typename K>
+static cudaError_t launch_fused_variant(K kernel, const FusedParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kernel), smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st) {
-    dim3 grid(p.S, p.T);
+    dim3 grid(p.S * p.KT, p.T);
     const size_t smem = static_cast<size_t>(2) * p.M * sizeof(float2) + 256 * 8 * sizeof(float);
     if (p.bus.mix) {  // in-kernel bus tree requested (B200CONV_BUS_TREE=1)
-        if (p.strip.ops)
-            upols_fused_kernel<4, 4, true, true><<<grid, 256, smem, st>>>(p);
-        else
-            upols_fused_kernel<4, 4, false, true><<<grid, 256, smem, st>>>(p);
-        return cudaGetLastError();
+        if (p.strip.ops) return launch_fused_variant(upols_fused_kernel<4, 4, true, true>, p, grid, smem, st);
+        return launch_fused_variant(upols_fused_kernel<4, 4, false, true>, p, grid, smem, st);
     }
-    if (p.strip.ops) {  // strip in the epilogue: one more instantiation of the product configuration
-        upols_fused_kernel<4, 4, true><<<grid, 256, smem, st>>>(p);
-        return cudaGetLastError();
-    }
+    // strip in the epilogue: one more instantiation of the product configuration
+    if (p.strip.ops) return launch_fused_variant(upols_fused_kernel<4, 4, true>, p, grid, smem, st);
     switch (upols_fused_occupancy()) {
-        case 8: upols_fused_kernel<2, 8, false><<<grid, 256, smem, st>>>(p); break;
-        case 4: upols_fused_kernel<4, 4, false><<<grid, 256, smem, st>>>(p); break;
-        default: upols_fused_kernel<8, 2, false><<<grid, 256, smem, st>>>(p); break;
+        case 8: return launch_fused_variant(upols_fused_kernel<2, 8, false>, p, grid, smem, st);
+        case 4: return launch_fused_variant(upols_fused_kernel<4, 4, false>, p, grid, smem, st);
+        default: return launch_fused_variant(upols_fused_kernel<8, 2, false>, p, grid, smem, st);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace b200conv

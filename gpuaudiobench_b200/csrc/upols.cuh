@@ -47,10 +47,12 @@ struct IrfftParams {
     int sample_major, Tg, toff;
 };
 
-// One launch per block for M = B <= 512: forward FFT (split 0) + FDL-MAC + inverse/overlap-save (last CTA).
+// One launch per block for M = B <= 4096: forward FFT (split 0) + FDL-MAC + inverse/overlap-save (last CTA).
 struct FusedParams {
     const float* d_in;    // [T][B]
-    float* prev;          // [T][B] previous buffer (updated when commit != 0)
+    const float* prev;    // [T][B] previous buffer
+    float* prev_w;        // [T][B] where this buffer is kept for the next block when commit != 0: the other half of a
+                          // ping-pong (several CTAs of a track read `prev` while tile 0 of split 0 writes)
     const float2* H;      // [T][P][M]
     float2* X;            // [T][P][M] ring; slot0 receives X_m
     float2* Ypart;        // [S][T][M]
@@ -59,13 +61,14 @@ struct FusedParams {
     float* out2;          // optional second copy of the output, same layout (pinned host memory: the
                           // last CTA of each track posts its PCIe writes while other CTAs still stream)
     int T, P, M, logM, S, slot0, commit;
+    int KT;               // bin tiles of 512 bins = max(1, M / 512); grid (S * KT, T)
     int sample_major, Tg, toff;
     StripParams strip;    // strip.ops != 0: the last CTA of a track runs the channel strip on its B output samples
                           // in shared memory before writing them (in/out/T/B/layout fields unused here)
     BusTreeParams bus;    // bus.mix != null: the stereo bus (and its multi-GPU sum) as an epilogue of this launch
 };
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st);
-constexpr int kFusedMaxM = 512;
+constexpr int kFusedMaxM = 4096;  // 2 * M * 8 B of FFT ping-pong: 64 KB at M = 4096 (3 CTAs per SM)
 
 cudaError_t launch_rfft_fwd(const RfftParams& p, cudaStream_t st);
 cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st);
