@@ -615,6 +615,8 @@ def run_sweep(args, rank, world, local_rank, dist):
                                    ("direct", 128, 16384, (32, 64, 128, 256, 512, 1024, 2048, 4096))):
         for B in sizes:
             key = f"sweep_{algo_name}_{B}"
+            if args.sweep_filter and not any(tok == f"{algo_name}:{B}" or tok == algo_name for tok in args.sweep_filter.split(",")):
+                continue
             WORKLOADS[key] = (algo_name, T, B, L, "track_major", f"sweep: {algo_name} {T} tracks/GPU x {B}-sample buffers x {L}-tap IR")
             r = run_workload(key, args, rank, world, local_rank, dist, want_cpu_baseline=(rank == 0), sweep=True)
             cpu = r.get("cpu_baseline") or {}
@@ -796,6 +798,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads in the default line")
     ap.add_argument("--sweep", action="store_true", help="buffer-size sweep (BASELINE config 5): one JSON line with a table")
+    ap.add_argument("--sweep-filter", default="", help="comma list of sweep points to run, e.g. upols:1024,upols:4096,direct")
     ap.add_argument("--strip", action="store_true", help="channel-strip kernels alone and attached to the engines")
     ap.add_argument("--latency", type=int, default=0, metavar="N", help="latency run: N blocks back-to-back and N periodic at B/fs")
     args = ap.parse_args()

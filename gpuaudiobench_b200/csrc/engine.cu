@@ -90,6 +90,8 @@ struct UpolsState {
     float* prev = nullptr;        // [2][T][B] previous buffer, ping-pong (fused kernel: read [par], write [par ^ 1])
     int par = 0;
     unsigned* counters = nullptr;
+    unsigned* xready = nullptr;   // [T] fused kernel with bin tiles: "X_m of launch `seq` is in the ring"
+    unsigned seq = 0;
     bool fused = false;
 };
 
@@ -177,7 +179,9 @@ int dev_alloc(b200conv_engine* e, Tp** out, size_t count, bool zero = true) {
 uint32_t resolve_impl(const b200conv_config& cfg) {
     if (cfg.algo != B200CONV_ALGO_DIRECT) return cfg.algo;
     if ((cfg.flags & B200CONV_FLAG_FFMA_ONLY) || env_int("B200CONV_DIRECT_TC", 1) == 0) return B200CONV_ALGO_DIRECT;
-    const bool shape_ok = cfg.block % kTcRows == 0 && cfg.block >= kTcRows && cfg.block <= kTcRows * kTcMaxA;
+    // (B = 128 is legal for the tensor-core kernel but measured slower than the FFMA kernel: 26.8 against 25.6 us at
+    // 128 tracks x 16384 taps — one row block per item leaves the tensor pipe idle behind the fixed cost)
+    const bool shape_ok = cfg.block % kTcRows == 0 && cfg.block >= 2 * kTcRows && cfg.block <= kTcRows * kTcMaxA;
     const double macs = static_cast<double>(cfg.tracks) * cfg.block * cfg.ir_len;
     return (shape_ok && macs >= 2.5e8) ? B200CONV_ALGO_DIRECT_TC : B200CONV_ALGO_DIRECT;
 }
@@ -534,6 +538,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if ((rc = dev_alloc(e, &u.Ypart, static_cast<size_t>(u.S) * e->T * u.M))) return bail(rc);
         if ((rc = dev_alloc(e, &u.prev, 2 * tb))) return bail(rc);
         if ((rc = dev_alloc(e, &u.counters, static_cast<size_t>(e->T)))) return bail(rc);
+        if ((rc = dev_alloc(e, &u.xready, static_cast<size_t>(e->T)))) return bail(rc);
     }
     err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
@@ -871,6 +876,9 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             fp.prev = u.prev + static_cast<size_t>(u.par) * e->T * e->B;
             fp.prev_w = u.prev + static_cast<size_t>(u.par ^ 1) * e->T * e->B;
             fp.KT = std::max(1, u.M / 512);
+            fp.xready = u.xready;
+            if (++u.seq == 0) u.seq = 1;
+            fp.seq = u.seq;
             fp.H = u.H;
             fp.X = u.X;
             fp.Ypart = u.Ypart;

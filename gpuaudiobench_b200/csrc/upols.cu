@@ -314,8 +314,10 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 // launch; grid (S * KT, T), 256 threads.  KT = max(1, M/512) bin tiles of 512 bins: for M > 512 a track's
 // spectrum is wider than the 256 float4 a CTA's threads cover, so the MAC of a (split, tile) pair is a CTA of
 // its own (the MAC is separable by bins; round 1 ran the 3-kernel path here at 0.63-0.81 of the HBM peak on the
-// step).  Every split-0 CTA runs the forward transform itself (redundant across the KT tiles, a few us each
-// while the other CTAs of the SM stream) and only tile 0 publishes it.  The newest spectrum X_m only enters the sum through
+// step).  Tile 0 of split 0 runs the forward transform and publishes X_m to the ring; the other tiles of split
+// 0 stream their older partitions first and take partition 0 last, from the ring, once tile 0 has raised the
+// track's "spectrum ready" word (the first version let every tile transform the window itself: 8 redundant
+// 4096-point FFTs and 8 PCIe reads of the input per track, 192 -> 285 us at B = 4096).  The newest spectrum X_m only enters the sum through
 // partition 0, which belongs to split 0, so only that CTA transforms the input (and publishes
 // X_m to the ring for later blocks); the other splits stream older ring slots straight away.
 // Each CTA leaves its partial spectrum in Ypart and takes a ticket on the track's counter; the
@@ -368,11 +370,11 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
         }
     }
 
-    if (s == 0) {
+    if (s == 0 && kt == 0) {
         const float2* in2 = reinterpret_cast<const float2*>(p.d_in + static_cast<size_t>(t) * M);
         const float2* prev2 = reinterpret_cast<const float2*>(p.prev + static_cast<size_t>(t) * M);
         float2* prevw2 = reinterpret_cast<float2*>(p.prev_w + static_cast<size_t>(t) * M);  // the OTHER half of the ping-pong:
-        const bool publish = (kt == 0);  // the other tiles' CTAs of this track may still be reading `prev`
+        const bool publish = true;
         for (int n = tid; n < half; n += 256) {
             const float2 pv = prev2[n], cv = in2[n];
             a[n] = pv;          // window = [previous buffer | current buffer], even/odd packed
@@ -405,6 +407,11 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
         }
         __syncthreads();
         xsm = xo;
+        if (KT > 1) {  // the other bin tiles of this track take partition 0 from the ring: tell them it is there
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(&p.xready[t], p.seq);
+        }
     }
 
     // ---- FDL-MAC over this split's partitions (same loop as fdl_mac_kernel) ----
@@ -418,8 +425,9 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-    if (s == 0) {  // partition 0 against the spectrum still in shared memory
-        if (g == 0) mac2(acc, ldg_stream(H4), reinterpret_cast<const float4*>(xsm)[u]);
+    if (s == 0) {
+        // partition 0 against the spectrum still in shared memory (tile 0) / from the ring after the older ones (other tiles)
+        if (kt == 0 && g == 0) mac2(acc, ldg_stream(H4), reinterpret_cast<const float4*>(xsm)[u]);
         p0 = 1;
     }
     int pp = p0 + g;
@@ -440,6 +448,18 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
         int sl = p.slot0 + pp;
         if (sl >= P) sl -= P;
         mac2(acc, ldg_stream(H4 + static_cast<size_t>(pp) * U), ldg_stream(X4 + static_cast<size_t>(sl) * U));
+    }
+    if (s == 0 && kt != 0) {  // (KT > 1 implies G == 1) partition 0 now: wait for tile 0's transform of this block
+        if (tid == 0) {
+            unsigned spins = 0;
+            while (atomicAdd(&p.xready[t], 0u) != p.seq && ++spins < (1u << 24)) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        const float4 h0 = ldg_stream(H4);
+        const float4 x0 = __ldcg(X4 + static_cast<size_t>(p.slot0) * U);  // written by another CTA of this launch: L2, not L1
+        mac2(acc, h0, x0);
     }
     if (G > 1) {
 #pragma unroll

@@ -62,6 +62,8 @@ struct FusedParams {
                           // last CTA of each track posts its PCIe writes while other CTAs still stream)
     int T, P, M, logM, S, slot0, commit;
     int KT;               // bin tiles of 512 bins = max(1, M / 512); grid (S * KT, T)
+    unsigned* xready;     // [T] KT > 1: tile 0 stores `seq` here when X_m is in the ring
+    unsigned seq;         // launch sequence number, never 0, different for every launch
     int sample_major, Tg, toff;
     StripParams strip;    // strip.ops != 0: the last CTA of a track runs the channel strip on its B output samples
                           // in shared memory before writing them (in/out/T/B/layout fields unused here)

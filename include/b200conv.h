@@ -67,8 +67,8 @@ typedef enum b200conv_layout {
 
 /* b200conv_config.flags */
 #define B200CONV_FLAG_FFMA_ONLY 1u /* ALGO_DIRECT: never dispatch to the tensor-core kernel (keeps the FFMA kernel's bit-exact
-                                      impulse behaviour and its 126-131 dB; the default planner picks DIRECT_TC for blocks that
-                                      are a multiple of 128 up to 1024 once tracks*block*ir_len >= 2.5e8, ~110 dB) */
+                                      impulse behaviour and its 126-131 dB; the default planner picks DIRECT_TC for blocks of
+                                      256, 384 ... 1024 samples once tracks*block*ir_len >= 2.5e8, ~110 dB) */
 
 /* b200conv_process flags */
 #define B200CONV_PEEK 1u /* compute this block but do not advance the stream state: repeated calls

@@ -168,7 +168,8 @@ def test_planner_dispatches_the_direct_form_between_ffma_and_tensor_cores(monkey
     assert g.plan(1, 512, 1024, D)["impl"] == D                # C1: far too small to amortise the fixed cost
     assert g.plan(128, 64, 16384, D)["impl"] == D              # block not a multiple of 128
     assert g.plan(128, 4096, 16384, D)["impl"] == D            # block > 1024
-    assert g.plan(128, 128, 16384, D)["impl"] == TC
+    assert g.plan(128, 128, 16384, D)["impl"] == D             # one row block per item: the FFMA kernel is faster
+    assert g.plan(128, 256, 16384, D)["impl"] == TC
     assert g.plan(128, 512, 16384, TC)["impl"] == TC and g.plan(2, 128, 40, TC)["impl"] == TC  # explicit request
     with pytest.raises(g.B200ConvError):
         g.plan(4, 64, 100, TC)
