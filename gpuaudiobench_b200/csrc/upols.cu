@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) irfft_ols_kernel(IrfftParams p, int TX, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused block kernel (M = B <= 4096): forward FFT -> FDL-MAC -> inverse FFT + overlap-save in ONE
+// Fused block kernel (M = B <= 2048): forward FFT -> FDL-MAC -> inverse FFT + overlap-save in ONE
 // launch; grid (S * KT, T), 256 threads.  KT = max(1, M/512) bin tiles of 512 bins: for M > 512 a track's
 // spectrum is wider than the 256 float4 a CTA's threads cover, so the MAC of a (split, tile) pair is a CTA of
 // its own (the MAC is separable by bins; round 1 ran the 3-kernel path here at 0.63-0.81 of the HBM peak on the

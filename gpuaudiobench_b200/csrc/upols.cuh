@@ -47,7 +47,7 @@ struct IrfftParams {
     int sample_major, Tg, toff;
 };
 
-// One launch per block for M = B <= 4096: forward FFT (split 0) + FDL-MAC + inverse/overlap-save (last CTA).
+// One launch per block for M = B <= 2048: forward FFT (split 0) + FDL-MAC + inverse/overlap-save (last CTA).
 struct FusedParams {
     const float* d_in;    // [T][B]
     const float* prev;    // [T][B] previous buffer
@@ -70,7 +70,10 @@ struct FusedParams {
     BusTreeParams bus;    // bus.mix != null: the stereo bus (and its multi-GPU sum) as an epilogue of this launch
 };
 cudaError_t launch_upols_fused(const FusedParams& p, cudaStream_t st);
-constexpr int kFusedMaxM = 4096;  // 2 * M * 8 B of FFT ping-pong: 64 KB at M = 4096 (3 CTAs per SM)
+constexpr int kFusedMaxM = 2048;  // measured at 512 tracks x 96000 taps: fused 129.8 / 138.5 us at B = 1024 / 2048 (three-kernel
+                                  // path: 149 / 158); at B = 4096 the fused kernel (64 KB of FFT ping-pong -> 3 CTAs per SM, 24
+                                  // partitions per CTA, two 4096-point transforms per track on single CTAs) took 236 us against
+                                  // 192 us for the three-kernel path, which therefore stays for B >= 4096
 
 cudaError_t launch_rfft_fwd(const RfftParams& p, cudaStream_t st);
 cudaError_t launch_fdl_mac(const MacParams& p, cudaStream_t st);
