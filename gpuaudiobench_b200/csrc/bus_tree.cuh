@@ -10,18 +10,16 @@
 //            ybus[t][..] (device scratch, track-major) and calls bus_tree_arrive();
 //   level 1  tracks are grouped G1 at a time; the LAST arriver of a (group, chunk) sums the group's
 //            rows in track order -> gpart[group][c][n];
-//   level 2  when every group of a chunk has delivered, the NG level-1 finishers each add the group partials of
-//            1/NG of the chunk's columns in group order -> that piece of the local bus (done at the END of the
-//            finisher CTA's convolution work: a final waits for the other groups, and must not hold up work they
-//            may depend on).  (An ordered running sum over groups was tried for UPOLS and lost: the CTAs of a
-//            wave retire together, so the chain serialised ~14 groups at the end of C3: 171 -> 183 us.)
-//   level 3  (world > 1) each owner pushes its piece into its slot of EVERY peer's symmetric buffer over NVLink
-//            and adds the world slots of its own buffer in rank order (bus_ll_* below).
+//   level 2  the LAST group of a chunk sums the group partials in group order -> the local bus chunk
+//            (an ordered running sum over groups was tried for UPOLS and lost: the CTAs of a wave retire
+//            together, so the chain serialised ~14 groups at the end of C3: 171 -> 183 us);
+//   level 3  (world > 1) that CTA pushes the chunk into its slot of EVERY peer's symmetric buffer over
+//            NVLink and adds the world slots of its own buffer in rank order (bus_ll_* below).
 //
 // Every sum runs in a fixed order whoever executes it, so the bus is deterministic run to run and
-// bit-identical on all ranks; no float atomics.  Level-1 counters re-arm themselves (the last arriver
-// stores 0), the level-2 counter is monotonic, so a launch needs no memset.  Per-track work is O(B) reads of
-// L2-resident rows; the critical path after the last track is two ticket round trips (+ one NVLink latency).
+// bit-identical on all ranks; no float atomics.  Counters re-arm themselves (the last arriver
+// stores 0), so a launch needs no memset.  Per-track work is O(B) reads of L2-resident rows; the
+// critical path after the last track is two ticket round trips (+ one NVLink flag round trip).
 //
 // Exchange protocol ("LL": data and flag travel in ONE 8-byte store, as in NCCL's low-latency protocol):
 // the symmetric buffer of a rank is uint64 ll[2][world][n], n = 2*B, slot = epoch & 1; a value is written as
@@ -58,12 +56,11 @@ struct BusTreeParams {
     float* ybus;         // [T][B] rows the bus is summed from (track-major, device memory)
     float4* gpart;       // [NG][B/2] group partials, one float4 {l0, r0, l1, r1} per column pair
     unsigned* gcount;    // [NG][NC] arrival tickets, zero between launches
-    unsigned* ccount;    // [NC] group arrivals, monotonic across launches (see seq)
+    unsigned* ccount;    // [NC] group tickets
     float* mix;          // [2][B] destination (device, or pinned host); null: no bus wanted, tree disabled
     int T, B;
     int G1, NG;          // tracks per group, groups
     int CH, NC;          // columns per chunk, chunks
-    uint32_t seq;        // launches with a bus since the last reset, >= 1: ccount[chunk] reaches NG * seq when all groups are in
     BusExchange x;       // multi-GPU exchange (x.world == 1: none)
 };
 
@@ -85,8 +82,12 @@ __device__ __forceinline__ void bus_ll_push(const BusExchange& x, int n, int i, 
     for (int p = 0; p < x.world; ++p)
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(x.peers[p] + off), "l"(word) : "memory");
 }
-// two adjacent values (i even) in ONE 16-byte store per rank: half the NVLink packets of two bus_ll_push.  Each 8-byte
-// half still carries its own epoch, so a reader that finds one half early and the other late simply keeps polling.
+// two adjacent values (i even) in ONE 16-byte store per rank.  Each 8-byte half still carries its own epoch, so a
+// reader that finds one half early and the other late simply keeps polling.  (Device timestamps at N = 2 after an L2
+// flush: 11 us from push to summed bus with four 8-byte store instructions per thread and peer, 5.3 us with these two
+// — the remote stores of a thread to one peer complete one after the other, ~2.6 us each when cold, 0.25 us warm.
+// Spreading the final over NG CTAs and the two planes over different threads did not shorten it further and cost
+// +2 us on one GPU: profiles/experiments/n2_exchange_*.jsonl.)
 __device__ __forceinline__ void bus_ll_push2(const BusExchange& x, int n, int i, float v0, float v1) {
     const unsigned long long w0 = (static_cast<unsigned long long>(x.epoch) << 32) | __float_as_uint(v0);
     const unsigned long long w1 = (static_cast<unsigned long long>(x.epoch) << 32) | __float_as_uint(v1);
@@ -206,106 +207,12 @@ __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int ch
     }
 }
 
-constexpr int kBusPendMax = 20;  // (group, chunk) finals a CTA can owe at the end of its work (shared-memory list)
-
-// The final of one (owner group, chunk): the chunk's column pairs are divided among the NG level-1 finishers, and
-// owner g adds the NG group partials of ITS pairs in group order, exchanges them over NVLink (world > 1) and writes
-// that piece of the bus.  Called by all nthr threads after ccount[chunk] has reached NG * seq.
-// Why divided: with one CTA doing the whole chunk the multi-GPU step paid for every NVLink packet of the bus from a
-// single SM — after bench.py's L2 flush ~85 ns per 128-byte packet (b200conv_bus_trace: 11 us for 2 x 64 packets at
-// C2, 5.3 us when the packets were halved, 0.5 us warm).  NG owners on NG SMs push 1/NG of the packets each.
-__device__ __forceinline__ void bus_final_slice(const BusTreeParams& bt, int g, int chunk, int tid, int nthr) {
-    const int npairs = bt.CH >> 1;
-    const int lo = static_cast<int>(static_cast<long long>(npairs) * g / bt.NG);
-    const int hi = static_cast<int>(static_cast<long long>(npairs) * (g + 1) / bt.NG);
-    const int c0 = chunk * bt.CH;
-    const int n = 2 * bt.B;
-    const size_t hp = static_cast<size_t>(bt.B) >> 1;
-    const bool tracer = bt.x.world > 1 && bt.x.trace && tid == 0 && chunk == 0 && g == 0;
-    if (tracer) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        bt.x.trace[(bt.x.epoch % kBusTraceLen) * 2] = now;
-    }
-    for (int pair0 = lo; pair0 < hi; pair0 += nthr) {
-        const int pair = pair0 + tid;
-        const bool act1 = pair < hi;
-        float4 part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (act1) {
-            const float4* gp = bt.gpart + (c0 >> 1) + pair;
-            for (int g0 = 0; g0 < bt.NG; g0 += 8) {
-                float4 v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    v[j] = (g0 + j < bt.NG) ? __ldcg(gp + static_cast<size_t>(g0 + j) * hp) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (g0 + j < bt.NG) {
-                        part.x += v[j].x; part.y += v[j].y; part.z += v[j].z; part.w += v[j].w;
-                    }
-                }
-            }
-        }
-        const int col = c0 + 2 * pair;
-        float sum[4] = {part.x, part.z, part.y, part.w};  // l0, l1, r0, r1
-        if (bt.x.world > 1) {
-            if (act1) {
-                bus_ll_push2(bt.x, n, col, part.x, part.z);  // (col and n are even: 16-byte aligned)
-                bus_ll_push2(bt.x, n, bt.B + col, part.y, part.w);
-            }
-            const int idx[4] = {col, col + 1, bt.B + col, bt.B + col + 1};
-            const bool act[4] = {act1, act1, act1, act1};
-            bus_ll_gather<4>(bt.x, n, idx, act, sum);  // fixed rank order: the bit-identical sum on every rank
-        }
-        if (act1) {
-            *reinterpret_cast<float2*>(bt.mix + col) = make_float2(sum[0], sum[1]);
-            *reinterpret_cast<float2*>(bt.mix + bt.B + col) = make_float2(sum[2], sum[3]);
-        }
-    }
-    if (tracer) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        bt.x.trace[(bt.x.epoch % kBusTraceLen) * 2 + 1] = now;
-    }
-}
-
-// The finals this CTA owes (list filled by bus_tree_arrive), run when the CTA has no convolution work left: a final
-// waits for the OTHER groups of its chunk, and a CTA that still had tracks to process could be what they wait for.
-// pend[0] = count, pend[1..] = g * NC + chunk.  Called by all nthr threads.
-__device__ __forceinline__ void bus_tree_finals(const BusTreeParams& bt, int tid, int nthr, uint32_t bar_id, int* pend) {
-    bus_bar(bar_id, nthr);
-    const int count = pend[0];
-    for (int i = 0; i < count; ++i) {
-        const int code = pend[1 + i];
-        const int g = code / bt.NC, chunk = code - g * bt.NC;
-        if (tid == 0) {  // every group of the chunk has delivered its partial for THIS launch
-            const unsigned target = static_cast<unsigned>(bt.NG) * bt.seq;
-            unsigned spins = 0;
-            for (;;) {
-                unsigned c;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(bt.ccount + chunk) : "memory");
-                if (static_cast<int>(c - target) >= 0) break;
-                if (++spins > kBusSpinLimit) {
-                    *reinterpret_cast<volatile uint32_t*>(bt.x.err) = 2u;
-                    break;
-                }
-            }
-            __threadfence();
-        }
-        bus_bar(bar_id, nthr);
-        bus_final_slice(bt, g, chunk, tid, nthr);
-    }
-    bus_bar(bar_id, nthr);
-    if (tid == 0) pend[0] = 0;
-}
-
 // Called by all `nthr` threads of the arriving group (tid = 0 .. nthr-1; they synchronise on hardware
-// barrier `bar_id`) after they have written ybus[t][chunk*CH .. +CH).  `flag` is one int of shared memory,
-// `pend` the CTA's list of owed finals (1 + kBusPendMax ints, pend[0] zeroed at kernel start).
+// barrier `bar_id`) after they have written ybus[t][chunk*CH .. +CH).  `flag` is one int of shared memory.
 // Thread `tid` owns the column pairs tid + q * nthr, q < NP; NP * nthr >= CH / 2 is required.
 template <int NP = 1>
 __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, int chunk, int tid, int nthr,
-                                                uint32_t bar_id, int* flag, int* pend) {
+                                                uint32_t bar_id, int* flag) {
     const int g = t / bt.G1;
     const int gsize = min(bt.G1, bt.T - g * bt.G1);
     const int c0 = chunk * bt.CH;
@@ -356,25 +263,48 @@ __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, 
             }
         }
     }
-    if (bt.NG == 1) {  // one group: its finisher holds the whole chunk
-        bus_finish_chunk<NP>(bt, chunk, part, tid, nthr);
-        return;
-    }
-    // ---- level 2 is owed: deliver the partial, note the final for the end of this CTA's work ----
-    const size_t hp = static_cast<size_t>(bt.B) >> 1;  // column pairs per bus row
+    if (bt.NG > 1) {
+        const size_t hp = static_cast<size_t>(bt.B) >> 1;  // column pairs per bus row
+        // ---- level 2: the last group of the chunk adds the NG partials in group order ----
 #pragma unroll
-    for (int q = 0; q < NP; ++q) {
-        const int pair = tid + q * nthr;
-        if (2 * pair < bt.CH) bt.gpart[static_cast<size_t>(g) * hp + (c0 >> 1) + pair] = part[q];
+        for (int q = 0; q < NP; ++q) {
+            const int pair = tid + q * nthr;
+            if (2 * pair < bt.CH) bt.gpart[static_cast<size_t>(g) * hp + (c0 >> 1) + pair] = part[q];
+        }
+        bus_bar(bar_id, nthr);
+        if (tid == 0) {
+            __threadfence();
+            const int last = (atomicAdd(bt.ccount + chunk, 1u) == static_cast<unsigned>(bt.NG) - 1u);
+            if (last) {
+                bt.ccount[chunk] = 0;
+                __threadfence();
+            }
+            *flag = last;
+        }
+        bus_bar(bar_id, nthr);
+        if (!*flag) return;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int pair = tid + q * nthr;
+            part[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (2 * pair < bt.CH) {
+                const float4* gp = bt.gpart + (c0 >> 1) + pair;
+                for (int g0 = 0; g0 < bt.NG; g0 += 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        v[j] = (g0 + j < bt.NG) ? __ldcg(gp + static_cast<size_t>(g0 + j) * hp) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (g0 + j < bt.NG) {
+                            part[q].x += v[j].x; part[q].y += v[j].y; part[q].z += v[j].z; part[q].w += v[j].w;
+                        }
+                    }
+                }
+            }
+        }
     }
-    if (pend[0] >= kBusPendMax) bus_tree_finals(bt, tid, nthr, bar_id, pend);  // list full (not reached by the planners' schedules)
-    bus_bar(bar_id, nthr);
-    if (tid == 0) {
-        __threadfence();
-        atomicAdd(bt.ccount + chunk, 1u);  // monotonic: reaches NG * seq when every group of this launch is in
-        pend[1 + pend[0]] = g * bt.NC + chunk;
-        pend[0] += 1;
-    }
+    bus_finish_chunk<NP>(bt, chunk, part, tid, nthr);
 }
 #endif  // __CUDACC__
 

@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
     constexpr bool kSwzTaps = (CL > 1);
     constexpr int NC = kFirWarps * 32;  // consumer threads (named barrier 1)
     __shared__ int s_flag;
-    __shared__ int s_pend[1 + kBusPendMax];  // bus finals this CTA owes (bus_tree.cuh)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty_bar = full_bar + kFirMaxStages;
@@ -120,7 +119,6 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
     const int k0 = u_lo - w0 * p.NS;   // first tap stage inside it
 
     if (threadIdx.x == 0) {
-        s_pend[0] = 0;
         for (int i = 0; i < p.nbuf; ++i) {
             mbar_init(&full_bar[i], 2);  // TMA expect_tx arrival + staged-data arrival
             mbar_init(&empty_bar[i], kFirWarps);
@@ -306,7 +304,7 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
 #pragma unroll
                         for (int i = 0; i < VPT; ++i)
                             if (tid + i * NC < OT) p.bus.ybus[tile_off + tid + i * NC] = v[i];
-                        bus_tree_arrive(p.bus, t, ot, tid, NC, 1, &s_flag, s_pend);
+                        bus_tree_arrive(p.bus, t, ot, tid, NC, 1, &s_flag);
                     }
 #pragma unroll
                     for (int i = 0; i < VPT; ++i) {
@@ -331,8 +329,6 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
                 if (++ot == p.ntiles) { ot = 0; ++t; }
             }
         }
-        // the pieces of the bus this CTA owes, now that it has no tap stages left
-        if (p.bus.mix) bus_tree_finals(p.bus, threadIdx.x, NC, 1, s_pend);
     }
 }
 

@@ -125,7 +125,6 @@ struct b200conv_engine {
     unsigned* d_gcount = nullptr; // [NG][NC]
     unsigned* d_ccount = nullptr; // [NC]
     int bus_G1 = 1, bus_NG = 1, bus_CH = 0, bus_NC = 1;
-    uint32_t bus_seq = 0;         // launches with an in-kernel bus tree since the last reset
     // multi-GPU bus group (b200conv_attach_bus): world == 1 means a stand-alone engine
     int bus_world = 1, bus_rank = 0;
     uint64_t bus_peers[kBusMaxWorld] = {};
@@ -304,10 +303,6 @@ int reset_state(b200conv_engine* e) {
         e->up.par = 0;
     }
     if (e->d_strip_state) CU_TRY(cudaMemset(e->d_strip_state, 0, static_cast<size_t>(2) * e->T * sizeof(float)));
-    // bus-tree tickets: level 1 re-arms itself, level 2 counts launches — both start from zero here
-    CU_TRY(cudaMemset(e->d_gcount, 0, static_cast<size_t>(e->bus_NG) * e->bus_NC * sizeof(unsigned)));
-    CU_TRY(cudaMemset(e->d_ccount, 0, static_cast<size_t>(e->bus_NC) * sizeof(unsigned)));
-    e->bus_seq = 0;
     CU_TRY(cudaDeviceSynchronize());
     e->blocks = 0;
     return B200CONV_OK;
@@ -357,11 +352,10 @@ BusExchange bus_exchange(const b200conv_engine* e) {
 
 // The bus tree of this block (bus_tree.cuh).  d_mix == null disables it.  On a multi-GPU job the epoch was
 // advanced by the caller (once per block with a bus, in lockstep on every rank).
-BusTreeParams bus_params(b200conv_engine* e, float* d_mix) {
+BusTreeParams bus_params(const b200conv_engine* e, float* d_mix) {
     BusTreeParams b{};
     b.mix = d_mix;
     if (!d_mix) return b;
-    b.seq = ++e->bus_seq;
     b.gains = e->d_gains;
     b.ybus = e->d_ybus;
     b.gpart = e->d_gpart;

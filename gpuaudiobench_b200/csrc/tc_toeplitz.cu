@@ -128,7 +128,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_toeplitz_kernel(const __grid
     uint64_t* dfull = bfull + 1;                               // the group's MMAs have completed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
     int* s_flag = reinterpret_cast<int*>(smem + 20);
-    int* s_pend = reinterpret_cast<int*>(smem + 24);           // [1 + kBusPendMax] bus finals this CTA owes (header has 128 B)
     const SmemMap sm = smem_map(p.B, p.R);
     float* xw = reinterpret_cast<float*>(smem + sm.xw_off);    // xw[i] = x[i - 128]
     unsigned char* band_hi = smem + sm.band_hi_off;            // band[g] = x[g-127 .. g-124], g < B + 124
@@ -141,7 +140,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_toeplitz_kernel(const __grid
     const int B = p.B;
 
     if (tid == 0) {
-        s_pend[0] = 0;
         mbar_init(bfull, 1);
         mbar_init(dfull, 1);
         mbar_fence_init();
@@ -296,10 +294,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_toeplitz_kernel(const __grid
             __syncthreads();  // TMEM drained, band / x window / images free before the next item overwrites them
         }
         if (warp < 4 && p.bus.mix && grp == 0) {  // group 0 carries this buffer's own samples
-            for (int chunk = 0; chunk < p.bus.NC; ++chunk) bus_tree_arrive<2>(p.bus, t, chunk, tid, 128, 1, s_flag, s_pend);
+            for (int chunk = 0; chunk < p.bus.NC; ++chunk) bus_tree_arrive<2>(p.bus, t, chunk, tid, 128, 1, s_flag);
         }
     }
-    if (warp < 4 && p.bus.mix) bus_tree_finals(p.bus, tid, 128, 1, s_pend);  // the pieces of the bus this CTA owes
     __syncthreads();
     if (warp == 4) tmem_dealloc(tmem, kTmemCols);
 }

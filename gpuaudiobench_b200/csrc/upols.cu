@@ -340,8 +340,6 @@ template <int kFusedUnroll, int kMinCtas, bool kStrip, bool kBusTree = false>
 __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(16) float2 fsm[];  // [2][M] FFT ping-pong | red[256*8]
     __shared__ int s_last;
-    __shared__ int s_pend[kBusTree ? 1 + kBusPendMax : 1];
-    if (kBusTree && threadIdx.x == 0) s_pend[0] = 0;  // (ordered before its use by the barriers of the transforms)
     const int M = p.M, half = M >> 1, U = M >> 1;  // U: float4 (bin pairs) per partition row
     const int KT = p.KT;                           // bin tiles (1 for M <= 512)
     const int G = (U >= 256) ? 1 : 256 / U;        // partition lanes per bin pair
@@ -547,8 +545,7 @@ __global__ void __launch_bounds__(256, kMinCtas) upols_fused_kernel(const __grid
         // and on a multi-GPU job the last one exchanges the bus over NVLink (bus_tree.cuh) — no further launch
         float2* yb = reinterpret_cast<float2*>(p.bus.ybus + static_cast<size_t>(t) * M);
         for (int n = tid; n < half; n += 256) yb[n] = z[half + n];
-        bus_tree_arrive(p.bus, t, 0, tid, 256, 0, &s_last, s_pend);
-        bus_tree_finals(p.bus, tid, 256, 0, s_pend);  // this CTA has no other track to process
+        bus_tree_arrive(p.bus, t, 0, tid, 256, 0, &s_last);
     }
     for (int copy = 0; copy < 2; ++copy) {
         float* dst = copy ? p.out2 : p.out;
