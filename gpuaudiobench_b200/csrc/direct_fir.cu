@@ -15,12 +15,17 @@
 // Scheduling (v2, after the first ncu pass: 20 % of SM time idle at 0.86 waves): the job is the
 // flat list of "units" (track, 512-output tile, tap stage); a persistent grid of 2 CTAs per SM
 // splits that list into equal contiguous spans, so every SM gets the same number of stages.  A
-// span may start and end in the middle of a track: each (CTA, track-tile) segment of a SHARED tile
-// writes one partial-sum row and takes a ticket on the tile's counter; the last arriver adds the
-// (static, at most MS) rows in segment order — deterministic, no float atomics — and runs the tile's
-// epilogue in the same launch: output in the requested layout, ring append of the consumed buffer,
-// and the stereo bus tree (bus_tree.cuh), which ends with the NVLink all-reduce on a multi-GPU job.
-// (v3: round 1 used a second launch, fir_finish_mix_kernel, for all of that: 5-9 us of a 54 us step.)
+// span may start and end in the middle of a track: each (CTA, track-tile) segment writes one
+// partial-sum row, and fir_finish_mix_kernel (launched with programmatic dependent launch, so that
+// its CTAs are resident and waiting when the last FIR CTA retires) adds the (static, at most MS) rows
+// of a tile in a fixed order — deterministic, no atomics — writes the output, appends the ring and
+// reduces the stereo bus over a thread-block cluster; on a multi-GPU job the cluster leaders exchange
+// their bus samples over NVLink right there (bus_tree.cuh: bus_ll_push / bus_ll_sum), so the
+// collective has no launch of its own.
+// Round 2 tried the whole tail INSIDE this kernel (last-arriver tickets per tile, then the bus tree):
+// one launch, but every tile of a span schedule completes at the very end, so the three dependent
+// ticket levels (~7 us of L2 round trips) all landed on the critical path: C2 54.3 -> 57.4 us,
+// B = 32 / 64: 17.9 / 20.6 -> 22.5 / 25.7 us.  The kernel boundary is the cheaper grid-wide barrier.
 //
 // Data movement: taps and history are kept PRE-SWIZZLED in HBM (common.cuh: swz_chunk) so that
 // one elected producer lane stages them with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP)
@@ -36,6 +41,18 @@
 #include "common.cuh"
 
 namespace b200conv {
+
+// ---------------------------------------------------------------------------------------------
+// History ring append: ring[t][swz(pos + i)] = in[t][i].  One float4 per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void ring_append_kernel(const float4* __restrict__ in, float4* __restrict__ ring, int T, int B4,
+                                   int cap4, int pos4) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * B4) return;
+    int t = idx / B4;
+    int f = idx - t * B4;
+    ring[static_cast<size_t>(t) * cap4 + swz_chunk(static_cast<uint32_t>(pos4 + f))] = in[idx];
+}
 
 // ---------------------------------------------------------------------------------------------
 // Block loads.  A block is 16 floats (64 B).  Swizzled tiles: byte offset of chunk i of block blk
@@ -96,12 +113,10 @@ __host__ __device__ __forceinline__ long long fir_cta_of_unit(long long u, long 
 }
 
 template <int A>
-__global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(const __grid_constant__ FirParams p) {
+__global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(FirParams p) {
     constexpr int CL = 32 / A;  // tap groups per warp
     constexpr int OT = A * 16;  // outputs per tile
     constexpr bool kSwzTaps = (CL > 1);
-    constexpr int NC = kFirWarps * 32;  // consumer threads (named barrier 1)
-    __shared__ int s_flag;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty_bar = full_bar + kFirMaxStages;
@@ -126,7 +141,8 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
         mbar_fence_init();
     }
     __syncthreads();
-    // PDL: a dependent launch (the strip kernel of a channel-strip job) may be scheduled as our CTAs retire
+    // PDL: let the finish kernel's CTAs be scheduled as ours retire (it waits on
+    // cudaGridDependencySynchronize before touching our partial rows)
     pdl_launch_dependents();
 
     if (warp == kFirWarps) {
@@ -190,6 +206,9 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
         int t = w0 / p.ntiles, ot = w0 - t * p.ntiles;
         int k = k0, slot = 0;
         uint32_t phase = 0;
+        // partial-sum row of the first segment: how many CTAs before this one share its tile
+        int seg = static_cast<int>(blockIdx.x - fir_cta_of_unit(static_cast<long long>(w0) * p.NS, U, G));
+
         for (int it = 0; it < n_units; ++it) {
             mbar_wait(&full_bar[slot], phase);
             const int c0 = k * p.JSb;
@@ -215,7 +234,7 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
 
             const bool tile_done = (k + 1 == p.NS);
             if (tile_done || it + 1 == n_units) {
-                // ---- flush this (CTA, tile) segment: tap groups -> warps -> one row of OT sums ----
+                // ---- flush this (CTA, tile) segment: tap groups -> warps -> one partial row ----
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     acc[r] += accB[r];
@@ -234,95 +253,18 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
                     for (int i = 0; i < 4; ++i)
                         dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
                 }
+                named_bar_sync(1, kFirWarps * 32);
+                float* dstrow = p.partial + (static_cast<size_t>(seg) * p.T + t) * p.B + ot * OT;
+                for (int o = threadIdx.x; o < OT; o += kFirWarps * 32) {
+                    float v = 0.0f;
+#pragma unroll
+                    for (int ww = 0; ww < kFirWarps; ++ww) v += red[ww * OT + o];
+                    dstrow[o] = v;
+                }
+                named_bar_sync(1, kFirWarps * 32);
 #pragma unroll
                 for (int r = 0; r < 16; ++r) acc[r] = 0.0f;
-                named_bar_sync(1, NC);
-                constexpr int VPT = (OT + NC - 1) / NC;  // outputs per consumer thread (2 at OT = 512)
-                const int tid = threadIdx.x;             // consumers are threads 0 .. NC-1
-                float v[VPT];
-#pragma unroll
-                for (int i = 0; i < VPT; ++i) {
-                    const int o = tid + i * NC;
-                    v[i] = 0.0f;
-                    if (o < OT) {
-#pragma unroll
-                        for (int ww = 0; ww < kFirWarps; ++ww) v[i] += red[ww * OT + o];
-                    }
-                }
-                named_bar_sync(1, NC);  // red may be rewritten by the next flush from here on
-                // which CTAs share this tile: [cta_first, cta_last]
-                const long long ufirst = static_cast<long long>(t * p.ntiles + ot) * p.NS;
-                const int cta_first = static_cast<int>(fir_cta_of_unit(ufirst, U, G));
-                const int nseg = static_cast<int>(fir_cta_of_unit(ufirst + p.NS - 1, U, G)) - cta_first + 1;
-                const size_t tile_off = static_cast<size_t>(t) * p.B + ot * OT;
-                bool finish = true;
-                if (nseg > 1) {
-                    float* dstrow = p.partial + static_cast<size_t>(blockIdx.x - cta_first) * p.T * p.B + tile_off;
-#pragma unroll
-                    for (int i = 0; i < VPT; ++i)
-                        if (tid + i * NC < OT) dstrow[tid + i * NC] = v[i];
-                    named_bar_sync(1, NC);  // orders every thread's row stores before thread 0's fence (cumulativity)
-                    if (tid == 0) {
-                        __threadfence();
-                        unsigned* cnt = p.tcount + t * p.ntiles + ot;
-                        const int last = (atomicAdd(cnt, 1u) == static_cast<unsigned>(nseg) - 1u);
-                        if (last) {
-                            *cnt = 0;  // re-armed for the next launch
-                            __threadfence();
-                        }
-                        s_flag = last;
-                    }
-                    named_bar_sync(1, NC);
-                    finish = (s_flag != 0);
-                    if (finish) {
-                        // every row (the own one too) is read back in segment order, all loads in flight before
-                        // the first add: the sum does not depend on which CTA happened to arrive last
-#pragma unroll
-                        for (int i = 0; i < VPT; ++i) {
-                            const int o = tid + i * NC;
-                            if (o < OT) {
-                                float rows[kFirMaxSegRows];
-#pragma unroll
-                                for (int sgm = 0; sgm < kFirMaxSegRows; ++sgm)
-                                    rows[sgm] = (sgm < nseg) ? __ldcg(p.partial + static_cast<size_t>(sgm) * p.T * p.B + tile_off + o) : 0.0f;
-                                float sum = rows[0];
-#pragma unroll
-                                for (int sgm = 1; sgm < kFirMaxSegRows; ++sgm)
-                                    if (sgm < nseg) sum += rows[sgm];
-                                for (int sgm = kFirMaxSegRows; sgm < nseg; ++sgm)  // (not reached by the planner's schedules)
-                                    sum += __ldcg(p.partial + static_cast<size_t>(sgm) * p.T * p.B + tile_off + o);
-                                v[i] = sum;
-                            }
-                        }
-                    }
-                }
-                if (finish) {
-                    // ---- tile epilogue.  The bus first: its tickets and L2 round trips are the critical path after
-                    // the last tile, so nothing slow (cold d_in reads, PCIe stores of a host-resident output) may sit
-                    // in front of its fence; output and ring append follow ----
-                    if (p.bus.mix) {
-#pragma unroll
-                        for (int i = 0; i < VPT; ++i)
-                            if (tid + i * NC < OT) p.bus.ybus[tile_off + tid + i * NC] = v[i];
-                        bus_tree_arrive(p.bus, t, ot, tid, NC, 1, &s_flag);
-                    }
-#pragma unroll
-                    for (int i = 0; i < VPT; ++i) {
-                        const int o = tid + i * NC;
-                        if (o < OT) {
-                            if (p.sample_major)
-                                p.out[static_cast<size_t>(ot * OT + o) * p.Tg + p.toff + t] = v[i];
-                            else
-                                p.out[tile_off + o] = v[i];
-                        }
-                    }
-                    if (p.ring_w) {  // ring[t][swz(pos + n)] = in[t][n] for this tile's columns, one float4 per thread
-                        const float4* src = reinterpret_cast<const float4*>(p.d_in + tile_off);
-                        float4* ring4 = reinterpret_cast<float4*>(p.ring_w + static_cast<size_t>(t) * p.cap);
-                        const uint32_t f0 = static_cast<uint32_t>(p.pos + ot * OT) >> 2;
-                        for (int c = tid; c < OT / 4; c += NC) ring4[swz_chunk(f0 + c)] = src[c];
-                    }
-                }
+                seg = 0;  // any further tile of this CTA starts at its stage 0
             }
             if (++k == p.NS) {
                 k = 0;
@@ -333,13 +275,15 @@ __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm) fir_direct_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stand-alone stereo bus of an output that is already in memory: the UPOLS engine (its tracks retire one by
-// one over the whole launch, and a per-track ticket in the streaming CTA cost more than this PDL-launched
-// kernel: measured 128 -> 133 us on the C4 shard) and a channel strip between convolution and bus.  On a
-// multi-GPU job the thread that holds a finished bus sample exchanges it over NVLink right here
-// (bus_ll_push / bus_ll_sum) — the collective needs no launch of its own.  Thread-block cluster per 32-sample column tile:
-// grid (B/32, CY), cluster (1, CY); the partials are reduced warp -> CTA (shared memory) -> cluster
-// (rank 0 reads the other CTAs' shared memory over DSMEM) in a fixed order.
+// Finish (one launch does everything after the FIR), as a thread-block cluster per 32-sample
+// column tile: grid (B/32, CY), cluster (1, CY), 4 warps per CTA.  Warp (rank, w) walks 8-track
+// groups (rank*4 + w) + j*4*CY and for each
+//   y = sum of the tile's partial rows in a fixed order, written track-major [T][B] or as this
+//       engine's column tile of the sample-major [B][Tg] matrix (bench_conv1d_accel.cu:249 layout);
+//   ring append of the buffer just consumed (skipped for PEEK): ring[t][swz(pos + n)] = in[t][n];
+//   stereo-bus partial l/r += gain * y.
+// The bus partials are then reduced warp -> CTA (shared memory) -> cluster (rank 0 reads the other
+// CTAs' shared memory over DSMEM) in a fixed order: deterministic, no float atomics, no 2nd launch.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cluster_bus_reduce(float l, float r, float* mix, int n0, int B, const BusExchange& x) {
     namespace cg = cooperative_groups;
@@ -375,6 +319,70 @@ __device__ __forceinline__ void cluster_bus_reduce(float l, float r, float* mix,
     cluster.sync();  // nobody's shared memory may go away before rank 0 has read it
 }
 
+__global__ void __launch_bounds__(kBusWarps * 32) fir_finish_mix_kernel(const __grid_constant__ FinishParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * 32, n = n0 + lane;
+    const int T = p.T, B = p.B;
+    const int chunk = p.chunk;  // tracks per warp step (<= kMixChunk), chosen so most warps need one step
+    const int ngroups = (T + chunk - 1) / chunk;
+    float l = 0.0f, r = 0.0f;
+    pdl_launch_dependents();  // e.g. the bus all-reduce kernel of a multi-GPU job
+    pdl_wait_primary();       // partial rows come from the FIR kernel launched just before us
+    if (n < B) {
+        const uint32_t ring_idx = swz_float(static_cast<uint32_t>(p.pos + n));
+        for (int gi = blockIdx.y * kBusWarps + warp; gi < ngroups; gi += kBusWarps * gridDim.y) {
+            const int t0 = gi * chunk;
+            const int tend = min(T, t0 + chunk);
+            float v[kMixChunk], xin[kMixChunk];
+#pragma unroll
+            for (int j = 0; j < kMixChunk; ++j) v[j] = 0.0f;
+            // rows in groups of 4: all loads of a group are issued before the first add (one L2 round trip
+            // per group instead of one per row); the adds keep the fixed row order
+            for (int s0 = 0; s0 < p.MS; s0 += 4) {
+                float pr[4][kMixChunk];
+#pragma unroll
+                for (int ds = 0; ds < 4; ++ds) {
+#pragma unroll
+                    for (int j = 0; j < kMixChunk; ++j)
+                        pr[ds][j] = (s0 + ds < p.MS && t0 + j < tend)
+                                        ? p.partial[(static_cast<size_t>(s0 + ds) * T + t0 + j) * B + n]
+                                        : 0.0f;
+                }
+#pragma unroll
+                for (int ds = 0; ds < 4; ++ds) {
+                    if (s0 + ds < p.MS) {
+#pragma unroll
+                        for (int j = 0; j < kMixChunk; ++j) v[j] += pr[ds][j];
+                    }
+                }
+            }
+            if (p.ring) {
+#pragma unroll
+                for (int j = 0; j < kMixChunk; ++j)
+                    if (t0 + j < tend) xin[j] = p.d_in[static_cast<size_t>(t0 + j) * B + n];
+            }
+#pragma unroll
+            for (int j = 0; j < kMixChunk; ++j) {
+                const int t = t0 + j;
+                if (t < tend) {
+                    if (p.sample_major)
+                        p.out[static_cast<size_t>(n) * p.Tg + p.toff + t] = v[j];
+                    else
+                        p.out[static_cast<size_t>(t) * B + n] = v[j];
+                    if (p.ring) p.ring[static_cast<size_t>(t) * p.cap + ring_idx] = xin[j];
+                    l = fmaf(p.gains[2 * t], v[j], l);
+                    r = fmaf(p.gains[2 * t + 1], v[j], r);
+                }
+            }
+        }
+    }
+    if (p.mix) cluster_bus_reduce(l, r, p.mix, n0, B, p.x);  // kernel-uniform branch
+}
+
+// Stand-alone stereo bus of an output that is already in memory: the UPOLS engine (its tracks retire one by
+// one over the whole launch, and a per-track ticket in the streaming CTA cost more than this PDL-launched
+// kernel: measured 128 -> 133 us on the C4 shard) and a channel strip between convolution and bus.  On a
+// multi-GPU job the thread that holds a finished bus sample exchanges it over NVLink right here.
 __global__ void __launch_bounds__(kBusWarps * 32) mix_cluster_kernel(const float* __restrict__ y, int sample_major, int Tg,
                                                                       int toff, const float* __restrict__ gains,
                                                                       float* __restrict__ mix, int T, int B,
@@ -448,6 +456,13 @@ __global__ void __launch_bounds__(kBusWarps * 32) mix_rows_kernel(const float* _
 // ---------------------------------------------------------------------------------------------
 // Host-side launchers
 // ---------------------------------------------------------------------------------------------
+cudaError_t launch_ring_append(const float* d_in, float* ring, int T, int B, int cap, int pos, cudaStream_t st) {
+    const int total = T * (B / 4);
+    ring_append_kernel<<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(d_in),
+                                                            reinterpret_cast<float4*>(ring), T, B / 4, cap / 4, pos / 4);
+    return cudaGetLastError();
+}
+
 template <int A>
 static cudaError_t launch_fir_t(const FirParams& p, size_t smem, cudaStream_t st) {
     // per (kernel, device): group.cu runs one engine per device in one process
@@ -487,6 +502,14 @@ static int bus_cluster_height(int T, int chunk = kMixChunk) {
     return cy;
 }
 
+// tracks per warp step of the finish kernel: the largest chunk for which the 8 x kBusWarps warps of
+// a full-height cluster still all have work, so each warp issues its loads in a single round
+static int finish_chunk(int T) {
+    int chunk = kMixChunk;
+    while (chunk > 1 && (T + chunk - 1) / chunk < 8 * kBusWarps) chunk /= 2;
+    return chunk;
+}
+
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, int cy, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -504,6 +527,13 @@ static cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, int cy,
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+cudaError_t launch_fir_finish_mix(const FinishParams& p0, cudaStream_t st) {
+    FinishParams p = p0;
+    p.chunk = finish_chunk(p.T);
+    const int cy = bus_cluster_height(p.T, p.chunk);
+    return launch_clustered(fir_finish_mix_kernel, dim3((p.B + 31) / 32, cy), cy, st, p);
 }
 
 cudaError_t launch_mix_cluster(const float* y, int sample_major, int Tg, int toff, const float* gains, float* mix, int T,

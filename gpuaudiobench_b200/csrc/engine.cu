@@ -69,7 +69,6 @@ struct DirectState {
     float* h = nullptr;
     float* ring = nullptr;
     float* partial = nullptr;
-    unsigned* tcount = nullptr;  // [T*ntiles] last-arriver tickets of shared track-tiles
     int pos = 0;
 };
 
@@ -524,7 +523,6 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if ((rc = dev_alloc(e, &d.h, static_cast<size_t>(e->T) * d.Lc * 16))) return bail(rc);
         if ((rc = dev_alloc(e, &d.ring, static_cast<size_t>(e->T) * d.cap))) return bail(rc);
         if ((rc = dev_alloc(e, &d.partial, static_cast<size_t>(d.MS) * tb))) return bail(rc);
-        if ((rc = dev_alloc(e, &d.tcount, static_cast<size_t>(e->T) * d.ntiles))) return bail(rc);
     } else if (impl == B200CONV_ALGO_DIRECT_TC) {
         TcState& c = e->tc;
         if ((rc = dev_alloc(e, &c.bimg, static_cast<size_t>(e->T) * c.g.NGRP * 2 * c.g.image_floats))) return bail(rc);
@@ -800,19 +798,27 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         p.ntiles = d.ntiles;
         p.U = e->T * d.ntiles * d.NS;
         p.G = d.G;
-        // tile epilogue inside the same launch: output, ring append, bus tree (+ NVLink all-reduce)
-        p.tcount = d.tcount;
-        p.out = d_out;
-        p.sample_major = sample_major;
-        p.Tg = e->Tg;
-        p.toff = e->toff;
-        p.ring_w = commit ? d.ring : nullptr;
-        p.cap = d.cap;
-        p.pos = d.pos;
-        p.bus = bus_params(e, e->strip_ops ? nullptr : d_mix);  // with a strip the bus is taken after it
         CU_TRY(launch_fir(p, d.A, d.smem, st));
-        e->launches += 1;
         tm.mark();
+        // tail of the block (PDL-launched behind the FIR): rows -> output, ring append, bus (+ NVLink exchange)
+        FinishParams f{};
+        f.partial = d.partial;
+        f.out = d_out;
+        f.MS = d.MS;
+        f.T = e->T;
+        f.B = e->B;
+        f.sample_major = sample_major;
+        f.Tg = e->Tg;
+        f.toff = e->toff;
+        f.gains = e->d_gains;
+        f.mix = e->strip_ops ? nullptr : d_mix;  // with a strip the bus is taken after it
+        f.d_in = d_in;
+        f.ring = commit ? d.ring : nullptr;
+        f.cap = d.cap;
+        f.pos = d.pos;
+        f.x = bus_exchange(e);
+        CU_TRY(launch_fir_finish_mix(f, st));
+        e->launches += 2;
         if (e->strip_ops) {
             int rc = run_strip(e, d_out, commit, st);
             if (rc) return rc;
@@ -820,8 +826,8 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
                 CU_TRY(launch_mix_cluster(d_out, sample_major, e->Tg, e->toff, e->d_gains, d_mix, e->T, e->B, bus_exchange(e), st));
                 e->launches += 1;
             }
-            tm.mark();
         }
+        tm.mark();
         marks = tm.idx;
         if (commit) d.pos = (d.pos + e->B) % d.cap;
     } else if (e->impl == B200CONV_ALGO_DIRECT_TC) {
@@ -1277,11 +1283,11 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
         info->alg_bytes_per_block = 0;
         info->partitions = e->dir.MS;
         info->fft_size = 0;
-        info->kernels_per_block = e->strip_ops ? 3 : 1;
-        info->stage_count = e->strip_ops ? 2 : 1;
+        info->kernels_per_block = e->strip_ops ? 4 : 2;
+        info->stage_count = 2;
         info->dominant_stage = 0;
         std::snprintf(info->stage_name[0], 24, "fir_direct");
-        std::snprintf(info->stage_name[1], 24, "strip+mix");
+        std::snprintf(info->stage_name[1], 24, e->strip_ops ? "finish+strip+mix" : "finish+mix+append");
     } else {
         const uint64_t P = e->up.P;
         info->flops_per_block = 8 * T * P * (B + 1);

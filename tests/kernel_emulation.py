@@ -44,8 +44,7 @@ def fir_cta_of_unit(u, U, G):
 
 
 class DirectEmu:
-    """Emulates the persistent fir_direct_kernel<A> including its tile epilogue (partial rows of shared tiles,
-    last-arriver ticket, fixed-order row sum, output, ring append of the consumed buffer)."""
+    """Emulates ring_append_kernel + the persistent fir_direct_kernel<A> + fir_finish_mix_kernel."""
 
     def __init__(self, T, B, L, plan):
         self.T, self.B, self.L = T, B, L
@@ -77,18 +76,15 @@ class DirectEmu:
         p, T, B = self.p, self.T, self.B
         A, CL, SPS, JSb, NS, G, MS, ntiles = p["A"], p["CL"], p["SPS"], p["JSb"], p["NS"], p["G"], p["MS"], p["ntiles"]
         capb, posb = self.cap // 16, self.pos // 16
-        partial = np.full((MS, T, B), np.nan)
+        partial = np.zeros((MS, T, B))
         written = np.zeros((MS, T, B), dtype=bool)
-        tcount = np.zeros(T * ntiles, dtype=int)
-        out = np.full((T, B), np.nan)
         OT = A * 16
         U = T * ntiles * NS
-        # CTAs run concurrently on the GPU; any serial order must give the same result.  Descending order makes
-        # the LOWEST CTA of a shared tile the last arriver and lets ring appends of early tracks happen before
-        # later CTAs read the ring — which is only correct if the append region is never read in the same launch.
-        for cta in (range(G - 1, -1, -1) if getattr(self, "reverse", False) else range(G)):
+        for cta in range(G):
             u_lo, u_hi = cta * U // G, (cta + 1) * U // G
             w, k = divmod(u_lo, NS)
+            seg = cta - fir_cta_of_unit(w * NS, U, G)
+            assert 0 <= seg < MS
             acc = np.zeros((KFIR_WARPS, 32, 16))
             for it in range(u_hi - u_lo):
                 t, ot = divmod(w, ntiles)
@@ -134,40 +130,20 @@ class DirectEmu:
                     for warp in range(KFIR_WARPS):
                         for a in range(A):
                             row[a * 16:(a + 1) * 16] += sum(acc[warp, g * A + a] for g in range(CL))
+                    assert not written[seg, t, ot * OT:(ot + 1) * OT].any(), "two segments wrote one partial row"
+                    partial[seg, t, ot * OT:(ot + 1) * OT] = row
+                    written[seg, t, ot * OT:(ot + 1) * OT] = True
                     acc[:] = 0
-                    cta_first = fir_cta_of_unit(w * NS, U, G)
-                    nseg = fir_cta_of_unit(w * NS + NS - 1, U, G) - cta_first + 1
-                    seg = cta - cta_first
-                    assert 0 <= seg < nseg <= MS
-                    cols = slice(ot * OT, (ot + 1) * OT)
-                    finish = True
-                    if nseg > 1:
-                        assert not written[seg, t, cols].any(), "two segments wrote one partial row"
-                        partial[seg, t, cols] = row
-                        written[seg, t, cols] = True
-                        tcount[w] += 1
-                        finish = tcount[w] == nseg
-                        if finish:
-                            tcount[w] = 0  # re-armed
-                            row = partial[0, t, cols].copy()
-                            for sgm in range(1, nseg):
-                                row += partial[sgm, t, cols]
-                    if finish:
-                        assert np.isnan(out[t, cols]).all(), "a tile was finished twice"
-                        out[t, cols] = row
-                        if commit:  # ring[t][swz(pos + n)] = in[t][n] for this tile's columns, one float4 per thread
-                            f0 = (self.pos + ot * OT) >> 2
-                            for c in range(OT // 4):
-                                pf = swz_chunk(f0 + c)
-                                self.ring[t, 4 * pf:4 * pf + 4] = x[t, ot * OT + 4 * c:ot * OT + 4 * c + 4]
+                    seg = 0
                 k += 1
                 if k == NS:
                     k, w = 0, w + 1
-        if commit:
+        if commit:  # fir_finish_mix_kernel appends the consumed buffer
+            for n in range(B):
+                self.ring[:, swz_float(self.pos + n)] = x[:, n]
             self.pos = (self.pos + B) % self.cap
-        assert not tcount.any(), "a tile counter was left armed"
-        assert not np.isnan(out).any(), "a tile was never finished, or a lane read a tile block nobody staged"
-        return out
+        assert not np.isnan(partial).any(), "a lane read a tile block nobody staged"
+        return partial.sum(axis=0)
 
 
 # ------------------------------------------------------------------------------------------------
