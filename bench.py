@@ -211,7 +211,8 @@ def parity_leg(name, eng, bus, step_fn, d_y, d_mix, rank, world, dev, dist, with
         rel = max(float(np.abs(got[i].astype(np.float64) - want[i]).max() / np.abs(want[i]).max()) for i in range(len(keep)))
     # bus: fp64 partial of this rank from its own last-block outputs, summed over ranks
     gains = default_mix_gains(Tg, t0, t0 + T).to(dev).double()  # [T][2]
-    partial = gains.T @ y_last                                   # [2][B] fp64
+    # (elementwise + reduce on purpose: an fp64 `@` would put a library GEMM into the ncu launch lists of this command)
+    partial = (gains.T.unsqueeze(-1) * y_last.unsqueeze(0)).sum(1)  # [2][B] fp64
     bus_got = d_mix.clone()
     identical = True
     if world > 1:

@@ -23,6 +23,8 @@ RAW_KEYS = [
     "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warps_eligible.avg.per_cycle_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
 ]
 
 
@@ -79,8 +81,11 @@ def full(rep):
         op = (toks[1] if toks[0].startswith("@") else toks[0]).split(".")[0]
         byop[op] += int(r[ie])
     te = sum(byop.values()) or 1
+    for op in ("UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS"):
+        if byop.get(op) and op not in dict(byop.most_common(14)):
+            print(f"(also executed: {op} {byop[op]})")
     print("\n== executed warp instructions by opcode, first launch")
-    for op, c in byop.most_common(12):
+    for op, c in byop.most_common(14):
         print(f"{op:10s} {c:12d} {100 * c / te:5.1f}%")
 
 
