@@ -369,10 +369,10 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, s
     peaks, peak_src = measured_peaks()
     if q["stage_name"][dom] == "tc_toeplitz":  # ALGO_DIRECT as the planner dispatched it: the tensor-core kernel
         # tensor pipe: the kernel ISSUES 3 TF32 products (hi/lo split) per algorithmic MAC, on L padded to 128 taps
-        # and N padded to the 144-column MMA; the roofline is the dense TF32 rate = half the measured bf16 rate
+        # and the C - 1 tensor-core columns padded to N-column groups; the roofline is the dense TF32 rate = half the measured bf16 rate
         tf32_peak = float(peaks.get("bf16_tflops", 2250.0 * 0.72)) / 2.0
         plan = g.plan(T, B, L, algo, flags=eng_flags)
-        issued = 3.0 * 2.0 * T * (plan["A"] * 128) * 128 * 80 * plan["NGRP"] * 1.0  # per block: A row blocks x 128 K x (128 x 80) x 3
+        issued = 3.0 * 2.0 * T * (plan["A"] * 128) * 128 * plan["N"] * plan["NGRP"] * 1.0  # per block: A row blocks x 128 K x (128 x N) x 3
         achieved = issued / (dom_ms * 1e-3) / 1e12
         fp32_peak, _ = g.measure_fp32_peak(local_rank)
         alg = q["flops_per_block"] / (dom_ms * 1e-3) / 1e12

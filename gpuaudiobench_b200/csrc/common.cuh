@@ -118,6 +118,11 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// the non-blocking half: these threads signal, the bar.sync side waits for `nthreads` arrivals in total
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16 B aligned; completion is
 // signalled on `bar` as `bytes` transaction bytes.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

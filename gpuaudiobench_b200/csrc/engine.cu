@@ -75,6 +75,8 @@ struct DirectState {
 struct TcState {
     TcGeometry g{};
     float* bimg = nullptr;   // [T][NGRP][2][32][R][4]
+    float* hhead = nullptr;  // [T][B] first B taps, fp32
+    unsigned long long* trace = nullptr;  // B200CONV_TC_TRACE=1: [grid][kTcTraceSlots] phase stamps of the last launch
     float* pend = nullptr;   // [T][capP]
     float* xprev = nullptr;  // [2][T][128] ping-pong
     int ppos = 0, xpar = 0;
@@ -267,7 +269,7 @@ int plan_tc(b200conv_engine* e) {
     TcState& c = e->tc;
     c.g = tc_geometry(B, e->L);
     if (c.g.smem_bytes > 227 * 1024) return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: tile does not fit shared memory");
-    c.grid = std::max(1, std::min(e->T * c.g.NGRP, 2 * e->sm_count));  // persistent over (track, column group) items
+    c.grid = std::max(1, std::min(e->T * c.g.NGRP, e->sm_count));  // persistent over (column group, track) items, one CTA per SM
     return B200CONV_OK;
 }
 
@@ -429,8 +431,8 @@ int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]) {
         int rc = plan_tc(&tmp);
         if (rc) return rc;
         const TcGeometry& g = tmp.tc.g;
-        const int32_t v[8] = {g.A, g.C, g.NE, g.NGRP, g.R, g.capP, static_cast<int32_t>(g.smem_bytes), tmp.tc.grid};
-        std::copy(v, v + 8, plan);
+        const int32_t v[9] = {g.A, g.C, g.NE, g.NGRP, g.R, g.capP, static_cast<int32_t>(g.smem_bytes), tmp.tc.grid, g.N};
+        std::copy(v, v + 9, plan);
     } else {
         return fail(B200CONV_ERR_INVALID, "b200conv_plan: unknown algo");
     }
@@ -526,6 +528,9 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
     } else if (impl == B200CONV_ALGO_DIRECT_TC) {
         TcState& c = e->tc;
         if ((rc = dev_alloc(e, &c.bimg, static_cast<size_t>(e->T) * c.g.NGRP * 2 * c.g.image_floats))) return bail(rc);
+        if ((rc = dev_alloc(e, &c.hhead, tb))) return bail(rc);
+        if (env_int("B200CONV_TC_TRACE", 0))
+            if ((rc = dev_alloc(e, &c.trace, static_cast<size_t>(c.grid) * kTcTraceSlots))) return bail(rc);
         if ((rc = dev_alloc(e, &c.pend, static_cast<size_t>(e->T) * c.g.capP))) return bail(rc);
         if ((rc = dev_alloc(e, &c.xprev, static_cast<size_t>(2) * e->T * 128))) return bail(rc);
     } else {
@@ -609,6 +614,11 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
             CU_TRY(cudaMemcpy(c.bimg + static_cast<size_t>(t0) * per_track, stage.data(),
                               static_cast<size_t>(nt) * per_track * sizeof(float), cudaMemcpyHostToDevice));
         }
+        std::vector<float> head(static_cast<size_t>(T) * B, 0.0f);  // the taps of the buffer's own samples (k < B)
+        for (int t = 0; t < T; ++t)
+            std::memcpy(head.data() + static_cast<size_t>(t) * B, host_ir + static_cast<size_t>(t) * L,
+                        static_cast<size_t>(std::min(B, L)) * sizeof(float));
+        CU_TRY(cudaMemcpy(c.hhead, head.data(), head.size() * sizeof(float), cudaMemcpyHostToDevice));
     } else {
         UpolsState& u = e->up;
         const size_t row = static_cast<size_t>(u.P) * B;  // taps zero padded to P*B
@@ -837,6 +847,8 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         p.d_in = d_in;
         p.xprev = c.xprev;
         p.bimg = c.bimg;
+        p.hhead = c.hhead;
+        p.trace = c.trace;
         p.pend = c.pend;
         p.out = d_out;
         p.T = e->T;
@@ -845,6 +857,8 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         p.C = c.g.C;
         p.NE = c.g.NE;
         p.NGRP = c.g.NGRP;
+        p.N = c.g.N;
+        p.tmem_cols = static_cast<uint32_t>(c.g.tmem_cols);
         p.R = c.g.R;
         p.capP = c.g.capP;
         p.ppos = c.ppos;
@@ -1241,6 +1255,17 @@ int b200conv_bus_trace(b200conv_engine* e, uint64_t* host_stamps, int count) {
         host_stamps[2 * i + 1] = all[(ep % kBusTraceLen) * 2 + 1];
     }
     return B200CONV_OK;
+}
+
+int b200conv_tc_trace(b200conv_engine* e, uint64_t* host_stamps, int max_ctas) {
+    if (!e || !host_stamps || max_ctas < 1) return fail(B200CONV_ERR_INVALID, "b200conv_tc_trace: bad argument");
+    if (e->impl != B200CONV_ALGO_DIRECT_TC || !e->tc.trace)
+        return fail(B200CONV_ERR_STATE, "b200conv_tc_trace: tensor-core direct engine created with B200CONV_TC_TRACE=1 only");
+    ENGINE_DEVICE(e->cfg.device);
+    CU_TRY(cudaDeviceSynchronize());
+    const int n = std::min(max_ctas, e->tc.grid);
+    CU_TRY(cudaMemcpy(host_stamps, e->tc.trace, static_cast<size_t>(n) * kTcTraceSlots * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int b200conv_bus_status(b200conv_engine* e) {

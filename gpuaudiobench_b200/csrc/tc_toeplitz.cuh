@@ -10,18 +10,21 @@
 namespace b200conv {
 
 constexpr int kTcRows = 128;    // MMA M: rows of a slab = samples per tap column (K depth of one row-block)
-constexpr int kTcCols = 80;     // MMA N: output-slab columns per group (TMEM accumulator columns); one group = one work item
+constexpr int kTcMaxCols = 128; // MMA N <= 128: output-slab columns per group (TMEM accumulator columns); one group = one work item
 constexpr int kTcKSteps = 16;   // 128 taps / 8 (K of one kind::tf32 instruction)
 constexpr int kTcPlanes = 32;   // 128 taps / 4 (16-byte K chunks)
 constexpr int kTcThreads = 160; // 4 epilogue/band warps + 1 load/MMA warp
 constexpr int kTcMaxA = 8;      // block <= 1024
+constexpr int kTcTraceSlots = 16;  // diagnostics: stamps per CTA
 
 struct TcGeometry {
     int A;      // row blocks per buffer = B / 128
     int C;      // tap columns = ceil(L / 128)
-    int NE;     // slab columns that receive a contribution = C + A - 1
-    int NGRP;   // column groups of kTcCols
-    int R;      // image rows per group = kTcCols + A - 1
+    int NE;     // slab columns that receive a contribution = C + A - 1; columns < A are the buffer's own samples (FP32 FMA)
+    int N;      // MMA N: columns per group = min(128, roundup(C - 1, 16))
+    int NGRP;   // column groups of N over the tensor-core columns A .. NE-1
+    int R;      // image rows per group = N + A - 1
+    int tmem_cols;  // TMEM allocation: power of two >= 3 N (two accumulators + the staged ring values)
     int capP;   // pending-output ring capacity in floats: roundup(128 * NE, B)
     size_t image_floats;  // floats of one (track, group, part) image = 32 * R * 4
     size_t smem_bytes;
@@ -32,14 +35,17 @@ struct TcParams {
     const float* d_in;   // [T][B]
     float* xprev;        // [2][T][128] the 128 samples before the current buffer, ping-pong: read [xpar], write [xpar ^ 1]
     const float* bimg;   // [T][NGRP][2][32][R][4] tap images (hi part, lo part), zero padded
+    const float* hhead;  // [T][B] the first B taps as they are (zero padded): the buffer's own samples, FP32 FMA
     float* pend;         // [T][capP] pending-output ring
     float* out;          // [T][B] or column tile of [B][Tg]
-    int T, B, A, C, NE, NGRP, R, capP;
+    int T, B, A, C, NE, N, NGRP, R, capP;
+    uint32_t tmem_cols;
     int ppos;            // ring index of output sample 0 of the current buffer
     int xpar;            // which half of xprev holds the previous buffer's tail
     int commit;
     int sample_major, Tg, toff;
     int debug;           // B200CONV_TC_DEBUG (measurement only): 1 skip the MMAs, 2 skip the pending-ring traffic, 4 skip the image load
+    unsigned long long* trace;  // diagnostics (B200CONV_TC_TRACE=1): [grid][kTcTraceSlots] %globaltimer stamps, else null
     BusTreeParams bus;   // bus.mix == null: no bus
 };
 

@@ -87,6 +87,7 @@ def load_library():
     L.b200conv_attach_bus.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int]
     L.b200conv_bus_status.argtypes = [C.c_void_p]
     L.b200conv_bus_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+    L.b200conv_tc_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
     L.b200conv_group_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]
     L.b200conv_group_destroy.argtypes = [C.c_void_p]
     L.b200conv_group_destroy.restype = None
@@ -131,7 +132,7 @@ def _plan_dict(arr):
     if algo == ALGO_DIRECT:
         keys = ("A", "CL", "SPS", "JSb", "NS", "G", "Lc", "cap", "nbuf", "xtile_blocks", "ntiles", "smem", "MS")
     elif algo == ALGO_DIRECT_TC:
-        keys = ("A", "C", "NE", "NGRP", "R", "capP", "smem", "grid")
+        keys = ("A", "C", "NE", "NGRP", "R", "capP", "smem", "grid", "N")
     else:
         keys = ("P", "M", "logM", "S")
     return dict(zip(keys, list(arr)))
@@ -379,6 +380,14 @@ class ConvEngine:
         buf = (C.c_uint64 * (2 * count))()
         _check(self.lib.b200conv_bus_trace(self.handle, buf, count))
         return np.array(buf, dtype=np.uint64).reshape(count, 2)
+
+    def tc_trace(self, max_ctas=296):
+        """[n_ctas][16] device timestamps (ns) of the phases of the last tensor-core launch (B200CONV_TC_TRACE=1)."""
+        buf = (C.c_uint64 * (16 * max_ctas))()
+        n = self.lib.b200conv_tc_trace(self.handle, buf, max_ctas)
+        if n < 0:
+            _check(n)
+        return np.array(buf, dtype=np.uint64).reshape(max_ctas, 16)[:n]
 
     def set_profiling(self, on):
         _check(self.lib.b200conv_set_profiling(self.handle, 1 if on else 0))

@@ -249,6 +249,13 @@ int b200conv_bus_status(b200conv_engine* e);
  * was complete; the difference is what the block spent on the exchange, rank skew included.  Tree-exchange kernels
  * only (direct engines); the engine must have been created with B200CONV_BUS_TRACE=1 in the environment. */
 int b200conv_bus_trace(b200conv_engine* e, uint64_t* host_stamps, int count);
+/* Diagnostics of the tensor-core direct engine (created with B200CONV_TC_TRACE=1 in the environment): device
+ * %globaltimer (ns) stamps of the first work item of every CTA of the LAST launch, host_stamps[16 cta + s], s = 0 item
+ * start, 1 band built, 2 own samples written (column group 0 only), 3 bus tree arrival done (group 0, bus only),
+ * 4 MMAs complete, 5 ring epilogue done, 6 tap image landed / first MMA issued, 7 last MMA issued, 8 ring values
+ * staged in TMEM, 9 / 10 first / fifth epilogue batch stored, 11..15 unused.  Returns the number of CTAs written
+ * (<= max_ctas) or a negative error. */
+int b200conv_tc_trace(b200conv_engine* e, uint64_t* host_stamps, int max_ctas);
 
 /* ---- multi-GPU in one process: one engine per GPU over contiguous track ranges -------------------
  * cfg->tracks is the TOTAL track count Tg (cfg->device / track_offset / total_tracks are ignored);

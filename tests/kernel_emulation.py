@@ -324,8 +324,9 @@ class TcEmu:
     """Mirrors tc_toeplitz_kernel: the band of 4-sample windows (A operand, Hankel via SBO = 128 B / LBO = 64 B),
     the tap images (B operand, rows 16 B apart, planes LBO apart, row block a read A-1-a rows down), the K-major
     no-swizzle core-matrix address rule of the tcgen05 shared-memory descriptor, TMEM accumulation over
-    (a, K-step), and the pending-output ring.  float64, no hi/lo split: this checks addressing, not rounding."""
-    ROWS, COLS, KSTEPS, PLANES = 128, 80, 16, 32
+    (a, K-step), the pending-output ring, and the FP32-FMA walk over the first B taps that produces the buffer's
+    own samples (columns e < A).  float64, no hi/lo split: this checks addressing, not rounding."""
+    ROWS, KSTEPS, PLANES = 128, 16, 32
 
     def __init__(self, T, B, L):
         assert B % 128 == 0
@@ -333,7 +334,8 @@ class TcEmu:
         self.A = B // 128
         self.C = (L + 127) // 128
         self.NE = self.C + self.A - 1
-        self.NGRP = (self.NE + self.COLS - 1) // self.COLS
+        self.COLS = min(128, max(16, (self.C - 1 + 15) // 16 * 16))      # MMA N: the tensor core does columns A .. NE-1
+        self.NGRP = max(1, (self.C - 1 + self.COLS - 1) // self.COLS)
         self.R = self.COLS + self.A - 1
         self.capP = (128 * self.NE + B - 1) // B * B
         self.pend = np.zeros((T, self.capP))
@@ -342,17 +344,20 @@ class TcEmu:
         self.images = None
 
     def load_ir(self, h):
-        # image[grp][S][row][j] = h[128 (e0 + row - (A-1)) + 127 - (4 S + j)], zero outside [0, L)
+        # image[grp][S][row][j] = h[128 c + 127 - (4 S + j)], tap column c = N grp + row + 1, zero outside [0, L)
         img = np.zeros((self.T, self.NGRP, self.PLANES, self.R, 4))
         for grp in range(self.NGRP):
             for S in range(self.PLANES):
                 for row in range(self.R):
-                    c = grp * self.COLS + row - (self.A - 1)
+                    c = grp * self.COLS + row + 1
                     for j in range(4):
                         k = 128 * c + 127 - (4 * S + j)
                         if 0 <= c < self.C and 0 <= k < self.L:
                             img[:, grp, S, row, j] = h[:, k]
         self.images = img
+        self.hhead = np.zeros((self.T, self.B))
+        n = min(self.B, self.L)
+        self.hhead[:, :n] = h[:, :n]
 
     @staticmethod
     def _operand(flat, start, rows, lbo, sbo):
@@ -376,6 +381,31 @@ class TcEmu:
             for g in range(B + 124):
                 band[g] = xw[g + 1:g + 5]
             band = band.ravel()
+            # own samples: lane l owns outputs 128 e + 4 l .. + 3 of every row block e, warp w the taps 32 w .. 32 w + 31
+            # of every tap column c <= e; window float4 index into xw: 32 + qd - kq, qd = 32 e + l, kq = 32 c + 8 w + i
+            hh = self.hhead[t].reshape(-1, 4)
+            xw4 = xw.reshape(-1, 4)
+            part = np.zeros((4, A, 32, 4))
+            for w in range(4):
+                for c in range(A):
+                    for e in range(c, A):
+                        for l in range(32):
+                            base = 32 + 32 * (e - c) + l - 8 * w
+                            assert base - 8 >= 0 and base < xw4.shape[0]
+                            xb = xw4[base]
+                            for i in range(8):
+                                xa = xw4[base - (i + 1)]
+                                win = np.concatenate([xa, xb])    # x[m-4 .. m+3], m = n0 - 4 kq
+                                for k in range(4):
+                                    part[w, e, l] += hh[32 * c + 8 * w + i, k] * win[4 - k:8 - k]
+                                xb = xa
+            for e in range(A):
+                idx = self.ppos + 128 * e
+                if idx >= self.capP:
+                    idx -= self.capP
+                v = ((part[0, e] + part[1, e]) + part[2, e]) + part[3, e]
+                y[t, 128 * e:128 * e + 128] = v.reshape(-1) + self.pend[t, idx:idx + 128]
+                new_pend[t, idx:idx + 128] = 0.0
             for grp in range(self.NGRP):
                 img = self.images[t, grp].ravel()
                 D = np.zeros((self.ROWS, self.COLS))
@@ -385,21 +415,18 @@ class TcEmu:
                         Aop = self._operand(band, 2048 * a + 128 * q, self.ROWS, 64, 128)
                         Bop = self._operand(img, 2 * q * plane_bytes + boff, self.COLS, plane_bytes, 128)
                         D += Aop @ Bop.T
-                e0 = grp * self.COLS
+                e0 = A + grp * self.COLS
+                idx0 = self.ppos + 128 * e0
+                if idx0 >= self.capP:
+                    idx0 -= self.capP
+                nwrap, ncol = (self.capP - idx0) >> 7, min(self.COLS, self.NE - e0)
                 for k in range(self.COLS):
-                    e = e0 + k
-                    if e >= self.NE:
+                    if k >= ncol:
                         assert not D[:, k].any(), "a column beyond NE received a contribution"
                         continue
-                    idx = self.ppos + 128 * e
-                    if idx >= self.capP:
-                        idx -= self.capP
-                    v = D[:, k] + self.pend[t, idx:idx + 128]
-                    if e < A:
-                        y[t, 128 * e:128 * e + 128] = v
-                        new_pend[t, idx:idx + 128] = 0.0
-                    else:
-                        new_pend[t, idx:idx + 128] = v
+                    idx = idx0 + 128 * k - (0 if k < nwrap else self.capP)   # the kernel's wrap-once rule
+                    assert 0 <= idx <= self.capP - 128 and idx == (self.ppos + 128 * (e0 + k)) % self.capP
+                    new_pend[t, idx:idx + 128] = D[:, k] + self.pend[t, idx:idx + 128]
             if commit:
                 self.xprev[t] = xw[B:B + 128]
         if commit:

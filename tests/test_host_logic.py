@@ -173,7 +173,7 @@ def test_planner_dispatches_the_direct_form_between_ffma_and_tensor_cores(monkey
 
 
 @pytest.mark.parametrize("T,B,L,nb", [(2, 128, 300, 5), (1, 256, 1000, 6), (1, 512, 2048, 6), (1, 128, 1, 3),
-                                      (1, 256, 10500, 3)])
+                                      (1, 256, 10500, 3), (1, 256, 20000, 2)])
 def test_tensor_core_fir_operand_addressing(T, B, L, nb):
     """tc_toeplitz.cu: the Hankel band read through overlapping core matrices, the shifted tap images, the
     accumulation over row blocks and K-steps, and the pending-output ring reproduce a plain convolution
@@ -183,7 +183,7 @@ def test_tensor_core_fir_operand_addressing(T, B, L, nb):
     h, xs = rng.standard_normal((T, L)), rng.standard_normal((nb, T, B))
     e = TcEmu(T, B, L)
     p = g.plan(T, B, L, g.ALGO_DIRECT_TC)
-    assert (p["A"], p["C"], p["NE"], p["NGRP"], p["R"], p["capP"]) == (e.A, e.C, e.NE, e.NGRP, e.R, e.capP)
+    assert (p["A"], p["C"], p["NE"], p["NGRP"], p["R"], p["capP"], p["N"]) == (e.A, e.C, e.NE, e.NGRP, e.R, e.capP, e.COLS)
     e.load_ir(h)
     assert np.array_equal(e.process(xs[0], commit=False), e.process(xs[0], commit=False))  # PEEK is idempotent
     ys = np.stack([e.process(xs[m]) for m in range(nb)])
