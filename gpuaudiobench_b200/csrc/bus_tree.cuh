@@ -155,16 +155,18 @@ __device__ __forceinline__ float bus_ll_sum(const BusExchange& x, int n, int i) 
 
 // The chunk's final local bus {l0, r0, l1, r1} of this thread's NP column pairs -> mix, or over NVLink first.
 // Thread `tid` owns the pairs tid + q * nthr (q < NP) of the chunk; a pair is active when 2 * pair < CH.
-template <int NP>
+// kPart: 0 = everything; 1 = the push only (multi-GPU; the caller finishes later with kPart = 2, when the peers'
+// values have had time to arrive — v is not needed then); 2 = gather, sum and write.
+template <int NP, int kPart = 0>
 __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int chunk, const float4 (&v)[NP], int tid, int nthr) {
     const int c0 = chunk * bt.CH;
     const int n = 2 * bt.B;
-    if (bt.x.world > 1 && bt.x.trace && tid == 0 && chunk == 0) {
+    if (kPart != 2 && bt.x.world > 1 && bt.x.trace && tid == 0 && chunk == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         bt.x.trace[(bt.x.epoch % kBusTraceLen) * 2] = now;
     }
-    if (bt.x.world > 1) {
+    if (kPart != 2 && bt.x.world > 1) {
 #pragma unroll
         for (int q = 0; q < NP; ++q) {  // all pushes first, then the polls: the NVLink latencies overlap
             const int pair = tid + q * nthr;
@@ -175,6 +177,7 @@ __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int ch
             }
         }
     }
+    if (kPart == 1) return;
     float sum[4 * NP];
     if (bt.x.world > 1) {  // fixed rank order: every rank computes the bit-identical sum
         int idx[4 * NP];
@@ -212,8 +215,10 @@ __device__ __forceinline__ void bus_finish_chunk(const BusTreeParams& bt, int ch
 // Called by all `nthr` threads of the arriving group (tid = 0 .. nthr-1; they synchronise on hardware
 // barrier `bar_id`) after they have written ybus[t][chunk*CH .. +CH).  `flag` is one int of shared memory.
 // Thread `tid` owns the column pairs tid + q * nthr, q < NP; NP * nthr >= CH / 2 is required.
-template <int NP = 1>
-__device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, int chunk, int tid, int nthr,
+// Returns true (to all threads alike) only with kDefer on a multi-GPU job, in the one CTA that completed the chunk's
+// local bus: its values are pushed to the peers, and the caller owes a bus_tree_finish for the chunk later.
+template <int NP = 1, bool kDefer = false>
+__device__ __forceinline__ bool bus_tree_arrive(const BusTreeParams& bt, int t, int chunk, int tid, int nthr,
                                                 uint32_t bar_id, int* flag) {
     const int g = t / bt.G1;
     const int gsize = min(bt.G1, bt.T - g * bt.G1);
@@ -234,7 +239,7 @@ __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, 
         *flag = last;
     }
     bus_bar(bar_id, nthr);
-    if (!*flag) return;
+    if (!*flag) return false;
     float4 part[NP];  // {l0, r0, l1, r1} per pair
     const float2* gn = reinterpret_cast<const float2*>(bt.gains) + g * bt.G1;
 #pragma unroll
@@ -284,7 +289,7 @@ __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, 
             *flag = last;
         }
         bus_bar(bar_id, nthr);
-        if (!*flag) return;
+        if (!*flag) return false;
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const int pair = tid + q * nthr;
@@ -306,7 +311,20 @@ __device__ __forceinline__ void bus_tree_arrive(const BusTreeParams& bt, int t, 
             }
         }
     }
+    if (kDefer && bt.x.world > 1) {
+        bus_finish_chunk<NP, 1>(bt, chunk, part, tid, nthr);
+        return true;
+    }
     bus_finish_chunk<NP>(bt, chunk, part, tid, nthr);
+    return false;
+}
+// the deferred half of bus_tree_arrive<NP, true>: poll the peers' values (long arrived by now), sum in rank order, write
+template <int NP = 1>
+__device__ __forceinline__ void bus_tree_finish(const BusTreeParams& bt, int chunk, int tid, int nthr) {
+    float4 none[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) none[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    bus_finish_chunk<NP, 2>(bt, chunk, none, tid, nthr);
 }
 #endif  // __CUDACC__
 

@@ -75,12 +75,15 @@ struct DirectState {
 struct TcState {
     TcGeometry g{};
     float* bimg = nullptr;   // [T][NGRP][2][32][R][4]
-    float* hhead = nullptr;  // [T][B] first B taps, fp32
+    float* hhead = nullptr;  // [T][Bs] first Bs taps, fp32
     unsigned long long* trace = nullptr;  // B200CONV_TC_TRACE=1: [grid][kTcTraceSlots] phase stamps of the last launch
     float* pend = nullptr;   // [T][capP]
     float* xprev = nullptr;  // [2][T][128] ping-pong
     int ppos = 0, xpar = 0;
     int grid = 0;
+    int Bs = 0, nsub = 1;    // block of one launch; caller's block = nsub * Bs (buffers > 1024 samples stream through in sub-blocks)
+    int nch = 1;             // bus chunks per launch (<= 512 columns each)
+    float* shadow = nullptr; // [T][capP] + [T][128]: state saved around a PEEK of more than one sub-block
 };
 
 struct UpolsState {
@@ -173,16 +176,17 @@ int dev_alloc(b200conv_engine* e, Tp** out, size_t count, bool zero = true) {
 }
 
 // ALGO_DIRECT is a request for the direct-form sum; the planner picks the kernel.  The tensor-core variant
-// (tc_toeplitz.cu) wins once the job amortises its ~15 us of fixed cost (launch, prologue, TMEM epilogue):
-// measured at C2 (128 x 512 x 16384, 1.07e9 MAC) 36.7 us against 57.4 us for the FFMA kernel; below ~2.5e8 MAC
-// per buffer the FFMA kernel's shorter fixed path is faster.  cfg.flags & B200CONV_FLAG_FFMA_ONLY or
+// (tc_toeplitz.cu) wins once the job amortises its fixed cost (launch, prologue, FP32 own samples, TMEM epilogue):
+// measured at C2 (128 x 512 x 16384, 1.07e9 MAC) 24.6 us against 54.3 us for the FFMA kernel; below ~2.5e8 MAC
+// per buffer the FFMA kernel's shorter fixed path is faster.  Blocks longer than 1024 samples stream through the
+// kernel in sub-blocks (B = 4096: 125 us against 345 us).  cfg.flags & B200CONV_FLAG_FFMA_ONLY or
 // B200CONV_DIRECT_TC=0 keep the FFMA kernel (bit-exact impulse behaviour, 126-131 dB instead of ~110 dB).
 uint32_t resolve_impl(const b200conv_config& cfg) {
     if (cfg.algo != B200CONV_ALGO_DIRECT) return cfg.algo;
     if ((cfg.flags & B200CONV_FLAG_FFMA_ONLY) || env_int("B200CONV_DIRECT_TC", 1) == 0) return B200CONV_ALGO_DIRECT;
-    // (B = 128 is legal for the tensor-core kernel but measured slower than the FFMA kernel: 26.8 against 25.6 us at
-    // 128 tracks x 16384 taps — one row block per item leaves the tensor pipe idle behind the fixed cost)
-    const bool shape_ok = cfg.block % kTcRows == 0 && cfg.block >= 2 * kTcRows && cfg.block <= kTcRows * kTcMaxA;
+    // (B = 128, one row block per item: 22.5 us against 25.7 us for the FFMA kernel at 128 tracks x 16384 taps)
+    const bool shape_ok = cfg.block % kTcRows == 0 && cfg.block >= kTcRows &&
+                          (cfg.block <= kTcRows * kTcMaxA || cfg.block % 512 == 0) && cfg.block <= 512 * kBusMaxChunks;
     const double macs = static_cast<double>(cfg.tracks) * cfg.block * cfg.ir_len;
     return (shape_ok && macs >= 2.5e8) ? B200CONV_ALGO_DIRECT_TC : B200CONV_ALGO_DIRECT;
 }
@@ -262,12 +266,26 @@ int plan_upols(b200conv_engine* e) {
     return B200CONV_OK;
 }
 
+// The block of one tensor-core launch: the caller's block up to 1024 samples, else the largest of 1024 / 512 that
+// divides it — the engine's state is a stream state, so a longer buffer is the same as several shorter ones.
+int tc_sub_block(int B) {
+    if (B <= kTcRows * kTcMaxA) return B;
+    if (B % 1024 == 0) return 1024;
+    if (B % 512 == 0) return 512;
+    return 0;
+}
+
 int plan_tc(b200conv_engine* e) {
     const int B = e->B;
-    if (B % kTcRows || B < kTcRows || B > kTcRows * kTcMaxA)
-        return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: block must be a multiple of 128 in [128, 1024]");
     TcState& c = e->tc;
-    c.g = tc_geometry(B, e->L);
+    c.Bs = (B % kTcRows == 0 && B >= kTcRows) ? tc_sub_block(B) : 0;
+    if (!c.Bs || B > 512 * kBusMaxChunks)
+        return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: block must be a multiple of 128 up to 1024, or a multiple of 512 up to 8192");
+    c.nsub = B / c.Bs;
+    c.nch = (c.Bs + 511) / 512;
+    if (c.Bs % c.nch || (c.Bs / c.nch) % 2)
+        return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: block does not split into even bus chunks");
+    c.g = tc_geometry(c.Bs, e->L);
     if (c.g.smem_bytes > 227 * 1024) return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: tile does not fit shared memory");
     c.grid = std::max(1, std::min(e->T * c.g.NGRP, e->sm_count));  // persistent over (column group, track) items, one CTA per SM
     return B200CONV_OK;
@@ -502,7 +520,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
             e->bus_CH = e->dir.A * 16;
             e->bus_NC = e->dir.ntiles;
         } else if (impl == B200CONV_ALGO_DIRECT_TC) {
-            e->bus_CH = std::min(e->B, 512);  // 128 epilogue threads own two column pairs each
+            e->bus_CH = e->tc.Bs / e->tc.nch;  // <= 512: 128 epilogue threads own two column pairs each
             e->bus_NC = e->B / e->bus_CH;
         } else {
             e->bus_CH = e->B;
@@ -532,6 +550,8 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         if (env_int("B200CONV_TC_TRACE", 0))
             if ((rc = dev_alloc(e, &c.trace, static_cast<size_t>(c.grid) * kTcTraceSlots))) return bail(rc);
         if ((rc = dev_alloc(e, &c.pend, static_cast<size_t>(e->T) * c.g.capP))) return bail(rc);
+        if (c.nsub > 1)
+            if ((rc = dev_alloc(e, &c.shadow, static_cast<size_t>(e->T) * (c.g.capP + 128)))) return bail(rc);
         if ((rc = dev_alloc(e, &c.xprev, static_cast<size_t>(2) * e->T * 128))) return bail(rc);
     } else {
         UpolsState& u = e->up;
@@ -614,10 +634,10 @@ int b200conv_load_ir(b200conv_engine* e, const float* host_ir) {
             CU_TRY(cudaMemcpy(c.bimg + static_cast<size_t>(t0) * per_track, stage.data(),
                               static_cast<size_t>(nt) * per_track * sizeof(float), cudaMemcpyHostToDevice));
         }
-        std::vector<float> head(static_cast<size_t>(T) * B, 0.0f);  // the taps of the buffer's own samples (k < B)
+        std::vector<float> head(static_cast<size_t>(T) * c.Bs, 0.0f);  // the taps of a launch's own samples (k < Bs)
         for (int t = 0; t < T; ++t)
-            std::memcpy(head.data() + static_cast<size_t>(t) * B, host_ir + static_cast<size_t>(t) * L,
-                        static_cast<size_t>(std::min(B, L)) * sizeof(float));
+            std::memcpy(head.data() + static_cast<size_t>(t) * c.Bs, host_ir + static_cast<size_t>(t) * L,
+                        static_cast<size_t>(std::min(c.Bs, L)) * sizeof(float));
         CU_TRY(cudaMemcpy(c.hhead, head.data(), head.size() * sizeof(float), cudaMemcpyHostToDevice));
     } else {
         UpolsState& u = e->up;
@@ -852,7 +872,10 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         p.pend = c.pend;
         p.out = d_out;
         p.T = e->T;
-        p.B = e->B;
+        p.B = c.Bs;
+        p.in_stride = e->B;
+        p.out_stride = e->B;
+        p.nchunk = c.nch;
         p.A = c.g.A;
         p.C = c.g.C;
         p.NE = c.g.NE;
@@ -861,16 +884,42 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
         p.tmem_cols = static_cast<uint32_t>(c.g.tmem_cols);
         p.R = c.g.R;
         p.capP = c.g.capP;
-        p.ppos = c.ppos;
-        p.xpar = c.xpar;
-        p.commit = commit ? 1 : 0;
         p.sample_major = sample_major;
         p.Tg = e->Tg;
         p.toff = e->toff;
         p.debug = env_int("B200CONV_TC_DEBUG", 0);  // measurement only (skip phases)
         p.bus = bus_params(e, e->strip_ops ? nullptr : d_mix);
-        CU_TRY(launch_tc_toeplitz(p, c.grid, st));
-        e->launches += 1;
+        // A PEEK of several sub-blocks has to commit the first ones to compute the later ones: the stream state
+        // (pending ring, previous-128 window) is saved before and put back afterwards.
+        const bool peek_multi = !commit && c.nsub > 1;
+        const size_t ring_floats = static_cast<size_t>(e->T) * c.g.capP;
+        int ppos = c.ppos, xpar = c.xpar;
+        if (peek_multi) {
+            CU_TRY(cudaMemcpyAsync(c.shadow, c.pend, ring_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            CU_TRY(cudaMemcpyAsync(c.shadow + ring_floats, c.xprev + static_cast<size_t>(xpar) * e->T * 128,
+                                   static_cast<size_t>(e->T) * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        for (int s = 0; s < c.nsub; ++s) {
+            p.n_off = s * c.Bs;
+            p.chunk0 = s * c.nch;
+            p.ppos = ppos;
+            p.xpar = xpar;
+            p.commit = (commit || s + 1 < c.nsub) ? 1 : 0;
+            CU_TRY(launch_tc_toeplitz(p, c.grid, st));
+            e->launches += 1;
+            if (p.commit) {
+                ppos = (ppos + c.Bs) % c.g.capP;
+                xpar ^= 1;
+            }
+        }
+        if (peek_multi) {
+            CU_TRY(cudaMemcpyAsync(c.pend, c.shadow, ring_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            CU_TRY(cudaMemcpyAsync(c.xprev + static_cast<size_t>(c.xpar) * e->T * 128, c.shadow + ring_floats,
+                                   static_cast<size_t>(e->T) * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        } else if (commit) {
+            c.ppos = ppos;
+            c.xpar = xpar;
+        }
         tm.mark();
         if (e->strip_ops) {
             int rc = run_strip(e, d_out, commit, st);
@@ -882,10 +931,6 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             tm.mark();
         }
         marks = tm.idx;
-        if (commit) {
-            c.ppos = (c.ppos + e->B) % c.g.capP;
-            c.xpar ^= 1;
-        }
     } else {
         UpolsState& u = e->up;
         const int slot0 = static_cast<int>((u.P - (e->blocks % u.P)) % u.P);
@@ -1298,7 +1343,7 @@ int b200conv_query(b200conv_engine* e, b200conv_info* info) {
         info->alg_bytes_per_block = 0;
         info->partitions = e->tc.g.NGRP;
         info->fft_size = 0;
-        info->kernels_per_block = e->strip_ops ? 3 : 1;
+        info->kernels_per_block = e->tc.nsub + (e->strip_ops ? 2 : 0);
         info->stage_count = e->strip_ops ? 2 : 1;
         info->dominant_stage = 0;
         std::snprintf(info->stage_name[0], 24, "tc_toeplitz");

@@ -199,16 +199,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
     const int B = p.B, N = p.N;
     const uint32_t tmem_cols = p.tmem_cols;
 
-    if (tid == 0) {
-        mbar_init(bfull, 1);
-        mbar_init(dfull, 1);
-        mbar_fence_init();
+    // Warp 4 sets up the barriers and the TMEM allocation while warps 0-3 already fetch the first item's input: no
+    // CTA-wide barrier here, the first item's band barrier publishes both.
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_init(bfull, 1);
+            mbar_init(dfull, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, tmem_cols);
+        tc_fence_before();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    uint32_t tmem = 0;
     uint32_t bphase = 0, dphase = 0;
     const uint32_t idesc = instr_desc_tf32(kTcRows, N);
 
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
         const int capP = p.capP, ppos = p.ppos;
         const bool commit = p.commit != 0, ring_io = !(p.debug & 2);
         const bool own = (grp == 0);
+        uint32_t owed = 0;  // bus chunks whose multi-GPU sum this CTA still has to collect
         auto ring_index = [&](int e) {
             int idx = ppos + 128 * e;
             return idx >= capP ? idx - capP : idx;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
             if (lane == 0) load_images(t, grp);  // the image buffer is free: the previous item's MMAs completed
         } else {
             // ---- band of 4-sample windows of [previous 128 | this buffer], split hi + lo ----
-            const float4* xin4 = reinterpret_cast<const float4*>(p.d_in + static_cast<size_t>(t) * B);
+            const float4* xin4 = reinterpret_cast<const float4*>(p.d_in + static_cast<size_t>(t) * p.in_stride + p.n_off);
             const float4* xp4 = reinterpret_cast<const float4*>(p.xprev + (static_cast<size_t>(p.xpar) * p.T + t) * 128);
             float4* xw4 = reinterpret_cast<float4*>(xw);
             for (int i = tid; i < 32; i += 128) xw4[i] = xp4[i];
@@ -278,6 +282,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         }
         __syncthreads();
+        tc_fence_after();
+        tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         if (stamp && warp == 0) tc_stamp(p, 1);
 
         if (warp == 4) {
@@ -372,22 +378,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
                     float* rslot = pring + ring_index(e) + 4 * lane;
                     v.x += rv[k].x; v.y += rv[k].y; v.z += rv[k].z; v.w += rv[k].w;
                     if (p.sample_major) {
-                        float* o = p.out + static_cast<size_t>(n0) * p.Tg + p.toff + t;
+                        float* o = p.out + static_cast<size_t>(p.n_off + n0) * p.Tg + p.toff + t;
                         o[0] = v.x;
                         o[p.Tg] = v.y;
                         o[2 * static_cast<size_t>(p.Tg)] = v.z;
                         o[3 * static_cast<size_t>(p.Tg)] = v.w;
                     } else {
-                        *reinterpret_cast<float4*>(p.out + static_cast<size_t>(t) * B + n0) = v;
+                        *reinterpret_cast<float4*>(p.out + static_cast<size_t>(t) * p.out_stride + p.n_off + n0) = v;
                     }
-                    if (p.bus.mix) *reinterpret_cast<float4*>(p.bus.ybus + static_cast<size_t>(t) * B + n0) = v;
+                    if (p.bus.mix) *reinterpret_cast<float4*>(p.bus.ybus + static_cast<size_t>(t) * p.bus.B + p.n_off + n0) = v;
                     if (commit && ring_io) *reinterpret_cast<float4*>(rslot) = make_float4(0.f, 0.f, 0.f, 0.f);  // becomes the farthest future slot
                 }
                 named_bar_arrive(2, kTcThreads);  // shared memory is the tensor core's from here
                 if (stamp && warp == 0) tc_stamp(p, 2);
                 // the bus: last-arriver tree over the tracks, and on a multi-GPU job its exchange — all of it under the MMAs
+                // (a multi-GPU job: the CTA that completes the local bus pushes it to the peers here and comes back for
+                // their values after its epilogue — by then they have arrived, nobody waits on NVLink)
                 if (p.bus.mix)
-                    for (int chunk = 0; chunk < p.bus.NC; ++chunk) bus_tree_arrive<2>(p.bus, t, chunk, tid, 128, 1, s_flag);
+                    for (int chunk = 0; chunk < p.nchunk; ++chunk)
+                        if (bus_tree_arrive<2, true>(p.bus, t, p.chunk0 + chunk, tid, 128, 1, s_flag)) owed |= 1u << chunk;
                 if (stamp && warp == 0) tc_stamp(p, 3);
             }
             // ---- epilogue: S (TMEM) + pending ring -> the new pending ring, columns e = A + N grp + j.
@@ -457,13 +466,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
             }
             tc_fence_before();
             if (stamp && warp == 0) tc_stamp(p, 5);
+            for (int chunk = 0; owed >> chunk; ++chunk)
+                if ((owed >> chunk) & 1u) bus_tree_finish<2>(p.bus, p.chunk0 + chunk, tid, 128);
         }
         bphase ^= 1u;
         dphase ^= 1u;
         __syncthreads();  // TMEM drained, band / x window / images free before the next item overwrites them
     }
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+    if (warp == 4) tmem_dealloc(*reinterpret_cast<volatile uint32_t*>(tmem_slot), tmem_cols);
 }
 
 TcGeometry tc_geometry(int B, int L) {

@@ -37,7 +37,11 @@ struct TcParams {
     const float* bimg;   // [T][NGRP][2][32][R][4] tap images (hi part, lo part), zero padded
     const float* hhead;  // [T][B] the first B taps as they are (zero padded): the buffer's own samples, FP32 FMA
     float* pend;         // [T][capP] pending-output ring
-    float* out;          // [T][B] or column tile of [B][Tg]
+    float* out;          // [T][out_stride] or column tile of [B_full][Tg]
+    // B is the block of THIS launch.  A caller's buffer longer than 1024 samples is streamed through the kernel in
+    // sub-blocks (the engine state is a stream state): the launch then works on samples n_off .. n_off + B of rows
+    // that are in_stride / out_stride / bus.B floats long, and on the bus chunks chunk0 .. chunk0 + nchunk.
+    int in_stride, out_stride, n_off, chunk0, nchunk;
     int T, B, A, C, NE, N, NGRP, R, capP;
     uint32_t tmem_cols;
     int ppos;            // ring index of output sample 0 of the current buffer

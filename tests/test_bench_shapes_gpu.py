@@ -130,11 +130,13 @@ def test_ffma_direct_sweep_points_at_16384_taps(oracle, B, A):
                 expect_plan={"A": A, "impl": g.ALGO_DIRECT}, flags=g.engine.FLAG_FFMA_ONLY)
 
 
-@pytest.mark.parametrize("B,impl", [(32, g.ALGO_DIRECT), (128, g.ALGO_DIRECT), (256, g.ALGO_DIRECT_TC), (512, g.ALGO_DIRECT_TC),
-                                    (1024, g.ALGO_DIRECT_TC), (2048, g.ALGO_DIRECT)])
+@pytest.mark.parametrize("B,impl", [(32, g.ALGO_DIRECT), (64, g.ALGO_DIRECT), (128, g.ALGO_DIRECT_TC), (256, g.ALGO_DIRECT_TC),
+                                    (512, g.ALGO_DIRECT_TC), (1024, g.ALGO_DIRECT_TC), (2048, g.ALGO_DIRECT_TC),
+                                    (4096, g.ALGO_DIRECT_TC)])
 def test_direct_sweep_points_as_the_planner_dispatches_them(oracle, B, impl):
     """The same sweep points through plain ALGO_DIRECT, i.e. what bench.py --sweep measures: the tensor-core kernel for
-    256 <= B <= 1024, the FFMA kernel elsewhere; one tolerance for both (100 dB, 1e-5 of max|y|)."""
+    B >= 128 (blocks over 1024 samples stream through it in sub-blocks of 1024), the FFMA kernel below; one tolerance
+    for both (100 dB, 1e-5 of max|y|)."""
     check_shape(oracle, g.ALGO_DIRECT, 128, B, 16384, oracle_tracks=[0, 127], fp64_tracks=[1, 64, 126],
                 expect_plan={"impl": impl})
 

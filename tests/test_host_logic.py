@@ -156,14 +156,17 @@ def test_upols_kernel_index_math(T, B, L, nb):
 
 def test_planner_dispatches_the_direct_form_between_ffma_and_tensor_cores(monkeypatch):
     """ALGO_DIRECT is a request for the direct-form sum; the planner picks the tensor-core kernel for blocks that
-    are a multiple of 128 (<= 1024) once tracks*block*taps >= 2.5e8 MAC, the FFMA kernel otherwise or on request."""
+    are a multiple of 128 up to 1024 — and for longer blocks that are a multiple of 512, which stream through the kernel
+    in sub-blocks — once tracks*block*taps >= 2.5e8 MAC, the FFMA kernel otherwise or on request."""
     D, TC = g.ALGO_DIRECT, g.ALGO_DIRECT_TC
     assert g.plan(128, 512, 16384, D)["impl"] == TC            # C2
     assert g.plan(128, 512, 16384, D, flags=g.engine.FLAG_FFMA_ONLY)["impl"] == D
     assert g.plan(1, 512, 1024, D)["impl"] == D                # C1: far too small to amortise the fixed cost
     assert g.plan(128, 64, 16384, D)["impl"] == D              # block not a multiple of 128
-    assert g.plan(128, 4096, 16384, D)["impl"] == D            # block > 1024
-    assert g.plan(128, 128, 16384, D)["impl"] == D             # one row block per item: the FFMA kernel is faster
+    assert g.plan(128, 4096, 16384, D)["impl"] == TC           # four sub-blocks of 1024
+    assert g.plan(128, 1536, 16384, D)["impl"] == TC           # three sub-blocks of 512
+    assert g.plan(128, 4096, 16384, TC)["A"] == 8              # the geometry is the sub-block's
+    assert g.plan(128, 128, 16384, D)["impl"] == TC            # one row block per item
     assert g.plan(128, 256, 16384, D)["impl"] == TC
     assert g.plan(128, 512, 16384, TC)["impl"] == TC and g.plan(2, 128, 40, TC)["impl"] == TC  # explicit request
     with pytest.raises(g.B200ConvError):

@@ -35,8 +35,11 @@ def assert_parity(got, ref, what=""):
     (2, 1024, 3000, 5),     # 8 row blocks
     (2, 128, 1, 3),         # single tap
     (5, 128, 128, 4),
-    (2, 512, 20000, 42),    # two column groups (NE > 144), ring wraps
+    (2, 512, 20000, 42),    # two column groups (C - 1 > 128), ring wraps
     (150, 256, 700, 5),     # more tracks than SMs: the persistent track loop
+    (3, 640, 4000, 6),      # bus chunks of 320 columns
+    (3, 2048, 3000, 4),     # streamed through the kernel as two sub-blocks of 1024
+    (2, 1536, 9000, 5),     # three sub-blocks of 512
 ])
 def test_streaming_blocks_match_oracle(oracle, T, B, L, M):
     xs = oracle.generate_input(M * T * B, 7).reshape(M, T, B)
@@ -49,7 +52,8 @@ def test_streaming_blocks_match_oracle(oracle, T, B, L, M):
     with g.ConvEngine(T, B, L, TC) as e:
         e.load_ir(h)
         got = np.concatenate([e.process_host(xs[m])[0] for m in range(M)], axis=1)
-        assert e.query()["blocks_processed"] == M and e.query()["kernels_per_block"] == 1
+        nsub = 1 if B <= 1024 else (B // 1024 if B % 1024 == 0 else B // 512)
+        assert e.query()["blocks_processed"] == M and e.query()["kernels_per_block"] == nsub
     for t in tracks:
         assert_parity(got[t], want[t], f"stream T={T} B={B} L={L} track {t}")
         assert_parity(got[t, -B:], want[t][-B:], "last block")
@@ -126,3 +130,26 @@ def test_c2_full_size_vs_r1_fp64_and_the_ffma_engine(oracle):
     theta = (np.arange(T) + 0.5) / T * np.pi / 2
     gains = np.stack([np.cos(theta), np.sin(theta)]) / np.sqrt(T)
     assert snr_db(bus, gains @ truth) >= 100
+
+
+@pytest.mark.parametrize("B", [640, 2048])
+def test_bus_and_peek_with_chunks_and_sub_blocks(oracle, B):
+    """The bus of a block that is reduced in several chunks (B = 640: two of 320 columns) or streamed as sub-blocks
+    (B = 2048: two launches), and PEEK across sub-blocks (state saved and put back): same outputs twice, then commit."""
+    T, L, M = 6, 2500, 3
+    xs = oracle.generate_input(M * T * B, 11).reshape(M, T, B)
+    h = oracle.generate_ir(T, L, "direct")
+    gains = (np.arange(2 * T, dtype=np.float32).reshape(T, 2) + 1) / (2 * T)
+    with g.ConvEngine(T, B, L, TC) as e:
+        e.load_ir(h)
+        e.set_mix_gains(gains)
+        for m in range(M):
+            y0, mix0 = e.process_host(xs[m], flags=g.PEEK, want_mix=True)
+            y1, mix1 = e.process_host(xs[m], flags=g.PEEK, want_mix=True)
+            y2, mix2 = e.process_host(xs[m], want_mix=True)
+            assert np.array_equal(y0, y1) and np.array_equal(y0, y2) and np.array_equal(mix0, mix2) and np.array_equal(mix0, mix1)
+            want_mix = gains.T.astype(np.float64) @ y2.astype(np.float64)
+            assert snr_db(mix2, want_mix) >= 120.0
+        for t in (0, T - 1):
+            want = oracle.stream(xs[:, t, :].ravel(), h[t])
+            assert_parity(y2[t], want[-B:], f"B={B} last block track {t}")
