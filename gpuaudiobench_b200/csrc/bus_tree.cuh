@@ -45,6 +45,8 @@ struct BusExchange {
     unsigned long long* peers[kBusMaxWorld];  // rank p's symmetric buffer uint64 [2][world][n], mapped on this device
     int rank, world;
     uint32_t epoch;  // >= 1, advances by one per exchanged block on every rank
+    uint32_t debug;  // measurement only (B200CONV_BUS_DEBUG, profiles/experiments/n2_fixed_cost.py): 1 push to the own buffer
+                     // only, 2 poll the own slot only, 4 collect right after the push instead of after the epilogue
     uint32_t* err;   // set to 1 if a peer's value did not arrive within the spin bound
     unsigned long long* trace;  // optional diagnostics (b200conv_bus_trace): [kBusTraceLen][2] = %globaltimer ns when this
                                 // rank's bus was ready to push / when the summed bus was complete, indexed by epoch
@@ -64,6 +66,16 @@ struct BusTreeParams {
     BusExchange x;       // multi-GPU exchange (x.world == 1: none)
 };
 
+// The column-slice bus (bus_slice_* below): when every track of the job is finished by a DIFFERENT, co-resident CTA
+// (tracks <= CTAs of one wave), the tracks meet at one counter and every CTA sums a slice of the bus columns over all
+// tracks — one level of L2 round trips instead of the tree's two, and on a multi-GPU job every CTA pushes its own
+// slice to the peers at once.
+struct BusSlice {
+    unsigned long long* arrive;  // device counter, never reset between launches: launch `seq` waits for T * seq
+    unsigned long long target;   // 0: slice bus off (the ticket tree is used)
+    int slice;                   // columns per CTA: a power of two >= 4, slice * T >= columns of the launch
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void bus_bar(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -81,7 +93,8 @@ __device__ __forceinline__ void bus_ll_push(const BusExchange& x, int n, int i, 
     const size_t off = (static_cast<size_t>(x.epoch & 1u) * x.world + x.rank) * n + i;
 #pragma unroll 1
     for (int p = 0; p < x.world; ++p)
-        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(x.peers[p] + off), "l"(word) : "memory");
+        if (!(x.debug & 1u) || p == x.rank)
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(x.peers[p] + off), "l"(word) : "memory");
 }
 // two adjacent values (i even) in ONE 16-byte store per rank.  Each 8-byte half still carries its own epoch, so a
 // reader that finds one half early and the other late simply keeps polling.  (Device timestamps at N = 2 after an L2
@@ -124,7 +137,9 @@ __device__ __forceinline__ void bus_ll_gather(const BusExchange& x, int n, const
             for (int dq = 0; dq < 4; ++dq)
 #pragma unroll
                 for (int j = 0; j < NV; ++j)
-                    if (q0 + dq < x.world && act[j] && static_cast<uint32_t>(w[dq][j] >> 32) != x.epoch) ok = false;
+                    if (q0 + dq < x.world && act[j] && static_cast<uint32_t>(w[dq][j] >> 32) != x.epoch &&
+                        (!(x.debug & 2u) || q0 + dq == x.rank))
+                        ok = false;
             if (ok) break;
             if (++spins > kBusSpinLimit) {
                 *reinterpret_cast<volatile uint32_t*>(x.err) = 1u;  // mapped host memory: a plain store
@@ -325,6 +340,109 @@ __device__ __forceinline__ void bus_tree_finish(const BusTreeParams& bt, int chu
 #pragma unroll
     for (int q = 0; q < NP; ++q) none[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     bus_finish_chunk<NP, 2>(bt, chunk, none, tid, nthr);
+}
+
+// ---- column-slice bus -------------------------------------------------------------------------------------------
+// Called by the `nthr` = 128 threads that have just written ybus[t][n_off .. n_off + Bs) (hardware barrier `bar_id`;
+// `part` is 4 KB of shared memory, `flag` one int).  CTA `t` owns the columns n_off + t * slice .. + slice.  Fixed
+// summation order (row lanes in track order, then lane partials in lane order): the same on every rank.
+// Returns true when the slice's multi-GPU values were pushed and bus_slice_finish is owed.
+__device__ __forceinline__ bool bus_slice_reduce(const BusTreeParams& bt, const BusSlice& sl, int t, int n_off, int Bs,
+                                                 int tid, uint32_t bar_id, float* part, int* flag) {
+    constexpr int nthr = 128;
+    bus_bar(bar_id, nthr);  // the row is written by all threads
+    const int c_lo = t * sl.slice;
+    const bool has_slice = c_lo < Bs;
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(sl.arrive, 1ULL);
+        if (has_slice) {
+            unsigned spins = 0;
+            unsigned long long seen;
+            do {
+                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(seen) : "l"(sl.arrive) : "memory");
+                if (++spins > kBusSpinLimit) {
+                    *reinterpret_cast<volatile uint32_t*>(bt.x.err) = 1u;  // a track never arrived: report, do not hang
+                    break;
+                }
+            } while (seen < sl.target);
+            __threadfence();
+        }
+    }
+    if (!has_slice) return false;
+    bus_bar(bar_id, nthr);  // every track's row is in L2
+    const int Q = sl.slice >> 2, RL = nthr / Q;  // column quads of the slice x row lanes
+    const int rl = tid / Q, q = tid - rl * Q;
+    const int col = n_off + c_lo + 4 * q;        // column in the caller's block
+    const bool live = c_lo + 4 * q < Bs;
+    float4 L = make_float4(0.f, 0.f, 0.f, 0.f), R = L;
+    if (live) {
+        const float* src = bt.ybus + col;
+        const float2* gn = reinterpret_cast<const float2*>(bt.gains);
+        for (int t0 = rl; t0 < bt.T; t0 += 4 * RL) {  // four rows in flight, added in track order
+            float4 y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                y[j] = (t0 + j * RL < bt.T) ? __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(t0 + j * RL) * bt.B))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (t0 + j * RL < bt.T) {
+                    const float2 g = gn[t0 + j * RL];
+                    L.x = fmaf(g.x, y[j].x, L.x); L.y = fmaf(g.x, y[j].y, L.y); L.z = fmaf(g.x, y[j].z, L.z); L.w = fmaf(g.x, y[j].w, L.w);
+                    R.x = fmaf(g.y, y[j].x, R.x); R.y = fmaf(g.y, y[j].y, R.y); R.z = fmaf(g.y, y[j].z, R.z); R.w = fmaf(g.y, y[j].w, R.w);
+                }
+            }
+        }
+    }
+    float4* part4 = reinterpret_cast<float4*>(part);  // [RL][Q][2] float4
+    part4[(rl * Q + q) * 2] = L;
+    part4[(rl * Q + q) * 2 + 1] = R;
+    bus_bar(bar_id, nthr);
+    const int n = 2 * bt.B;
+    const bool multi = bt.x.world > 1;
+    if (multi && bt.x.trace && tid == 0 && t == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        bt.x.trace[(bt.x.epoch % kBusTraceLen) * 2] = now;
+    }
+    for (int f = tid; f < 8 * Q; f += nthr) {  // one thread per bus value of the slice: lane partials in lane order
+        const int fq = f >> 3, k = f & 7;
+        if (c_lo + 4 * fq >= Bs) continue;
+        float sum = 0.0f;
+        for (int r = 0; r < RL; ++r) sum += part[((r * Q + fq) * 2) * 4 + k];
+        const int i = (k < 4 ? 0 : bt.B) + n_off + c_lo + 4 * fq + (k & 3);
+        if (multi)
+            bus_ll_push(bt.x, n, i, sum);
+        else
+            bt.mix[i] = sum;
+    }
+    (void)flag;
+    if (multi && (bt.x.debug & 4u)) {  // measurement only: collect right away instead of after the epilogue
+        for (int f = tid; f < 8 * Q; f += nthr) {
+            const int fq = f >> 3, k = f & 7;
+            if (c_lo + 4 * fq >= Bs) continue;
+            const int i = (k < 4 ? 0 : bt.B) + n_off + c_lo + 4 * fq + (k & 3);
+            bt.mix[i] = bus_ll_sum(bt.x, n, i);
+        }
+        return false;
+    }
+    return multi;
+}
+// the owed half on a multi-GPU job: the peers' values of this CTA's slice (long arrived), summed in rank order
+__device__ __forceinline__ void bus_slice_finish(const BusTreeParams& bt, const BusSlice& sl, int t, int n_off, int Bs, int tid) {
+    const int c_lo = t * sl.slice, Q = sl.slice >> 2, n = 2 * bt.B;
+    for (int f = tid; f < 8 * Q; f += 128) {
+        const int fq = f >> 3, k = f & 7;
+        if (c_lo + 4 * fq >= Bs) continue;
+        const int i = (k < 4 ? 0 : bt.B) + n_off + c_lo + 4 * fq + (k & 3);
+        bt.mix[i] = bus_ll_sum(bt.x, n, i);
+    }
+    if (bt.x.trace && tid == 0 && t == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        bt.x.trace[(bt.x.epoch % kBusTraceLen) * 2 + 1] = now;
+    }
 }
 #endif  // __CUDACC__
 

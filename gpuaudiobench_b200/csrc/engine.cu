@@ -84,6 +84,9 @@ struct TcState {
     int Bs = 0, nsub = 1;    // block of one launch; caller's block = nsub * Bs (buffers > 1024 samples stream through in sub-blocks)
     int nch = 1;             // bus chunks per launch (<= 512 columns each)
     float* shadow = nullptr; // [T][capP] + [T][128]: state saved around a PEEK of more than one sub-block
+    unsigned long long* arrive = nullptr;  // column-slice bus: arrival counter, launch `seq` waits for T * seq
+    unsigned long long seq = 0;
+    int slice = 0;           // columns per CTA of the slice bus; 0: the ticket tree (more tracks than CTAs of one wave)
 };
 
 struct UpolsState {
@@ -288,6 +291,14 @@ int plan_tc(b200conv_engine* e) {
     c.g = tc_geometry(c.Bs, e->L);
     if (c.g.smem_bytes > 227 * 1024) return fail(B200CONV_ERR_INVALID, "tensor-core direct engine: tile does not fit shared memory");
     c.grid = std::max(1, std::min(e->T * c.g.NGRP, e->sm_count));  // persistent over (column group, track) items, one CTA per SM
+    // The column-slice bus needs every track on its own CTA of the first wave (items are ordered group 0 first, so
+    // CTA t < T owns track t): all of them are resident at once and can wait for each other.
+    c.slice = 0;
+    if (e->T <= c.grid && env_int("B200CONV_BUS_SLICE", 1)) {
+        int sl = 4;
+        while (sl * e->T < c.Bs) sl *= 2;
+        if (sl <= 512) c.slice = sl;
+    }
     return B200CONV_OK;
 }
 
@@ -316,6 +327,8 @@ int reset_state(b200conv_engine* e) {
         CU_TRY(cudaMemset(e->tc.xprev, 0, static_cast<size_t>(2) * e->T * 128 * sizeof(float)));
         e->tc.ppos = 0;
         e->tc.xpar = 0;
+        CU_TRY(cudaMemset(e->tc.arrive, 0, sizeof(unsigned long long)));
+        e->tc.seq = 0;
     } else {
         CU_TRY(cudaMemset(e->up.X, 0, static_cast<size_t>(e->T) * e->up.P * e->up.M * sizeof(float2)));
         CU_TRY(cudaMemset(e->up.prev, 0, static_cast<size_t>(2) * e->T * e->B * sizeof(float)));
@@ -366,6 +379,7 @@ BusExchange bus_exchange(const b200conv_engine* e) {
     x.epoch = e->bus_epoch;
     x.err = e->d_bus_err;
     x.trace = e->d_bus_trace;
+    x.debug = static_cast<uint32_t>(env_int("B200CONV_BUS_DEBUG", 0));
     return x;
 }
 
@@ -547,6 +561,7 @@ int b200conv_create(const b200conv_config* cfg, b200conv_engine** out) {
         TcState& c = e->tc;
         if ((rc = dev_alloc(e, &c.bimg, static_cast<size_t>(e->T) * c.g.NGRP * 2 * c.g.image_floats))) return bail(rc);
         if ((rc = dev_alloc(e, &c.hhead, tb))) return bail(rc);
+        if ((rc = dev_alloc(e, &c.arrive, 1))) return bail(rc);
         if (env_int("B200CONV_TC_TRACE", 0))
             if ((rc = dev_alloc(e, &c.trace, static_cast<size_t>(c.grid) * kTcTraceSlots))) return bail(rc);
         if ((rc = dev_alloc(e, &c.pend, static_cast<size_t>(e->T) * c.g.capP))) return bail(rc);
@@ -905,6 +920,12 @@ static int process_impl(b200conv_engine* e, const float* d_in, float* d_out, flo
             p.ppos = ppos;
             p.xpar = xpar;
             p.commit = (commit || s + 1 < c.nsub) ? 1 : 0;
+            p.slice = BusSlice{};
+            if (p.bus.mix && c.slice) {
+                p.slice.arrive = c.arrive;
+                p.slice.target = static_cast<unsigned long long>(e->T) * ++c.seq;
+                p.slice.slice = c.slice;
+            }
             CU_TRY(launch_tc_toeplitz(p, c.grid, st));
             e->launches += 1;
             if (p.commit) {

@@ -152,14 +152,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct SmemMap {
-    int xw_off, hs_off, red_off, band_hi_off, band_lo_off, bimg_off, total;
+    int xw_off, hs_off, red_off, part_off, band_hi_off, band_lo_off, bimg_off, total;
 };
 __host__ __device__ inline SmemMap smem_map(int B, int R) {
     SmemMap m{};
     m.xw_off = 128;
     m.hs_off = m.xw_off + round_up((B + 128) * 4, 128);
     m.red_off = m.hs_off + B * 4;               // [4 warps][A][32 lanes] float4 = 16 B bytes
-    m.band_hi_off = m.red_off + B * 16;
+    m.part_off = m.red_off + B * 16;            // column-slice bus: [128 threads][2] float4
+    m.band_hi_off = m.part_off + 4096;
     const int band_bytes = round_up((B + 127) * 16, 128);
     m.band_lo_off = m.band_hi_off + band_bytes;
     m.bimg_off = round_up(m.band_lo_off + band_bytes, 1024);
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
     float* xw = reinterpret_cast<float*>(smem + sm.xw_off);    // xw[i] = x[i - 128]
     float4* hs4 = reinterpret_cast<float4*>(smem + sm.hs_off); // the first B taps (own samples)
     float4* red4 = reinterpret_cast<float4*>(smem + sm.red_off);
+    float* bus_part = reinterpret_cast<float*>(smem + sm.part_off);
     unsigned char* band_hi = smem + sm.band_hi_off;            // band[g] = x[g-127 .. g-124], g < B + 124
     unsigned char* band_lo = smem + sm.band_lo_off;
     unsigned char* bimg_s = smem + sm.bimg_off;                // [2 parts][32 planes][R rows][16 B]
@@ -394,9 +396,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
                 // the bus: last-arriver tree over the tracks, and on a multi-GPU job its exchange — all of it under the MMAs
                 // (a multi-GPU job: the CTA that completes the local bus pushes it to the peers here and comes back for
                 // their values after its epilogue — by then they have arrived, nobody waits on NVLink)
-                if (p.bus.mix)
-                    for (int chunk = 0; chunk < p.nchunk; ++chunk)
-                        if (bus_tree_arrive<2, true>(p.bus, t, p.chunk0 + chunk, tid, 128, 1, s_flag)) owed |= 1u << chunk;
+                if (p.bus.mix) {
+                    if (p.slice.target) {
+                        if (bus_slice_reduce(p.bus, p.slice, t, p.n_off, B, tid, 1, bus_part, s_flag)) owed = 1u;
+                    } else {
+                        for (int chunk = 0; chunk < p.nchunk; ++chunk)
+                            if (bus_tree_arrive<2, true>(p.bus, t, p.chunk0 + chunk, tid, 128, 1, s_flag)) owed |= 1u << chunk;
+                    }
+                }
                 if (stamp && warp == 0) tc_stamp(p, 3);
             }
             // ---- epilogue: S (TMEM) + pending ring -> the new pending ring, columns e = A + N grp + j.
@@ -466,8 +473,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_toeplitz_kernel(const __grid
             }
             tc_fence_before();
             if (stamp && warp == 0) tc_stamp(p, 5);
-            for (int chunk = 0; owed >> chunk; ++chunk)
-                if ((owed >> chunk) & 1u) bus_tree_finish<2>(p.bus, p.chunk0 + chunk, tid, 128);
+            if (owed && p.slice.target) {
+                bus_slice_finish(p.bus, p.slice, t, p.n_off, B, tid);
+            } else {
+                for (int chunk = 0; owed >> chunk; ++chunk)
+                    if ((owed >> chunk) & 1u) bus_tree_finish<2>(p.bus, p.chunk0 + chunk, tid, 128);
+            }
         }
         bphase ^= 1u;
         dphase ^= 1u;

@@ -51,6 +51,7 @@ struct TcParams {
     int debug;           // B200CONV_TC_DEBUG (measurement only): 1 skip the MMAs, 2 skip the pending-ring traffic, 4 skip the image load
     unsigned long long* trace;  // diagnostics (B200CONV_TC_TRACE=1): [grid][kTcTraceSlots] %globaltimer stamps, else null
     BusTreeParams bus;   // bus.mix == null: no bus
+    BusSlice slice;      // slice.target != 0: the column-slice bus (every track on its own co-resident CTA), else the tree
 };
 
 cudaError_t launch_tc_toeplitz(const TcParams& p, int grid, cudaStream_t st);
