@@ -344,7 +344,7 @@ __device__ __forceinline__ void bus_tree_finish(const BusTreeParams& bt, int chu
 
 // ---- column-slice bus -------------------------------------------------------------------------------------------
 // Called by the `nthr` = 128 threads that have just written ybus[t][n_off .. n_off + Bs) (hardware barrier `bar_id`;
-// `part` is 4 KB of shared memory, `flag` one int).  CTA `t` owns the columns n_off + t * slice .. + slice.  Fixed
+// `part` is 4.5 KB of shared memory, `flag` one int).  CTA `t` owns the columns n_off + t * slice .. + slice.  Fixed
 // summation order (row lanes in track order, then lane partials in lane order): the same on every rank.
 // Returns true when the slice's multi-GPU values were pushed and bus_slice_finish is owed.
 __device__ __forceinline__ bool bus_slice_reduce(const BusTreeParams& bt, const BusSlice& sl, int t, int n_off, int Bs,
@@ -406,16 +406,38 @@ __device__ __forceinline__ bool bus_slice_reduce(const BusTreeParams& bt, const 
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         bt.x.trace[(bt.x.epoch % kBusTraceLen) * 2] = now;
     }
-    for (int f = tid; f < 8 * Q; f += nthr) {  // one thread per bus value of the slice: lane partials in lane order
-        const int fq = f >> 3, k = f & 7;
-        if (c_lo + 4 * fq >= Bs) continue;
-        float sum = 0.0f;
-        for (int r = 0; r < RL; ++r) sum += part[((r * Q + fq) * 2) * 4 + k];
+    // The RL lane partials of each of the slice's NO = 8 Q bus values, in lane order — in two steps when there are more
+    // threads than values (C2: 8 values, 128 lanes: 16 segments of 8 lanes, then the 16 segment sums), because a single
+    // thread adding 128 shared-memory values one after the other is 2 us on the way to the bus.
+    const int NO = 8 * Q;
+    const int nseg = NO < nthr ? nthr / NO : 1, per = RL / nseg;
+    float* part2 = part + 8 * nthr;  // [nseg][NO]
+    auto emit = [&](int o, float sum) {
+        const int fq = o >> 3, k = o & 7;
+        if (c_lo + 4 * fq >= Bs) return;
         const int i = (k < 4 ? 0 : bt.B) + n_off + c_lo + 4 * fq + (k & 3);
         if (multi)
             bus_ll_push(bt.x, n, i, sum);
         else
             bt.mix[i] = sum;
+    };
+    if (nseg > 1) {
+        const int o = tid % NO, sg = tid / NO;
+        float sum = 0.0f;
+        for (int r = sg * per; r < (sg + 1) * per; ++r) sum += part[(r * Q + (o >> 3)) * 8 + (o & 7)];
+        part2[sg * NO + o] = sum;
+        bus_bar(bar_id, nthr);
+        if (tid < NO) {
+            float tot = 0.0f;
+            for (int g2 = 0; g2 < nseg; ++g2) tot += part2[g2 * NO + tid];
+            emit(tid, tot);
+        }
+    } else {
+        for (int o = tid; o < NO; o += nthr) {
+            float sum = 0.0f;
+            for (int r = 0; r < RL; ++r) sum += part[(r * Q + (o >> 3)) * 8 + (o & 7)];
+            emit(o, sum);
+        }
     }
     (void)flag;
     if (multi && (bt.x.debug & 4u)) {  // measurement only: collect right away instead of after the epilogue

@@ -159,8 +159,8 @@ __host__ __device__ inline SmemMap smem_map(int B, int R) {
     m.xw_off = 128;
     m.hs_off = m.xw_off + round_up((B + 128) * 4, 128);
     m.red_off = m.hs_off + B * 4;               // [4 warps][A][32 lanes] float4 = 16 B bytes
-    m.part_off = m.red_off + B * 16;            // column-slice bus: [128 threads][2] float4
-    m.band_hi_off = m.part_off + 4096;
+    m.part_off = m.red_off + B * 16;            // column-slice bus: [128 threads][2] float4 + [128] segment sums
+    m.band_hi_off = m.part_off + 4096 + 512;
     const int band_bytes = round_up((B + 127) * 16, 128);
     m.band_lo_off = m.band_hi_off + band_bytes;
     m.bimg_off = round_up(m.band_lo_off + band_bytes, 1024);
