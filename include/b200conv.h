@@ -56,7 +56,8 @@ typedef enum b200conv_algo {
     B200CONV_ALGO_UPOLS = 1,  /* partitioned overlap-save — replaces the cuFFT pipeline, cuda/bench_conv1d_accel.cu:258-304 */
     B200CONV_ALGO_DIRECT_TC = 2 /* the same direct-form sum as ALGO_DIRECT on the tensor cores (tcgen05 kind::tf32 with a
                                    3-term hi/lo split, accumulators in TMEM): input-side Toeplitz GEMM per track and buffer,
-                                   state = pending-output ring.  block: multiple of 128 in [128, 1024].
+                                   state = pending-output ring; the buffer's own samples in FP32 FMA.  block: a multiple
+                                   of 128 up to 1024, or a multiple of 512 up to 8192 (streamed as sub-blocks).
                                    Replaces cuda/bench_conv1d.cu:7-27 like ALGO_DIRECT (csrc/tc_toeplitz.cu) */
 } b200conv_algo;
 
@@ -68,7 +69,8 @@ typedef enum b200conv_layout {
 /* b200conv_config.flags */
 #define B200CONV_FLAG_FFMA_ONLY 1u /* ALGO_DIRECT: never dispatch to the tensor-core kernel (keeps the FFMA kernel's bit-exact
                                       impulse behaviour and its 126-131 dB; the default planner picks DIRECT_TC for blocks of
-                                      256, 384 ... 1024 samples once tracks*block*ir_len >= 2.5e8, ~110 dB) */
+                                      128, 256 ... 1024 samples and multiples of 512 beyond, once
+                                      tracks*block*ir_len >= 2.5e8, ~110 dB) */
 
 /* b200conv_process flags */
 #define B200CONV_PEEK 1u /* compute this block but do not advance the stream state: repeated calls
@@ -280,7 +282,8 @@ const char* b200conv_group_last_error(void);
 
 /* Launch plan the engine would use for `cfg` on a device with `sm_count` SMs; needs no GPU.
  * plan[0..15] = direct: {A, CL, SPS, JSb, NS, G, Lc, cap, nbuf, xtile_blocks, ntiles, smem_bytes, MS, 0...}
- *               UPOLS : {P, M, logM, S, 0...};  DIRECT_TC: {A, C, NE, NGRP, R, capP, smem_bytes, grid, 0...}.
+ *               UPOLS : {P, M, logM, S, 0...};  DIRECT_TC: {A, C, NE, NGRP, R, capP, smem_bytes, grid, N, 0...}
+ *               (A, R, capP, N describe one launch: the sub-block when block > 1024).
  * plan[15] = the b200conv_algo value of the kernel family the planner chose (ALGO_DIRECT may resolve to DIRECT_TC).
  * Used by the host-logic tests and by capacity planning. */
 int b200conv_plan(const b200conv_config* cfg, int sm_count, int32_t plan[16]);
