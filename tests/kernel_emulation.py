@@ -434,3 +434,65 @@ class TcEmu:
             self.ppos = (self.ppos + B) % self.capP
         assert not np.isnan(y).any()
         return y
+
+
+def bus_slice_width(T, Bs):
+    """csrc/engine.cu plan_tc: columns per CTA of the column-slice bus (0 = ticket tree)."""
+    sl = 4
+    while sl * T < Bs:
+        sl *= 2
+    return sl if sl <= 512 else 0
+
+
+def bus_slice_emulate(y, gains, B, n_off, Bs, sl):
+    """Mirrors bus_slice_reduce (csrc/bus_tree.cuh) for one launch: CTA t sums the columns n_off + t*sl .. + sl of the
+    rows y[T][B] over all tracks with 128 threads = (row lanes) x (column quads), lane partials through shared memory
+    in two steps.  Returns mix[2][B] with NaN where the launch writes nothing, and asserts every slot is written once."""
+    T = y.shape[0]
+    nthr = 128
+    mix = np.full(2 * B, np.nan)
+    Q, RL = sl // 4, nthr // (sl // 4)
+    assert Q * RL == nthr and sl * T >= Bs
+    for t in range(T):
+        c_lo = t * sl
+        if c_lo >= Bs:
+            continue
+        part = np.zeros(nthr * 8)
+        for tid in range(nthr):
+            rl, q = tid // Q, tid % Q
+            col = n_off + c_lo + 4 * q
+            L, R = np.zeros(4), np.zeros(4)
+            if c_lo + 4 * q < Bs:
+                assert col + 4 <= B
+                for t0 in range(rl, T, 4 * RL):
+                    for j in range(4):
+                        row = t0 + j * RL
+                        if row < T:
+                            L += gains[row, 0] * y[row, col:col + 4]
+                            R += gains[row, 1] * y[row, col:col + 4]
+            part[(rl * Q + q) * 8:(rl * Q + q) * 8 + 4] = L
+            part[(rl * Q + q) * 8 + 4:(rl * Q + q) * 8 + 8] = R
+        NO = 8 * Q
+        nseg = nthr // NO if NO < nthr else 1
+        per = RL // nseg
+        assert per * nseg == RL
+
+        def emit(o, total):
+            fq, k = o >> 3, o & 7
+            if c_lo + 4 * fq >= Bs:
+                return
+            i = (0 if k < 4 else B) + n_off + c_lo + 4 * fq + (k & 3)
+            assert np.isnan(mix[i]), "a bus value written twice"
+            mix[i] = total
+
+        if nseg > 1:
+            part2 = np.zeros(nseg * NO)
+            for tid in range(nthr):
+                o, sg = tid % NO, tid // NO
+                part2[sg * NO + o] = sum(part[(r * Q + (o >> 3)) * 8 + (o & 7)] for r in range(sg * per, (sg + 1) * per))
+            for tid in range(NO):
+                emit(tid, sum(part2[g2 * NO + tid] for g2 in range(nseg)))
+        else:
+            for o in range(NO):
+                emit(o, sum(part[(r * Q + (o >> 3)) * 8 + (o & 7)] for r in range(RL)))
+    return mix.reshape(2, B)

@@ -191,3 +191,23 @@ def test_tensor_core_fir_operand_addressing(T, B, L, nb):
     assert np.array_equal(e.process(xs[0], commit=False), e.process(xs[0], commit=False))  # PEEK is idempotent
     ys = np.stack([e.process(xs[m]) for m in range(nb)])
     assert np.abs(ys - _truth(xs, h)).max() < 1e-10
+
+
+@pytest.mark.parametrize("T,B,Bs,n_off", [(128, 512, 512, 0), (3, 512, 512, 0), (16, 2048, 1024, 1024), (148, 128, 128, 0),
+                                          (1, 512, 512, 0), (5, 640, 640, 0), (40, 1024, 1024, 0)])
+def test_column_slice_bus_index_math(T, B, Bs, n_off):
+    """bus_slice_reduce (csrc/bus_tree.cuh): slice width as the engine picks it, the (row lane, column quad) thread
+    map, the two-step sum of the lane partials and the output index: every bus value of the launch's columns is
+    written exactly once and equals gains^T y; nothing outside the launch's columns is touched."""
+    from kernel_emulation import bus_slice_emulate, bus_slice_width
+    rng = np.random.default_rng(9)
+    y, gains = rng.standard_normal((T, B)), rng.standard_normal((T, 2))
+    sl = bus_slice_width(T, Bs)
+    assert sl >= 4 and sl & (sl - 1) == 0 and sl * T >= Bs and (sl == 4 or (sl // 2) * T < Bs)
+    mix = bus_slice_emulate(y, gains, B, n_off, Bs, sl)
+    want = gains.T @ y
+    inside = np.zeros(B, dtype=bool)
+    inside[n_off:n_off + Bs] = True
+    assert not np.isnan(mix[:, inside]).any() and np.isnan(mix[:, ~inside]).all()
+    assert np.abs(mix[:, inside] - want[:, inside]).max() < 1e-12
+    assert bus_slice_width(1, 1024) == 0  # one track, 1024 columns: wider than a CTA's 512 -> the ticket tree
