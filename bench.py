@@ -301,6 +301,9 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, s
         else:
             torch.cuda.synchronize(dev)
 
+    import gc
+    gc.collect()
+    gc.disable()  # a collector pause on one rank's host thread shows up as a late bus push on every rank's device clock
     aligned_start()
     wall0 = time.perf_counter()
     for k in range(K):
@@ -309,6 +312,7 @@ def run_workload(name, args, rank, world, local_rank, dist, want_cpu_baseline, s
         step(k)
         ev1[k].record(stream)
     torch.cuda.synchronize(dev)
+    gc.enable()
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
