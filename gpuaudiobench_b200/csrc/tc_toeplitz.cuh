@@ -48,7 +48,8 @@ struct TcParams {
     int xpar;            // which half of xprev holds the previous buffer's tail
     int commit;
     int sample_major, Tg, toff;
-    int debug;           // B200CONV_TC_DEBUG (measurement only): 1 skip the MMAs, 2 skip the pending-ring traffic, 4 skip the image load
+    int debug;           // B200CONV_TC_DEBUG (measurement only): 1 skip the MMAs, 2 skip the pending-ring traffic, 4 skip the image load,
+                         // 32 skip staging the ring values in TMEM (wrong results, timing only)
     unsigned long long* trace;  // diagnostics (B200CONV_TC_TRACE=1): [grid][kTcTraceSlots] %globaltimer stamps, else null
     BusTreeParams bus;   // bus.mix == null: no bus
     BusSlice slice;      // slice.target != 0: the column-slice bus (every track on its own co-resident CTA), else the tree

@@ -240,6 +240,8 @@ int b200conv_bus_allreduce(const float* d_local, float* d_out, const uint64_t* p
  * blocks with a bus (d_mix / h_mix != NULL), PEEK blocks included.  peer_buffers[p]: address, valid on
  * THIS engine's device, of rank p's zero-initialised buffer of b200conv_bus_buffer_bytes(world, 2*B)
  * bytes (as for b200conv_bus_allreduce).  peer_buffers == NULL or world <= 1 detaches.
+ * One engine per device is the intended use; engines of one group that share a device must be small enough to be
+ * resident together (each waits inside its kernel for the others' bus), or run with B200CONV_BUS_SLICE=0.
  * No reference counterpart (the reference is single-GPU). */
 int b200conv_attach_bus(b200conv_engine* e, const uint64_t* peer_buffers, int rank, int world);
 /* Synchronises the engine's stream; B200CONV_ERR_CUDA if a peer missed a bus exchange since the last
