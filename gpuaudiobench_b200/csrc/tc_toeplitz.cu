@@ -14,16 +14,16 @@
 //
 // The future outputs live in a per-track pending-output ring (overlap-add in the time domain): a buffer adds
 // S to it, emits its own B samples and hands the rest on.  S accumulates over (a, d) inside TMEM — 16 A K-steps
-// of one 128 x 64 x 8 kind::tf32 MMA each per 64-column group — so the skewed sum costs nothing outside the
-// tensor core.
+// of three 128 x N x 8 kind::tf32 MMAs per N-column group (N <= 128) — so the skewed sum costs nothing outside
+// the tensor core.
 //
 // The columns are split by WHEN they are needed.  The buffer's own samples are the columns e < A: they involve
 // the first B taps only (1.6 % of the work at C2), and everything after the kernel — the stereo bus, its
-// multi-GPU exchange, the caller — waits for them.  They are computed right away in FP32 FMA by the four warps
-// that would otherwise sit idle while the tensor core runs, written out, and handed to the bus tree, so that the
-// tree's chain of L2 round trips and the NVLink exchange run UNDER the MMAs instead of after them.  The tensor
-// core does the columns A <= e < NE, which only feed the pending ring (C - 1 columns: 127 = two groups of 64
-// at L = 16384, no padding).
+// multi-GPU exchange, the caller — waits for them.  They are computed FIRST, in FP32 FMA by the four band /
+// epilogue warps (not beside the MMAs: the tensor core's operand reads saturate shared memory), written out, and
+// handed to the in-kernel bus (bus_tree.cuh), so that its chain of L2 round trips and the NVLink exchange run
+// UNDER the MMAs instead of after them.  The tensor core does the columns A <= e < NE, which only feed the pending
+// ring (C - 1 columns: 127 = one group of 128 at L = 16384).  One (group, track) item per CTA, one CTA per SM.
 //
 // Operands, both K-major, no swizzle ("interleaved" canonical layout: 8-row x 16-byte core matrices, 8-row
 // groups SBO apart, the two 16-byte K chunks of an instruction LBO apart):
@@ -31,7 +31,7 @@
 //      16 B apart, and with LBO = 64 B a K chunk further is the same as 4 rows further — so ONE array of
 //      "4-sample windows", band[g] = x[g-127 .. g-124], serves every (a, K-step) by moving the start address
 //      (+2048 B per row block, +128 B per K-step).  No Toeplitz matrix is ever materialised: B+124 windows.
-//   B (taps): image[plane S][row][4] = h[128 (row + 1 + 64 grp) + 127 - (4 S + j)] (row 0 of group 0 is tap
+//   B (taps): image[plane S][row][4] = h[128 (row + 1 + N grp) + 127 - (4 S + j)] (row 0 of group 0 is tap
 //      column 1: column e = A of row block a = A-1), rows 16 B apart (SBO = 128 B), planes LBO = 16 R apart;
 //      the row block a reads it (A-1-a) rows down.  Built once per IR.
 //
